@@ -1,0 +1,1 @@
+/* intentionally empty: unused include of the reference (oracle build only) */
