@@ -1,0 +1,83 @@
+/*
+ * lfm_b200.h -- extension C ABI of the B200 LFM engine (plain pointers and sizes; no CUDA or torch types).
+ * Everything the reference can only do through its C++ object (header knobs, src/klb_imageHeader.h:32-94; the
+ * compile-time predictor "way", src/common.h:19) plus memory-to-memory and device-resident entry points used for
+ * measurement. The file-based functions produce/consume exactly the .lfm layout of the reference
+ * (src/klb_imageHeader.cpp:164-196, src/klb_imageIO.cpp:1145-1225).
+ */
+#ifndef __LFM_B200_H__
+#define __LFM_B200_H__
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#include <stdint.h>
+#include "common.h"
+
+/* run-time replacement of the compile-time LFM_PREDICTOR_WAY (src/common.h:19): 0 tiles/both, 1 angle, 2 space.
+   The way is NOT stored in the file (reference defect): reader and writer must agree.
+   Initial value: environment LFM_PREDICTOR_WAY, else 0. Returns the previous value, -1 on a bad argument. */
+int lfmSetPredictorWay(int way);
+int lfmGetPredictorWay(void);
+
+/* number of GPUs the blocks are sharded over (default: environment LFM_B200_GPUS, else 1; clamped to the visible
+   devices). first_device: index of the first device used. Returns the count in effect. */
+int lfmSetDevices(int first_device, int count);
+
+/* writeKLBstack with the header knobs exposed (mirrors matlabWrapper/writeLFMstack.cpp:424-443 and
+   test/mainTest_lfmIO.cxx:60-97): headerVersion 0..7 = auto-select, 8+k = force predictor k, |0x80 = video stack. */
+int writeLFMstackEx(const void* im, const char* filename, const uint32_t xyzct[KLB_DATA_DIMS], enum KLB_DATA_TYPE dataType,
+                    int numThreads, const float32_t pixelSize[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS],
+                    enum KLB_COMPRESSION_TYPE compressionType, const char metadata[KLB_METADATA_SIZE],
+                    uint8_t headerVersion, uint8_t Nnum);
+
+/* header byte 0 / byte 1 of a file (stored predictor | video bit, Nnum); 0 ok */
+int readLFMheaderEx(const char* filename, uint8_t* headerVersion, uint8_t* Nnum);
+
+/* memory -> memory: the complete .lfm file image (header + blockOffset + payload) of a HOST stack into a malloc()ed
+   buffer the caller free()s. Same arguments as writeLFMstackEx. */
+int lfmCompressToMemory(const void* im, const uint32_t xyzct[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS],
+                        uint8_t headerVersion, uint8_t Nnum, void** file_bytes, uint64_t* file_size);
+/* inverse: decode a complete .lfm file image held in HOST memory into im (host, full stack) */
+int lfmDecompressFromMemory(const void* file_bytes, uint64_t file_size, void* im);
+
+/* device-resident entry points (one GPU, the current lfmSetDevices first device). d_im / d_out are CUDA device pointers.
+   lfmCompressDevice leaves the compacted block streams on the device; *d_payload stays valid until the next call.
+   blockOffset[Nb] (host) receives the inclusive prefix sum of the stream sizes = header.blockOffset[]. */
+int lfmCompressDevice(const void* d_im, const uint32_t xyzct[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS],
+                      uint8_t headerVersion, uint8_t Nnum, uint8_t* storedHeaderVersion, uint64_t* blockOffset,
+                      uint64_t numBlocks, const void** d_payload, uint64_t* payload_bytes);
+int lfmDecompressDevice(const void* d_payload, const uint64_t* blockOffset, uint64_t numBlocks,
+                        const uint32_t xyzct[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS],
+                        uint8_t storedHeaderVersion, uint8_t Nnum, void* d_out);
+
+/* number of KLB blocks for a stack (klb_imageHeader.cpp:77-85, after clamping blockSize to xyzct; NULL = default) */
+uint64_t lfmNumBlocks(const uint32_t xyzct[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS]);
+
+/* statistics of the last compress / decompress call on this thread's engine(s) */
+typedef struct {
+	int    predictor;         /* stored predictor 0..7 */
+	int    selected;          /* 1 if chosen by the 2-D entropy rule */
+	float  entropy[8];        /* candidate entropies when selected */
+	double ms_select, ms_predict, ms_rle, ms_bwt, ms_mtf, ms_huff;       /* kernel time per stage, CUDA events */
+	double ms_decode, ms_ibwt, ms_unrle, ms_unpredict;
+	double ms_h2d, ms_d2h, ms_total;
+	uint64_t gpu_launches;    /* kernels launched */
+	uint64_t periodic_blocks; /* exactly periodic bzip2 blocks met (origPtr tie rule applied) */
+	uint64_t payload_bytes;
+} lfm_stats;
+int lfmGetLastStats(lfm_stats* out);
+
+/* last error text of the library (thread-unsafe, diagnostic only) */
+const char* lfmLastError(void);
+
+/* test hook: per-stage intermediates of the block encoder for ONE host buffer treated as one KLB block of
+   n bytes (n even). Arrays must hold: rle1/bwt >= n*5/4+32 bytes, mtfv >= n*5/4+40 uint16, stream >= 2n+8300 bytes.
+   info[8] = { nblock, crc, origPtr, nInUse, nMTF, nGroups, nSelectors, streamBytes } */
+int lfmDebugEncodeBlock(const void* bytes, uint32_t n, uint8_t* rle1, uint8_t* bwt, uint16_t* mtfv, uint8_t* stream, uint32_t info[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

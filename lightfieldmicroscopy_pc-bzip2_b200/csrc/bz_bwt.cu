@@ -1,0 +1,176 @@
+// bz_bwt.cu -- Burrows-Wheeler transform of bzip2 blocks on sm_100a.
+//
+// Replaces BZ2_blockSort (src/external/bzip2-1.0.6/blocksort.c:1031-1090) as called from BZ2_compressBlock
+// (compress.c:603-619) under klb_imageIO::blockCompressor (src/klb_imageIO.cpp:217).  Contract: order the n cyclic
+// rotations of the post-RLE1 block, emit the last column and origPtr = rank of rotation 0.
+//
+// B200 design: ONE CTA per bzip2 block, persistent over the job list.  The whole block text (<= 184 KB for the
+// default 96x96x8 uint16 KLB block) lives in shared memory, so each of the 8 LSD radix passes over the 8-byte
+// rotation prefix only moves 4-byte rotation indices through L2 and fetches its digit from shared memory.
+// Rotations that still tie after 8 bytes are finished by prefix doubling (Larsson-Sadakane) restricted to the
+// unresolved set, with the same tile pass.  Exactly periodic blocks keep their ties; rotation 0 is placed last in
+// its group (what bzip2 does for the periods met in practice).
+#include "lfm_radix.cuh"
+
+namespace lfm {
+
+// scratch layout per CTA (uint32 arrays of `cap` elements each)
+enum { S_SA0 = 0, S_SA1, S_ISA, S_G0, S_G1, S_R0, S_R1, S_V0, S_V1, S_U0, S_U1, S_COUNT };
+
+extern __shared__ __align__(16) uint8_t bwt_smem[];
+
+__global__ void __launch_bounds__(BWT_NT, 1)
+k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jobs, uint32_t njobs,
+      uint8_t* __restrict__ bwt_all, uint32_t* __restrict__ scratch_all, int text_in_smem)
+{
+	uint32_t (*wcnt)[256] = reinterpret_cast<uint32_t (*)[256]>(bwt_smem);
+	uint32_t* base = reinterpret_cast<uint32_t*>(bwt_smem + BWT_NW * 256 * 4);
+	uint32_t* run  = base + 256;
+	uint32_t* red  = run + 256;          // 64
+	uint32_t* misc = red + 64;           // 16
+	uint8_t*  stext = reinterpret_cast<uint8_t*>(misc + 16);
+
+	uint32_t* scr = scratch_all + (size_t)blockIdx.x * S_COUNT * cap;
+	const uint32_t tid = threadIdx.x;
+
+	for (uint32_t job = blockIdx.x; job < njobs; job += gridDim.x) {
+		const uint32_t n = jobs[job].n;
+		const uint8_t* gtext = txt_all + (size_t)job * cap;
+		uint8_t* bwt = bwt_all + (size_t)job * cap;
+		if (n == 0) { if (tid == 0) { jobs[job].orig_ptr = 0; jobs[job].periodic = 0; } continue; }
+
+		// ---- phase 0: text -> shared (with 8 wrap-around bytes), byte histogram -> base[]
+		const uint8_t* text;
+		if (text_in_smem) {
+			for (uint32_t i = tid * 4; i < n; i += BWT_NT * 4) {
+				uint32_t wv = *reinterpret_cast<const uint32_t*>(gtext + i);   // cap is a multiple of 16: reading past n stays inside the job's slot
+				*reinterpret_cast<uint32_t*>(stext + i) = wv;
+			}
+			__syncthreads();
+			if (tid < 8) stext[n + tid] = stext[tid % n];
+			text = stext;
+		} else {
+			text = gtext;    // the slot keeps 8 wrap bytes after n (written by k_rle1)
+		}
+		__syncthreads();
+		digit_starts(n, base, wcnt, red, [&](uint32_t e) { return (uint32_t)text[e]; });
+
+		// ---- phase 1: 8 LSD passes over the 8-byte prefix (byte 7 first)
+		uint32_t* src = nullptr; uint32_t* dst = scr + (size_t)S_SA0 * cap;
+		for (int p = 7; p >= 0; p--) {
+			if (tid < 256) run[tid] = base[tid];
+			__syncthreads();
+			const uint32_t* s = src; uint32_t* d = dst;
+			radix_scatter<uint32_t>(n, run, wcnt,
+				[&](uint32_t e) { return s ? s[e] : e; },
+				[&](uint32_t idx) { return (uint32_t)text[idx + p]; },
+				[&](uint32_t pos, uint32_t idx) { d[pos] = idx; });
+			src = dst;
+			dst = (dst == scr + (size_t)S_SA0 * cap) ? scr + (size_t)S_SA1 * cap : scr + (size_t)S_SA0 * cap;
+		}
+		uint32_t* sa = src;                               // sorted by 8-byte prefix
+		uint32_t* isa = scr + (size_t)S_ISA * cap;
+
+		// ---- phase 2: group heads, ranks, unresolved set
+		uint32_t* G[2] = { scr + (size_t)S_G0 * cap, scr + (size_t)S_G1 * cap };
+		uint32_t* Rk[2] = { scr + (size_t)S_R0 * cap, scr + (size_t)S_R1 * cap };
+		uint32_t* V[2] = { scr + (size_t)S_V0 * cap, scr + (size_t)S_V1 * cap };
+		uint32_t* U[2] = { scr + (size_t)S_U0 * cap, scr + (size_t)S_U1 * cap };
+		uint32_t m = split_groups(n, red,
+			[&](uint32_t j) -> bool {                     // does rotation sa[j] differ from sa[j-1] within 8 bytes?
+				if (j == 0 || j >= n) return true;
+				uint32_t a = sa[j - 1], b = sa[j];
+				#pragma unroll
+				for (int k = 0; k < 8; k++) if (text[a + k] != text[b + k]) return true;
+				return false;
+			},
+			[&](uint32_t j) { return j; },
+			[&](uint32_t j, uint32_t head, bool un, uint32_t slot) {
+				uint32_t sfx = sa[j];
+				isa[sfx] = head;
+				if (un) { G[0][slot] = head; V[0][slot] = sfx; U[0][slot] = j; }
+			});
+
+		// ---- phase 3: prefix doubling on the unresolved set
+		const int npass = n <= (1u << 8) ? 1 : n <= (1u << 16) ? 2 : 3;
+		int cur = 0, ucur = 0;
+		uint64_t h = 8;
+		while (m > 0 && h < n) {
+			uint32_t hh = (uint32_t)h;
+			for (uint32_t e = tid; e < m; e += BWT_NT) {
+				uint32_t i = V[cur][e] + hh; if (i >= n) i -= n;     // hh < n
+				Rk[cur][e] = isa[i];
+			}
+			__syncthreads();
+			// LSD: secondary key (rank at distance h) first, then the group head
+			for (int key = 0; key < 2; key++) {
+				for (int ps = 0; ps < npass; ps++) {
+					const uint32_t* kg = G[cur]; const uint32_t* kr = Rk[cur]; const uint32_t* kv = V[cur];
+					uint32_t* og = G[cur ^ 1]; uint32_t* orr = Rk[cur ^ 1]; uint32_t* ov = V[cur ^ 1];
+					const int sh = ps * 8;
+					digit_starts(m, run, wcnt, red, [&](uint32_t e) { return ((key ? kg[e] : kr[e]) >> sh) & 255u; });
+					radix_scatter<Trip>(m, run, wcnt,
+						[&](uint32_t e) { Trip t; t.g = kg[e]; t.r = kr[e]; t.v = kv[e]; return t; },
+						[&](const Trip& t) { return ((key ? t.g : t.r) >> sh) & 255u; },
+						[&](uint32_t pos, const Trip& t) { og[pos] = t.g; orr[pos] = t.r; ov[pos] = t.v; });
+					cur ^= 1;
+				}
+			}
+			// U was not moved by the sort: sorted entry s belongs at suffix-array position U[ucur][s].
+			// Re-split the groups, update sa / isa, keep what is still unresolved.
+			{
+				const uint32_t* kg = G[cur]; const uint32_t* kr = Rk[cur]; const uint32_t* kv = V[cur];
+				const uint32_t* up = U[ucur];
+				uint32_t* ng = G[cur ^ 1]; uint32_t* nv = V[cur ^ 1]; uint32_t* nu = U[ucur ^ 1];
+				const uint32_t mm = m;
+				m = split_groups(mm, red,
+					[&](uint32_t s) -> bool { return s == 0 || s >= mm || kg[s] != kg[s - 1] || kr[s] != kr[s - 1]; },
+					[&](uint32_t s) { return up[s]; },
+					[&](uint32_t s, uint32_t head, bool un, uint32_t slot) {
+						uint32_t sfx = kv[s], pos = up[s];
+						sa[pos] = sfx;
+						isa[sfx] = head;
+						if (un) { ng[slot] = head; nv[slot] = sfx; nu[slot] = pos; }
+					});
+				cur ^= 1; ucur ^= 1;
+			}
+			__syncthreads();
+			h <<= 1;
+		}
+
+		// ---- phase 4: last column, origPtr (ties left <=> exactly periodic block: rotation 0 goes last in its group)
+		for (uint32_t j = tid; j < n; j += BWT_NT) {
+			uint32_t s = sa[j];
+			bwt[j] = text[s ? s - 1 : n - 1];
+			if (s == 0 && m == 0) jobs[job].orig_ptr = j;
+		}
+		if (m > 0) {
+			if (tid == 0) misc[1] = 0;
+			__syncthreads();
+			uint32_t g0 = isa[0], c = 0;
+			for (uint32_t e = tid; e < m; e += BWT_NT) c += (G[cur][e] == g0);
+			if (c) atomicAdd(&misc[1], c);
+			__syncthreads();
+			if (tid == 0) jobs[job].orig_ptr = g0 + misc[1] - 1;
+		}
+		if (tid == 0) jobs[job].periodic = m > 0;
+		__syncthreads();
+	}
+}
+
+size_t bwt_smem_bytes(uint32_t cap, int text_in_smem)
+{
+	size_t fixed = (size_t)BWT_NW * 256 * 4 + (256 + 256 + 64 + 16) * 4;
+	return fixed + (text_in_smem ? (size_t)cap + 16 : 0);
+}
+size_t bwt_scratch_elems_per_cta(uint32_t cap) { return (size_t)S_COUNT * cap; }
+
+void launch_bwt(const uint8_t* txt, uint32_t cap, EncJob* jobs, uint32_t njobs, uint8_t* bwt, uint32_t* scratch,
+                int grid, int text_in_smem, cudaStream_t st)
+{
+	size_t smem = bwt_smem_bytes(cap, text_in_smem);
+	cudaFuncSetAttribute(k_bwt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	k_bwt<<<grid, BWT_NT, smem, st>>>(txt, cap, jobs, njobs, bwt, scratch, text_in_smem);
+}
+
+}  // namespace lfm

@@ -1,0 +1,375 @@
+// engine.cu -- per-GPU pipeline driver (see engine.h). Host code; all arithmetic runs in the kernels.
+#include "engine.h"
+#include "kernels.h"
+#include <cstdio>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <memory>
+#include <algorithm>
+
+namespace lfm {
+
+struct Totals { unsigned long long running; uint32_t err; uint32_t periodic; uint32_t overflow; uint32_t pad; };
+
+// exclusive offsets of the batch's streams inside the payload (running base carried across batches)
+__global__ void k_offsets(const EncJob* __restrict__ jobs, uint32_t njobs, Totals* tot, uint64_t* __restrict__ offs,
+                          uint32_t* __restrict__ sizes, uint64_t payload_cap)
+{
+	__shared__ uint32_t red[64];
+	__shared__ unsigned long long s_base;
+	if (threadIdx.x == 0) s_base = tot->running;
+	__syncthreads();
+	uint32_t err = 0, per = 0;
+	for (uint32_t j0 = 0; j0 < njobs; j0 += 1024) {
+		uint32_t j = j0 + threadIdx.x;
+		uint32_t v = 0;
+		if (j < njobs) { v = jobs[j].out_bytes; err |= jobs[j].status; per += jobs[j].periodic; }
+		uint32_t total; uint32_t inc = block_scan_add<1024>(v, red, &total);
+		unsigned long long base = s_base;
+		if (j < njobs) { offs[j] = base + inc - v; sizes[j] = v; }
+		__syncthreads();
+		if (threadIdx.x == 0) s_base = base + total;
+		__syncthreads();
+	}
+	if (err) atomicOr(&tot->err, err);
+	if (per) atomicAdd(&tot->periodic, per);
+	__syncthreads();
+	if (threadIdx.x == 0) { tot->running = s_base; if (s_base > payload_cap) tot->overflow = 1; }
+}
+
+// copy each stream from its slot to its final place (byte granular; destination is unaligned by nature)
+__global__ void k_compact(const uint8_t* __restrict__ slots, uint32_t ocap, const uint64_t* __restrict__ offs,
+                          const uint32_t* __restrict__ sizes, uint8_t* __restrict__ payload, uint64_t payload_cap)
+{
+	const uint32_t job = blockIdx.x;
+	const uint32_t n = sizes[job];
+	const uint64_t o = offs[job];
+	if (o + n > payload_cap) return;
+	const uint8_t* src = slots + (size_t)job * ocap;
+	uint8_t* dst = payload + o;
+	// head bytes until dst is 4-aligned, then words assembled from the (4-aligned) source with a byte shift
+	uint32_t head = (uint32_t)((4 - (o & 3)) & 3); if (head > n) head = n;
+	if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+	const uint32_t nwords = (n - head) / 4;
+	const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+	uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + head);
+	const uint32_t sh = head * 8;
+	for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) {
+		uint32_t a = s32[i], b = s32[i + 1];
+		d32[i] = sh ? __funnelshift_r(a, b, sh) : a;
+	}
+	uint32_t done = head + nwords * 4;
+	if (threadIdx.x < n - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
+}
+
+__global__ void k_dec_status(const DecJob* __restrict__ jobs, uint32_t njobs, uint32_t* flag)
+{
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j < njobs && jobs[j].status) atomicOr(flag, 1u << min(jobs[j].status, 31u));
+}
+
+// ------------------------------------------------------------------------------------------------
+static std::mutex g_mu;
+static std::map<int, std::unique_ptr<Engine>> g_engines;
+
+Engine& Engine::for_device(int device)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	auto it = g_engines.find(device);
+	if (it == g_engines.end()) it = g_engines.emplace(device, std::unique_ptr<Engine>(new Engine(device))).first;
+	return *it->second;
+}
+
+Engine::Engine(int device) : device_(device)
+{
+	cudaSetDevice(device_);
+	cudaDeviceProp p;
+	if (cudaGetDeviceProperties(&p, device_) == cudaSuccess) sm_count_ = p.multiProcessorCount;
+	cudaStream_t st; cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+	stream_ = st;
+}
+
+int Engine::check(const char* what)
+{
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) {
+		err_ = std::string(what) + ": " + cudaGetErrorString(e);
+		fprintf(stderr, "lfm_b200: CUDA error in %s\n", err_.c_str());
+		return LFM_ERR_CUDA;
+	}
+	return LFM_OK;
+}
+
+int Engine::reserve(Buf& b, size_t bytes)
+{
+	if (b.cap >= bytes) return LFM_OK;
+	if (b.p) cudaFree(b.p);
+	b.p = nullptr; b.cap = 0;
+	size_t want = bytes + bytes / 8 + 256;
+	if (cudaMalloc(&b.p, want) != cudaSuccess) {
+		cudaGetLastError();
+		if (cudaMalloc(&b.p, bytes) != cudaSuccess) { err_ = "cudaMalloc failed"; cudaGetLastError(); return LFM_ERR_CUDA; }
+		want = bytes;
+	}
+	b.cap = want;
+	return LFM_OK;
+}
+
+static inline uint32_t round16(uint64_t v) { return (uint32_t)((v + 15) & ~(uint64_t)15); }
+
+static Geom make_geom(const StackDesc& s)
+{
+	Geom g;
+	uint64_t st = 1;
+	for (int i = 0; i < 5; i++) {
+		g.xyzct[i] = s.xyzct[i]; g.bs[i] = s.blockSize[i];
+		g.nb[i] = (uint32_t)std::ceil((float)s.xyzct[i] / (float)s.blockSize[i]);   // klb_imageHeader.cpp:77-85
+		g.stride[i] = st; st *= s.xyzct[i];
+	}
+	return g;
+}
+
+struct EncSizes { uint32_t cap, mcap, selcap, ocap; int level; int text_in_smem; bool single_block_ok; };
+static EncSizes enc_sizes(const StackDesc& s)
+{
+	EncSizes z;
+	uint64_t blockBytes = 2;
+	for (int i = 0; i < 5; i++) blockBytes *= s.blockSize[i];
+	z.level = (int)std::min<uint64_t>(9, (blockBytes + 99999) / 100000);     // klb_imageIO.cpp:108
+	uint64_t maxn = blockBytes + blockBytes / 4 + 1;                           // RLE1 worst case: 4 -> 5 bytes
+	z.single_block_ok = maxn < (uint64_t)(100000 * z.level - 19);
+	z.cap = round16(maxn + 8);
+	z.mcap = round16((uint64_t)z.cap + 2);
+	z.selcap = round16((uint64_t)z.mcap / kGSize + 2);
+	z.ocap = round16(maxn + maxn / 8 + maxn / 16 + 8192);
+	z.text_in_smem = bwt_smem_bytes(z.cap, 1) <= 227 * 1024;
+	return z;
+}
+
+// ------------------------------------------------------------------------------------------------ selection
+int Engine::select_mode(const uint16_t* d_frame0, const StackDesc& s, float entropy[8], int* winner)
+{
+	cudaSetDevice(device_);
+	cudaStream_t st = (cudaStream_t)stream_;
+	const int W = (int)s.xyzct[0], H = (int)s.xyzct[1];
+	const uint64_t fpx = (uint64_t)W * H;
+	const uint32_t chunk_px = 450000;                                          // klb_imageIO.cpp:2032
+	const uint32_t nchunks = (uint32_t)((fpx + chunk_px - 1) / chunk_px);
+	const uint32_t sstride = round16((uint64_t)chunk_px * 2 + 2);
+	int rc;
+	if ((rc = reserve(sel_cand_, 7 * fpx * 2))) return rc;
+	if ((rc = reserve(sel_sorted_, (size_t)8 * nchunks * sstride))) return rc;
+	if ((rc = reserve(sel_hist_, (size_t)8 * nchunks * 65536 * 4))) return rc;
+	if ((rc = reserve(sel_e_, (size_t)8 * nchunks * 4))) return rc;
+	const uint16_t* cands[8];
+	cands[0] = d_frame0;
+	for (int k = 1; k < 8; k++) {
+		uint16_t* c = (uint16_t*)sel_cand_.p + (size_t)(k - 1) * fpx;
+		launch_predict_fwd(d_frame0, c, W, H, s.Nnum, s.way, k, 0, 0, 1, st);
+		cands[k] = c;
+	}
+	launch_select(cands, 8, fpx, chunk_px, nchunks, (uint8_t*)sel_sorted_.p, sstride, (uint32_t*)sel_hist_.p, (float*)sel_e_.p, st);
+	std::vector<float> e((size_t)8 * nchunks);
+	cudaMemcpyAsync(e.data(), sel_e_.p, e.size() * 4, cudaMemcpyDeviceToHost, st);
+	cudaStreamSynchronize(st);
+	if ((rc = check("select_mode"))) return rc;
+	int best = 0;
+	for (int id = 0; id < 8; id++) {
+		float acc = 0.f;
+		for (uint32_t c = 0; c < nchunks; c++) acc += e[(size_t)id * nchunks + c];     // `*entropy += ...` per chunk
+		entropy[id] = id ? acc : (float)(acc * 0.96);                                  // klb_imageIO.cpp:2087-2090
+		if (id && entropy[id] <= entropy[best]) best = id;                             // std::map: equal keys -> last wins
+	}
+	*winner = best;
+	return LFM_OK;
+}
+
+int Engine::predict(const uint16_t* d_img, uint16_t* d_sym, const StackDesc& s, int predictor, int video, uint32_t z0, uint32_t nz)
+{
+	cudaSetDevice(device_);
+	if (predictor < 1 || predictor > 7 || s.way < 0 || s.way > 2) return LFM_ERR_UNSUPPORTED;
+	if (video && s.way != 0) return LFM_ERR_UNSUPPORTED;     // the reference's z!=0 angle/space kernels are not invertible
+	launch_predict_fwd(d_img, d_sym, (int)s.xyzct[0], (int)s.xyzct[1], s.Nnum, s.way, predictor, video, z0, nz, (cudaStream_t)stream_);
+	return check("predict");
+}
+
+int Engine::unpredict(const uint16_t* d_sym, uint16_t* d_out, const StackDesc& s, int predictor, int video, uint32_t z0, uint32_t nz)
+{
+	cudaSetDevice(device_);
+	if (predictor < 1 || predictor > 7 || s.way < 0 || s.way > 2) return LFM_ERR_UNSUPPORTED;
+	if (video && s.way != 0) return LFM_ERR_UNSUPPORTED;
+	cudaStream_t st = (cudaStream_t)stream_;
+	const int W = (int)s.xyzct[0], H = (int)s.xyzct[1];
+	if (!video) launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 0, z0, 1, nz, st);
+	else {
+		// odd frames need the decoded even frame before them: evens first, then odds (z0 must be even)
+		uint32_t first_even = z0 + (z0 & 1), first_odd = z0 + 1 - (z0 & 1);
+		uint32_t n_even = first_even < z0 + nz ? (z0 + nz - first_even + 1) / 2 : 0;
+		uint32_t n_odd = first_odd < z0 + nz ? (z0 + nz - first_odd + 1) / 2 : 0;
+		launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 1, first_even, 2, n_even, st);
+		launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 1, first_odd, 2, n_odd, st);
+	}
+	return check("unpredict");
+}
+
+// ------------------------------------------------------------------------------------------------ compress
+int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t first, uint64_t count,
+                            uint32_t* sizes_out, const uint8_t** d_payload, uint64_t* payload_bytes, CompressStats* stt)
+{
+	cudaSetDevice(device_);
+	cudaStream_t st = (cudaStream_t)stream_;
+	const Geom g = make_geom(s);
+	const EncSizes z = enc_sizes(s);
+	if (!z.single_block_ok) {
+		err_ = "block size needs multi-block bzip2 streams (not implemented): keep blockBytes*1.25 < 100000*level-19";
+		return LFM_ERR_UNSUPPORTED;
+	}
+	if (count == 0) { *d_payload = nullptr; *payload_bytes = 0; return LFM_OK; }
+	const size_t per_job = (size_t)z.cap * 2 + (size_t)z.mcap * 2 + z.selcap + z.ocap + sizeof(EncJob);
+	uint64_t B = std::min<uint64_t>(count, std::max<uint64_t>(1, ((size_t)6 << 30) / per_job));
+	B = std::min<uint64_t>(B, 16384);
+	const int grid = (int)std::min<uint64_t>(B, (uint64_t)sm_count_);
+	uint64_t blockBytes = 2; for (int i = 0; i < 5; i++) blockBytes *= s.blockSize[i];
+	uint64_t pcap = std::min<uint64_t>(count * (uint64_t)z.ocap, count * blockBytes + count * blockBytes / 3 + count * 1024 + (1 << 20));
+	int rc;
+	if ((rc = reserve(jobs_, B * sizeof(EncJob)))) return rc;
+	if ((rc = reserve(txt_, B * z.cap))) return rc;
+	if ((rc = reserve(bwt_, B * z.cap))) return rc;
+	if ((rc = reserve(mtfv_, B * (size_t)z.mcap * 2))) return rc;
+	if ((rc = reserve(sel_, B * z.selcap))) return rc;
+	if ((rc = reserve(out_, B * (size_t)z.ocap + 16))) return rc;
+	if ((rc = reserve(scratch_, (size_t)grid * bwt_scratch_elems_per_cta(z.cap) * 4))) return rc;
+	if ((rc = reserve(payload_, pcap + 16))) return rc;
+	if ((rc = reserve(sizes_, count * 4))) return rc;
+	if ((rc = reserve(offs_, B * 8 + sizeof(Totals)))) return rc;
+	Totals* tot = (Totals*)((uint8_t*)offs_.p + B * 8);
+	cudaMemsetAsync(tot, 0, sizeof(Totals), st);
+
+	std::vector<cudaEvent_t> evs;
+	auto mark = [&]() { if (stt) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); evs.push_back(e); } };
+	uint64_t launches = 0;
+	for (uint64_t b0 = 0; b0 < count; b0 += B) {
+		const uint32_t nj = (uint32_t)std::min<uint64_t>(B, count - b0);
+		mark();
+		launch_rle1(d_sym, g, first + b0, nj, (uint8_t*)txt_.p, z.cap, (EncJob*)jobs_.p, st);
+		mark();
+		launch_bwt((uint8_t*)txt_.p, z.cap, (EncJob*)jobs_.p, nj, (uint8_t*)bwt_.p, (uint32_t*)scratch_.p,
+		           (int)std::min<uint32_t>(nj, (uint32_t)grid), z.text_in_smem, st);
+		mark();
+		launch_mtf((uint8_t*)bwt_.p, z.cap, (EncJob*)jobs_.p, nj, (uint16_t*)mtfv_.p, z.mcap, st);
+		mark();
+		launch_huff_pack((uint16_t*)mtfv_.p, z.mcap, (EncJob*)jobs_.p, nj, (uint8_t*)sel_.p, z.selcap, (uint8_t*)out_.p, z.ocap, z.level, st);
+		k_offsets<<<1, 1024, 0, st>>>((EncJob*)jobs_.p, nj, tot, (uint64_t*)offs_.p, (uint32_t*)sizes_.p + b0, pcap);
+		k_compact<<<nj, 256, 0, st>>>((uint8_t*)out_.p, z.ocap, (uint64_t*)offs_.p, (uint32_t*)sizes_.p + b0, (uint8_t*)payload_.p, pcap);
+		mark();
+		launches += 6;
+		last_njobs_ = nj;
+	}
+	last_cap_ = z.cap; last_mcap_ = z.mcap;
+	Totals h;
+	cudaMemcpyAsync(&h, tot, sizeof(Totals), cudaMemcpyDeviceToHost, st);
+	cudaMemcpyAsync(sizes_out, sizes_.p, count * 4, cudaMemcpyDeviceToHost, st);
+	cudaStreamSynchronize(st);
+	if ((rc = check("compress_blocks"))) return rc;
+	if (stt) {
+		for (size_t i = 0; i + 4 < evs.size(); i += 5) {
+			float ms;
+			cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); stt->ms_rle += ms;
+			cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]); stt->ms_bwt += ms;
+			cudaEventElapsedTime(&ms, evs[i + 2], evs[i + 3]); stt->ms_mtf += ms;
+			cudaEventElapsedTime(&ms, evs[i + 3], evs[i + 4]); stt->ms_huff += ms;
+		}
+		for (auto e : evs) cudaEventDestroy(e);
+		stt->launches += launches;
+		stt->periodic_blocks += h.periodic;
+	}
+	if (h.overflow) { err_ = "payload buffer overflow"; return LFM_ERR_BZIP; }
+	if (h.err) { err_ = "block encoder reported an error"; return LFM_ERR_BZIP; }
+	*d_payload = (const uint8_t*)payload_.p;
+	*payload_bytes = h.running;
+	return LFM_OK;
+}
+
+int Engine::fetch_encode_trace(EncodeTrace& t)
+{
+	cudaSetDevice(device_);
+	cudaStream_t st = (cudaStream_t)stream_;
+	t.cap = last_cap_; t.mcap = last_mcap_; t.njobs = last_njobs_;
+	t.jobs.resize((size_t)t.njobs * sizeof(EncJob));
+	t.txt.resize((size_t)t.njobs * t.cap); t.bwt.resize((size_t)t.njobs * t.cap); t.mtfv.resize((size_t)t.njobs * t.mcap);
+	cudaMemcpyAsync(t.jobs.data(), jobs_.p, t.jobs.size(), cudaMemcpyDeviceToHost, st);
+	cudaMemcpyAsync(t.txt.data(), txt_.p, t.txt.size(), cudaMemcpyDeviceToHost, st);
+	cudaMemcpyAsync(t.bwt.data(), bwt_.p, t.bwt.size(), cudaMemcpyDeviceToHost, st);
+	cudaMemcpyAsync(t.mtfv.data(), mtfv_.p, t.mtfv.size() * 2, cudaMemcpyDeviceToHost, st);
+	cudaStreamSynchronize(st);
+	return check("fetch_encode_trace");
+}
+
+// ------------------------------------------------------------------------------------------------ decompress
+int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, const uint64_t* end, const uint64_t* block_ids,
+                              uint64_t count, uint16_t* d_sym, const StackDesc& s, DecompressStats* stt)
+{
+	cudaSetDevice(device_);
+	cudaStream_t st = (cudaStream_t)stream_;
+	if (count == 0) return LFM_OK;
+	const Geom g = make_geom(s);
+	const EncSizes z = enc_sizes(s);
+	if (!z.single_block_ok) { err_ = "block size needs multi-block bzip2 streams (not implemented)"; return LFM_ERR_UNSUPPORTED; }
+	const size_t per_job = (size_t)z.cap * 2 + z.selcap + sizeof(DecJob) + 24;
+	uint64_t B = std::min<uint64_t>(count, std::max<uint64_t>(1, ((size_t)6 << 30) / per_job));
+	B = std::min<uint64_t>(B, 32768);
+	const int grid = (int)std::min<uint64_t>(B, (uint64_t)sm_count_);
+	int rc;
+	if ((rc = reserve(djobs_, B * sizeof(DecJob) + 16))) return rc;
+	if ((rc = reserve(bwt_, B * z.cap))) return rc;
+	if ((rc = reserve(txt_, B * z.cap))) return rc;
+	if ((rc = reserve(sel_, B * z.selcap))) return rc;
+	if ((rc = reserve(tt_, inv_bwt_scratch_elems(grid, z.cap) * 4))) return rc;
+	if ((rc = reserve(dbegin_, count * 8))) return rc;
+	if ((rc = reserve(dend_, count * 8))) return rc;
+	if ((rc = reserve(dids_, count * 8))) return rc;
+	uint32_t* flag = (uint32_t*)((uint8_t*)djobs_.p + B * sizeof(DecJob));
+	cudaMemsetAsync(flag, 0, 4, st);
+	cudaMemcpyAsync(dbegin_.p, begin, count * 8, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(dend_.p, end, count * 8, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(dids_.p, block_ids, count * 8, cudaMemcpyHostToDevice, st);
+	std::vector<cudaEvent_t> evs;
+	auto mark = [&]() { if (stt) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); evs.push_back(e); } };
+	uint64_t launches = 0;
+	for (uint64_t b0 = 0; b0 < count; b0 += B) {
+		const uint32_t nj = (uint32_t)std::min<uint64_t>(B, count - b0);
+		mark();
+		launch_decode(d_payload, (uint64_t*)dbegin_.p + b0, (uint64_t*)dend_.p + b0, nj, (DecJob*)djobs_.p, (uint8_t*)bwt_.p, z.cap,
+		              (uint8_t*)sel_.p, z.selcap, st);
+		mark();
+		launch_inv_bwt((uint8_t*)bwt_.p, z.cap, (DecJob*)djobs_.p, nj, (uint32_t*)tt_.p, (uint8_t*)txt_.p,
+		               (int)std::min<uint32_t>(nj, (uint32_t)grid), st);
+		mark();
+		launch_unrle((uint8_t*)txt_.p, z.cap, (DecJob*)djobs_.p, nj, d_sym, g, (uint64_t*)dids_.p + b0, st);
+		k_dec_status<<<(nj + 255) / 256, 256, 0, st>>>((DecJob*)djobs_.p, nj, flag);
+		mark();
+		launches += 4;
+	}
+	uint32_t hflag = 0;
+	cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st);
+	cudaStreamSynchronize(st);
+	if ((rc = check("decompress_blocks"))) return rc;
+	if (stt) {
+		for (size_t i = 0; i + 3 < evs.size(); i += 4) {
+			float ms;
+			cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); stt->ms_decode += ms;
+			cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]); stt->ms_ibwt += ms;
+			cudaEventElapsedTime(&ms, evs[i + 2], evs[i + 3]); stt->ms_unrle += ms;
+		}
+		for (auto e : evs) cudaEventDestroy(e);
+		stt->launches += launches;
+	}
+	if (hflag) {
+		char m[96]; snprintf(m, sizeof(m), "block decoder status mask 0x%x", hflag); err_ = m;
+		return (hflag & (1u << 4)) ? LFM_ERR_UNSUPPORTED : LFM_ERR_BZIP;
+	}
+	return LFM_OK;
+}
+
+}  // namespace lfm

@@ -1,0 +1,35 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (definitions in the .cu files named beside each).
+#pragma once
+#include "lfm_device.cuh"
+
+namespace lfm {
+
+// lfm_predict.cu
+void launch_predict_fwd(const uint16_t* img, uint16_t* sym, int W, int H, int T, int way, int k, int video,
+                        uint32_t z0, uint32_t nz, cudaStream_t st);
+void launch_unpredict(const uint16_t* sym, uint16_t* out, int W, int H, int T, int way, int k, int video,
+                      uint32_t z_start, uint32_t z_step, uint32_t count, cudaStream_t st);
+// lfm_select.cu
+void launch_select(const uint16_t* const cand_ptrs[8], int ncand, uint64_t fpx, uint32_t chunk_px, uint32_t nchunks,
+                   uint8_t* sorted, uint32_t sstride, uint32_t* hist, float* e_out, cudaStream_t st);
+// bz_encode.cu
+void launch_rle1(const uint16_t* sym, const Geom& g, uint64_t first_block, uint32_t njobs, uint8_t* txt, uint32_t cap,
+                 EncJob* jobs, cudaStream_t st);
+void launch_mtf(const uint8_t* bwt, uint32_t cap, EncJob* jobs, uint32_t njobs, uint16_t* mtfv, uint32_t mcap, cudaStream_t st);
+void launch_huff_pack(const uint16_t* mtfv, uint32_t mcap, EncJob* jobs, uint32_t njobs, uint8_t* sel, uint32_t selcap,
+                      uint8_t* out, uint32_t ocap, int level, cudaStream_t st);
+// bz_bwt.cu
+size_t bwt_smem_bytes(uint32_t cap, int text_in_smem);
+size_t bwt_scratch_elems_per_cta(uint32_t cap);
+void launch_bwt(const uint8_t* txt, uint32_t cap, EncJob* jobs, uint32_t njobs, uint8_t* bwt, uint32_t* scratch,
+                int grid, int text_in_smem, cudaStream_t st);
+// bz_decode.cu
+void launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t* end, uint32_t njobs, DecJob* jobs,
+                   uint8_t* bwt, uint32_t cap, uint8_t* sel, uint32_t selcap, cudaStream_t st);
+size_t inv_bwt_scratch_elems(int grid, uint32_t cap);
+void launch_inv_bwt(const uint8_t* bwt, uint32_t cap, DecJob* jobs, uint32_t njobs, uint32_t* tt_scratch, uint8_t* txt,
+                    int grid, cudaStream_t st);
+void launch_unrle(const uint8_t* txt, uint32_t cap, DecJob* jobs, uint32_t njobs, uint16_t* sym, const Geom& g,
+                  const uint64_t* block_ids, cudaStream_t st);
+
+}  // namespace lfm

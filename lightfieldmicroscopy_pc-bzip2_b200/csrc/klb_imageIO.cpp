@@ -1,0 +1,643 @@
+// klb_imageIO.cpp -- host orchestration of the .lfm compress / decompress path on B200 GPUs.
+//
+// Mirrors the observable behaviour of the reference's klb_imageIO::writeImage / readImage / readImageFull
+// (src/klb_imageIO.cpp:2248-2492, :2614-2782): same header handling, same predictor request rules, same block
+// partition and blockOffset table, same return codes.  What differs is where the work runs:
+//   * predictor, mode selection and the whole bzip2 block codec run as CUDA kernels (csrc/*.cu) instead of
+//     CUDA predictor + std::thread bzip2;
+//   * KLB blocks are sharded over the configured GPUs by contiguous z-slabs (block ids are x fastest, so a slab is a
+//     contiguous block-id range and a contiguous payload range); no collective on the data path -- the host does the
+//     inclusive prefix sum of the block sizes that becomes header.blockOffset[] (cf. blockWriter, :1145-1225);
+//   * there is no CPU fallback: without a CUDA device every call fails with code 6.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include <cuda_runtime.h>
+#include "klb_imageIO.h"
+#include "lfm_b200.h"
+#include "engine.h"
+
+using namespace lfm;
+
+// ------------------------------------------------------------------------------------------------ settings / stats
+namespace {
+struct Settings {
+	int way = -1;            // -1: not initialised yet
+	int first_device = 0;
+	int ndev = -1;
+} g_set;
+lfm_stats g_stats;
+std::string g_err;
+
+int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+int current_way() { if (g_set.way < 0) { int w = env_int("LFM_PREDICTOR_WAY", LFM_PREDICTOR_WAY_DEFAULT); g_set.way = (w >= 0 && w <= 2) ? w : 0; } return g_set.way; }
+int visible_devices() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+int current_ndev()
+{
+	if (g_set.ndev < 0) g_set.ndev = std::max(1, env_int("LFM_B200_GPUS", 1));
+	int vis = visible_devices();
+	return std::max(0, std::min(g_set.ndev, vis - g_set.first_device));
+}
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct FrameSource {              // contiguous stack or one pointer per XY slice
+	const uint16_t* base = nullptr;
+	const uint16_t* const* slices = nullptr;
+	const uint16_t* frame(uint64_t f, uint64_t fpx) const { return slices ? slices[f] : base + f * fpx; }
+};
+
+struct Layout {                   // derived block / frame geometry
+	uint32_t nb[5];
+	uint64_t Nb, blocksPerSlab, nSlabs, F, fpx;
+};
+Layout make_layout(const klb_image_header& h)
+{
+	Layout L;
+	L.Nb = 1;
+	for (int d = 0; d < 5; d++) { L.nb[d] = (uint32_t)std::ceil((float)h.xyzct[d] / (float)h.blockSize[d]); L.Nb *= L.nb[d]; }
+	L.blocksPerSlab = (uint64_t)L.nb[0] * L.nb[1];
+	L.nSlabs = (uint64_t)L.nb[2] * L.nb[3] * L.nb[4];
+	L.F = (uint64_t)h.xyzct[2] * h.xyzct[3] * h.xyzct[4];
+	L.fpx = (uint64_t)h.xyzct[0] * h.xyzct[1];
+	return L;
+}
+// flattened frame range [f0, f1] touched by slabs [s0, s1)
+void slab_frames(const klb_image_header& h, const Layout& L, uint64_t s0, uint64_t s1, uint64_t& f0, uint64_t& f1)
+{
+	f0 = ~0ull; f1 = 0;
+	for (uint64_t s = s0; s < s1; s++) {
+		uint64_t bz = s % L.nb[2], r = s / L.nb[2], bc = r % L.nb[3], bt = r / L.nb[3];
+		uint64_t z0 = bz * h.blockSize[2], z1 = std::min<uint64_t>(h.xyzct[2], z0 + h.blockSize[2]) - 1;
+		uint64_t c0 = bc * h.blockSize[3], c1 = std::min<uint64_t>(h.xyzct[3], c0 + h.blockSize[3]) - 1;
+		uint64_t t0 = bt * h.blockSize[4], t1 = std::min<uint64_t>(h.xyzct[4], t0 + h.blockSize[4]) - 1;
+		f0 = std::min(f0, z0 + h.xyzct[2] * (c0 + (uint64_t)h.xyzct[3] * t0));
+		f1 = std::max(f1, z1 + h.xyzct[2] * (c1 + (uint64_t)h.xyzct[3] * t1));
+	}
+}
+StackDesc make_desc(const klb_image_header& h, int way)
+{
+	StackDesc s;
+	for (int d = 0; d < 5; d++) { s.xyzct[d] = h.xyzct[d]; s.blockSize[d] = h.blockSize[d]; }
+	s.Nnum = h.Nnum ? h.Nnum : 1; s.way = way;
+	return s;
+}
+int validate(const klb_image_header& h, bool writing)
+{
+	if (h.compressionType != KLB_COMPRESSION_TYPE::BZIP2) {
+		if (h.compressionType == KLB_COMPRESSION_TYPE::NONE || h.compressionType == KLB_COMPRESSION_TYPE::ZLIB) {
+			std::cout << "ERROR: lfm_b200: only BZIP2 block compression is implemented by the GPU engine" << std::endl;
+			return LFM_ERR_UNSUPPORTED;
+		}
+		std::cout << "ERROR: workerfunc: compression type not implemented" << std::endl;
+		return writing ? LFM_ERR_CREATE : LFM_ERR_OPEN;
+	}
+	if (h.getBytesPerPixel() != 2) {
+		std::cout << "ERROR: lfm_b200: only 16-bit pixels are supported (the reference's predictor path reinterprets everything as uint16)" << std::endl;
+		return LFM_ERR_UNSUPPORTED;
+	}
+	for (int d = 0; d < 5; d++) if (h.xyzct[d] == 0 || h.blockSize[d] == 0) return LFM_ERR_BZIP;
+	return LFM_OK;
+}
+
+struct DevMem {                   // RAII device allocation
+	void* p = nullptr;
+	~DevMem() { if (p) cudaFree(p); }
+	int alloc(size_t n) { if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) { cudaGetLastError(); p = nullptr; return LFM_ERR_CUDA; } return 0; }
+};
+
+// ------------------------------------------------------------------------------------------------ compress core
+struct ShardOut { std::vector<uint8_t> payload; std::vector<uint32_t> sizes; int rc = 0; CompressStats st; double ms_h2d = 0, ms_d2h = 0; };
+
+int compress_core(const FrameSource& src, klb_image_header& h, std::vector<ShardOut>& shards, std::vector<uint64_t>& shardFirstBlock)
+{
+	memset(&g_stats, 0, sizeof(g_stats));
+	int rc = validate(h, true);
+	if (rc) return rc;
+	const int ndev = current_ndev();
+	if (ndev <= 0) { std::cout << "ERROR: lfm_b200: no CUDA device available (this engine has no CPU fallback)" << std::endl; return LFM_ERR_CUDA; }
+	const int way = current_way();
+	for (int d = 0; d < 5; d++) h.blockSize[d] = std::min(h.blockSize[d], h.xyzct[d]);     // src/klb_imageIO.cpp:2407-2408
+	const Layout L = make_layout(h);
+	h.resizeBlockOffset(L.Nb);
+	const StackDesc desc = make_desc(h, way);
+	const uint8_t hv_in = h.headerVersion;
+	const int video = (hv_in & 0x80) ? 1 : 0;
+	int k;
+	const double t_start = now_ms();
+	if ((hv_in & 0x7F) < NUM_PREDICTORS) {
+		// auto-select on frame 0 (branches A and B of writeImage, src/klb_imageIO.cpp:2273-2377)
+		Engine& e = Engine::for_device(g_set.first_device);
+		cudaSetDevice(e.device());
+		DevMem f0;
+		if (f0.alloc(L.fpx * 2)) return LFM_ERR_CUDA;
+		cudaMemcpy(f0.p, src.frame(0, L.fpx), L.fpx * 2, cudaMemcpyHostToDevice);
+		double t0 = now_ms();
+		rc = e.select_mode((const uint16_t*)f0.p, desc, g_stats.entropy, &k);
+		if (rc) { g_err = e.last_error(); return rc; }
+		g_stats.ms_select = now_ms() - t0;
+		g_stats.selected = 1; g_stats.gpu_launches += 7 + 3;
+	} else {
+		k = hv_in & 0x77 & 0x7F;                       // `hv & 0x7F - 8` parses as hv & 0x77 (src/klb_imageIO.cpp:2380)
+		if (k > 7) { std::cout << "ERROR: The predictors hava not selected!" << std::endl; return LFM_ERR_UNSUPPORTED; }
+	}
+	if (k != 0 && video && way != 0) {
+		std::cout << "ERROR: lfm_b200: video stacks are only invertible with predictor way 0 (tiles); refusing to write" << std::endl;
+		return LFM_ERR_UNSUPPORTED;
+	}
+	h.headerVersion = (uint8_t)((hv_in & 0x80) | k);
+	g_stats.predictor = k;
+
+	const int D = (int)std::min<uint64_t>((uint64_t)ndev, L.nSlabs);
+	shards.assign(D, ShardOut());
+	shardFirstBlock.assign(D, 0);
+	auto work = [&](int d) {
+		ShardOut& out = shards[d];
+		const uint64_t s0 = L.nSlabs * d / D, s1 = L.nSlabs * (d + 1) / D;
+		uint64_t f0, f1; slab_frames(h, L, s0, s1, f0, f1);
+		if (k != 0 && video && (f0 & 1)) f0--;              // an odd first frame is predicted from the even one before it
+		const uint64_t nf = f1 - f0 + 1;
+		Engine& e = Engine::for_device(g_set.first_device + d);
+		cudaSetDevice(e.device());
+		cudaStream_t st = (cudaStream_t)e.stream();
+		DevMem dimg, dsym;
+		if (dimg.alloc(nf * L.fpx * 2) || (k != 0 && dsym.alloc(nf * L.fpx * 2))) { out.rc = LFM_ERR_CUDA; return; }
+		double t0 = now_ms();
+		if (src.base) cudaMemcpyAsync(dimg.p, src.frame(f0, L.fpx), nf * L.fpx * 2, cudaMemcpyHostToDevice, st);
+		else for (uint64_t f = 0; f < nf; f++) cudaMemcpyAsync((uint16_t*)dimg.p + f * L.fpx, src.frame(f0 + f, L.fpx), L.fpx * 2, cudaMemcpyHostToDevice, st);
+		cudaStreamSynchronize(st);
+		out.ms_h2d = now_ms() - t0;
+		const uint16_t* img_base = (const uint16_t*)dimg.p - f0 * L.fpx;       // virtual base: absolute frame indexing
+		const uint16_t* sym_base = img_base;
+		if (k != 0) {
+			cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+			cudaEventRecord(a, st);
+			out.rc = e.predict(img_base, (uint16_t*)dsym.p - f0 * L.fpx, desc, k, video, (uint32_t)f0, (uint32_t)nf);
+			cudaEventRecord(b, st); cudaEventSynchronize(b);
+			float ms = 0; cudaEventElapsedTime(&ms, a, b); out.st.ms_predict = ms; out.st.launches++;
+			cudaEventDestroy(a); cudaEventDestroy(b);
+			if (out.rc) return;
+			sym_base = (const uint16_t*)dsym.p - f0 * L.fpx;
+		}
+		const uint64_t first = s0 * L.blocksPerSlab, count = (s1 - s0) * L.blocksPerSlab;
+		shardFirstBlock[d] = first;
+		out.sizes.resize(count);
+		const uint8_t* dpay = nullptr; uint64_t pbytes = 0;
+		out.rc = e.compress_blocks(sym_base, desc, first, count, out.sizes.data(), &dpay, &pbytes, &out.st);
+		if (out.rc) { g_err = e.last_error(); return; }
+		t0 = now_ms();
+		out.payload.resize(pbytes);
+		if (pbytes) cudaMemcpyAsync(out.payload.data(), dpay, pbytes, cudaMemcpyDeviceToHost, st);
+		cudaStreamSynchronize(st);
+		out.ms_d2h = now_ms() - t0;
+		if (cudaGetLastError() != cudaSuccess) out.rc = LFM_ERR_CUDA;
+	};
+	if (D == 1) work(0);
+	else {
+		std::vector<std::thread> th;
+		for (int d = 0; d < D; d++) th.emplace_back(work, d);
+		for (auto& t : th) t.join();
+	}
+	for (auto& s : shards) if (s.rc) return s.rc;
+	// host-side inclusive prefix sum of the block sizes -> blockOffset[] (END offsets)
+	uint64_t acc = 0;
+	for (int d = 0; d < D; d++) {
+		const ShardOut& s = shards[d];
+		for (size_t i = 0; i < s.sizes.size(); i++) { acc += s.sizes[i]; h.blockOffset[shardFirstBlock[d] + i] = acc; }
+		g_stats.ms_predict = std::max(g_stats.ms_predict, s.st.ms_predict);
+		g_stats.ms_rle = std::max(g_stats.ms_rle, s.st.ms_rle); g_stats.ms_bwt = std::max(g_stats.ms_bwt, s.st.ms_bwt);
+		g_stats.ms_mtf = std::max(g_stats.ms_mtf, s.st.ms_mtf); g_stats.ms_huff = std::max(g_stats.ms_huff, s.st.ms_huff);
+		g_stats.ms_h2d = std::max(g_stats.ms_h2d, s.ms_h2d); g_stats.ms_d2h = std::max(g_stats.ms_d2h, s.ms_d2h);
+		g_stats.gpu_launches += s.st.launches; g_stats.periodic_blocks += s.st.periodic_blocks;
+	}
+	g_stats.payload_bytes = acc;
+	g_stats.ms_total = now_ms() - t_start;
+	return LFM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ decompress core
+// payload: pointer to the first payload byte (after the blockOffset table) in HOST memory
+int decompress_core(const klb_image_header& h, const uint8_t* payload, uint64_t payload_size, uint16_t* out, const klb_ROI* roi)
+{
+	memset(&g_stats, 0, sizeof(g_stats));
+	int rc = validate(h, false);
+	if (rc) return rc;
+	const int ndev = current_ndev();
+	if (ndev <= 0) { std::cout << "ERROR: lfm_b200: no CUDA device available (this engine has no CPU fallback)" << std::endl; return LFM_ERR_CUDA; }
+	if (h.Nb == 0) { std::cerr << "ERROR: Image to read has not blocks" << std::endl; return LFM_ERR_BZIP; }
+	const int way = current_way();
+	const Layout L = make_layout(h);
+	if (L.Nb != h.Nb) return LFM_ERR_BZIP;
+	if (h.blockOffset[L.Nb - 1] > payload_size) { std::cerr << "ERROR: lfm_b200: file is truncated" << std::endl; return LFM_ERR_BZIP; }
+	const StackDesc desc = make_desc(h, way);
+	const int k = h.headerVersion & 0x7F, video = (h.headerVersion & 0x80) ? 1 : 0;
+	if (k > 7) return LFM_ERR_UNSUPPORTED;
+	if (k != 0 && video && way != 0) {
+		std::cout << "ERROR: lfm_b200: video stack written with predictor way != 0 cannot be inverted (reference defect, see DESIGN.md)" << std::endl;
+		return LFM_ERR_UNSUPPORTED;
+	}
+	const double t_start = now_ms();
+	g_stats.predictor = k;
+
+	// which slabs / blocks are needed
+	uint32_t lb[5], ub[5];
+	bool full = true;
+	for (int d = 0; d < 5; d++) {
+		lb[d] = roi ? roi->xyzctLB[d] : 0; ub[d] = roi ? roi->xyzctUB[d] : h.xyzct[d] - 1;
+		if (ub[d] >= h.xyzct[d] || lb[d] > ub[d]) return LFM_ERR_OPEN;
+		if (lb[d] != 0 || ub[d] != h.xyzct[d] - 1) full = false;
+	}
+	// slabs intersecting the ROI along z, c, t
+	std::vector<uint64_t> slabs;
+	for (uint64_t s = 0; s < L.nSlabs; s++) {
+		uint64_t bz = s % L.nb[2], r = s / L.nb[2], bc = r % L.nb[3], bt = r / L.nb[3];
+		auto hit = [&](int d, uint64_t b) { uint64_t a0 = b * h.blockSize[d], a1 = std::min<uint64_t>(h.xyzct[d], a0 + h.blockSize[d]) - 1; return a0 <= ub[d] && a1 >= lb[d]; };
+		if (hit(2, bz) && hit(3, bc) && hit(4, bt)) slabs.push_back(s);
+	}
+	// video + predictor: an odd first frame needs the even frame before it -> also the slab that holds it
+	if (k != 0 && video && !slabs.empty()) {
+		uint64_t f0, f1; slab_frames(h, L, slabs.front(), slabs.front() + 1, f0, f1);
+		if ((f0 & 1) && slabs.front() > 0) slabs.insert(slabs.begin(), slabs.front() - 1);
+	}
+	const bool contiguous = !slabs.empty() && (slabs.back() - slabs.front() + 1 == slabs.size());
+	const int D = (full && contiguous) ? (int)std::min<uint64_t>((uint64_t)ndev, slabs.size()) : 1;
+
+	std::vector<int> rcs(D, 0);
+	std::vector<DecompressStats> sts(D);
+	std::vector<double> h2d(D, 0), d2h(D, 0);
+	auto work = [&](int d) {
+		// this shard's slabs
+		std::vector<uint64_t> my(slabs.begin() + slabs.size() * d / D, slabs.begin() + slabs.size() * (d + 1) / D);
+		if (my.empty()) return;
+		uint64_t f0 = ~0ull, f1 = 0;
+		for (uint64_t s : my) { uint64_t a, b; slab_frames(h, L, s, s + 1, a, b); f0 = std::min(f0, a); f1 = std::max(f1, b); }
+		if (k != 0 && video && (f0 & 1)) { rcs[d] = LFM_ERR_UNSUPPORTED; return; }   // odd block depth + video across shards
+		const uint64_t nf = f1 - f0 + 1;
+		// block list: all XY blocks of the slab when a predictor is in use (whole frames are needed), else only ROI hits
+		std::vector<uint64_t> ids, beg, end;
+		for (uint64_t s : my) for (uint64_t b = 0; b < L.blocksPerSlab; b++) {
+			if (k == 0 && !full) {
+				uint64_t bx = b % L.nb[0], by = b / L.nb[0];
+				uint64_t x0 = bx * h.blockSize[0], x1 = std::min<uint64_t>(h.xyzct[0], x0 + h.blockSize[0]) - 1;
+				uint64_t y0 = by * h.blockSize[1], y1 = std::min<uint64_t>(h.xyzct[1], y0 + h.blockSize[1]) - 1;
+				if (x0 > ub[0] || x1 < lb[0] || y0 > ub[1] || y1 < lb[1]) continue;
+			}
+			uint64_t id = s * L.blocksPerSlab + b;
+			ids.push_back(id); beg.push_back(id ? h.blockOffset[id - 1] : 0); end.push_back(h.blockOffset[id]);
+			if (end.back() < beg.back()) { rcs[d] = LFM_ERR_BZIP; return; }
+		}
+		const uint64_t p0 = beg.front(), p1 = end.back();      // ids ascend, so do the byte ranges
+		Engine& e = Engine::for_device(g_set.first_device + d);
+		cudaSetDevice(e.device());
+		cudaStream_t st = (cudaStream_t)e.stream();
+		DevMem dpay, dsym, dimg, droi;
+		if (dpay.alloc(p1 - p0 + 16) || dsym.alloc(nf * L.fpx * 2) || (k != 0 && dimg.alloc(nf * L.fpx * 2))) { rcs[d] = LFM_ERR_CUDA; return; }
+		double t0 = now_ms();
+		cudaMemcpyAsync(dpay.p, payload + p0, p1 - p0, cudaMemcpyHostToDevice, st);
+		if (k == 0 && !full) cudaMemsetAsync(dsym.p, 0, nf * L.fpx * 2, st);
+		cudaStreamSynchronize(st);
+		h2d[d] = now_ms() - t0;
+		for (size_t i = 0; i < beg.size(); i++) { beg[i] -= p0; end[i] -= p0; }
+		uint16_t* sym_base = (uint16_t*)dsym.p - f0 * L.fpx;
+		rcs[d] = e.decompress_blocks((const uint8_t*)dpay.p, beg.data(), end.data(), ids.data(), ids.size(), sym_base, desc, &sts[d]);
+		if (rcs[d]) { g_err = e.last_error(); return; }
+		const uint16_t* res_base = sym_base;
+		if (k != 0) {
+			cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+			cudaEventRecord(a, st);
+			rcs[d] = e.unpredict(sym_base, (uint16_t*)dimg.p - f0 * L.fpx, desc, k, video, (uint32_t)f0, (uint32_t)nf);
+			cudaEventRecord(b, st); cudaEventSynchronize(b);
+			float ms = 0; cudaEventElapsedTime(&ms, a, b); sts[d].ms_unpredict = ms; sts[d].launches += video ? 2 : 1;
+			cudaEventDestroy(a); cudaEventDestroy(b);
+			if (rcs[d]) return;
+			res_base = (const uint16_t*)dimg.p - f0 * L.fpx;
+		}
+		t0 = now_ms();
+		if (full) {
+			// this shard's frames, contiguous in the output
+			uint64_t a, b; slab_frames(h, L, my.front(), my.back() + 1, a, b);
+			cudaMemcpyAsync(out + a * L.fpx, res_base + a * L.fpx, (b - a + 1) * L.fpx * 2, cudaMemcpyDeviceToHost, st);
+		} else {
+			// crop: ROI rows are contiguous runs of (ub0-lb0+1) pixels
+			const uint64_t rx = ub[0] - lb[0] + 1, ry = ub[1] - lb[1] + 1;
+			uint64_t o = 0;
+			for (uint64_t t = lb[4]; t <= ub[4]; t++) for (uint64_t c = lb[3]; c <= ub[3]; c++) for (uint64_t z = lb[2]; z <= ub[2]; z++) {
+				uint64_t f = z + (uint64_t)h.xyzct[2] * (c + (uint64_t)h.xyzct[3] * t);
+				cudaMemcpy2DAsync(out + o, rx * 2, res_base + f * L.fpx + (uint64_t)lb[1] * h.xyzct[0] + lb[0], (size_t)h.xyzct[0] * 2,
+				                  rx * 2, ry, cudaMemcpyDeviceToHost, st);
+				o += rx * ry;
+			}
+		}
+		cudaStreamSynchronize(st);
+		d2h[d] = now_ms() - t0;
+		if (cudaGetLastError() != cudaSuccess) rcs[d] = LFM_ERR_CUDA;
+	};
+	if (D == 1) work(0);
+	else {
+		std::vector<std::thread> th;
+		for (int d = 0; d < D; d++) th.emplace_back(work, d);
+		for (auto& t : th) t.join();
+	}
+	for (int d = 0; d < D; d++) {
+		if (rcs[d]) return rcs[d];
+		g_stats.ms_decode = std::max(g_stats.ms_decode, sts[d].ms_decode); g_stats.ms_ibwt = std::max(g_stats.ms_ibwt, sts[d].ms_ibwt);
+		g_stats.ms_unrle = std::max(g_stats.ms_unrle, sts[d].ms_unrle); g_stats.ms_unpredict = std::max(g_stats.ms_unpredict, sts[d].ms_unpredict);
+		g_stats.ms_h2d = std::max(g_stats.ms_h2d, h2d[d]); g_stats.ms_d2h = std::max(g_stats.ms_d2h, d2h[d]);
+		g_stats.gpu_launches += sts[d].launches;
+	}
+	g_stats.ms_total = now_ms() - t_start;
+	return LFM_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ klb_imageIO
+klb_imageIO::klb_imageIO() { numThreads = (int)std::thread::hardware_concurrency(); }
+klb_imageIO::klb_imageIO(const std::string& filename_) : filename(filename_) { numThreads = (int)std::thread::hardware_concurrency(); }
+
+static int write_file(FILE* fout, klb_image_header& h, const std::vector<ShardOut>& shards)
+{
+	h.writeHeader(fout);
+	for (const auto& s : shards) if (!s.payload.empty() && fwrite(s.payload.data(), 1, s.payload.size(), fout) != s.payload.size()) return LFM_ERR_CREATE;
+	return LFM_OK;
+}
+
+int klb_imageIO::writeImage(const char* img, int /*numThreads*/)
+{
+	FILE* fout = fopen(filename.c_str(), "wb");
+	if (fout == NULL) { std::cout << "ERROR: file " << filename << " could not be opened" << std::endl; return LFM_ERR_CREATE; }
+	FrameSource src; src.base = (const uint16_t*)img;
+	std::vector<ShardOut> shards; std::vector<uint64_t> first;
+	int rc = compress_core(src, header, shards, first);
+	if (rc == 0) rc = write_file(fout, header, shards);
+	fclose(fout);
+	return rc;
+}
+
+int klb_imageIO::writeImageStackSlices(const char** img, int /*numThreads*/)
+{
+	if (header.xyzct[3] != 1 || header.xyzct[4] != 1) {
+		std::cout << "ERROR: writeImageStackSlices: number of channels or number of time points must be 1 for this API call" << std::endl;
+		return LFM_ERR_OPEN;
+	}
+	FILE* fout = fopen(filename.c_str(), "wb");
+	if (fout == NULL) { std::cout << "ERROR: file " << filename << " could not be opened" << std::endl; return LFM_ERR_CREATE; }
+	FrameSource src; src.slices = (const uint16_t* const*)img;
+	std::vector<ShardOut> shards; std::vector<uint64_t> first;
+	int rc = compress_core(src, header, shards, first);
+	if (rc == 0) rc = write_file(fout, header, shards);
+	fclose(fout);
+	return rc;
+}
+
+int klb_imageIO::writeImageToMemory(const char* img, std::string& fileBytes)
+{
+	FrameSource src; src.base = (const uint16_t*)img;
+	std::vector<ShardOut> shards; std::vector<uint64_t> first;
+	int rc = compress_core(src, header, shards, first);
+	if (rc) return rc;
+	uint8_t fixed[320]; header.packFixed(fixed);
+	fileBytes.assign((const char*)fixed, 320);
+	fileBytes.append((const char*)header.blockOffset, header.Nb * 8);
+	for (const auto& s : shards) fileBytes.append((const char*)s.payload.data(), s.payload.size());
+	return LFM_OK;
+}
+
+int klb_imageIO::readImageFromMemory(const char* fileBytes, size_t fileSize, char* imgOut, const klb_ROI* ROI)
+{
+	if (fileSize < 320) return LFM_ERR_BZIP;
+	header.unpackFixed((const uint8_t*)fileBytes);
+	for (int d = 0; d < 5; d++) if (header.blockSize[d] == 0) return LFM_ERR_BZIP;
+	header.resizeBlockOffset(header.calculateNumBlocks());
+	if (fileSize < 320 + header.Nb * 8) return LFM_ERR_BZIP;
+	memcpy(header.blockOffset, fileBytes + 320, header.Nb * 8);
+	return decompress_core(header, (const uint8_t*)fileBytes + 320 + header.Nb * 8, fileSize - 320 - header.Nb * 8, (uint16_t*)imgOut, ROI);
+}
+
+static int read_file(const std::string& filename, klb_image_header& header, std::vector<uint8_t>& payload)
+{
+	if (filename.empty()) { std::cerr << "ERROR: Filename has not been defined. We cannot read image" << std::endl; return LFM_ERR_OPEN; }
+	if (header.Nb == 0) {
+		int err = header.readHeader(filename.c_str());
+		if (err > 0) return err;
+		if (header.Nb == 0) { std::cerr << "ERROR: Image to read has not blocks" << std::endl; return LFM_ERR_BZIP; }
+	}
+	FILE* fid = fopen(filename.c_str(), "rb");
+	if (fid == NULL) { std::cout << "ERROR: blockUncompressor: thread opening file " << filename << std::endl; return LFM_ERR_OPEN; }
+	const uint64_t psize = header.blockOffset[header.Nb - 1];
+	payload.resize(psize);
+	fseek(fid, (long)header.getSizeInBytes(), SEEK_SET);
+	size_t got = fread(payload.data(), 1, psize, fid);
+	fclose(fid);
+	if (got != psize) { std::cerr << "ERROR: lfm_b200: file is truncated" << std::endl; return LFM_ERR_BZIP; }
+	return LFM_OK;
+}
+
+int klb_imageIO::readImageFull(char* imgOut, int /*numThreads*/)
+{
+	std::vector<uint8_t> payload;
+	int rc = read_file(filename, header, payload);
+	if (rc) return rc;
+	return decompress_core(header, payload.data(), payload.size(), (uint16_t*)imgOut, NULL);
+}
+
+int klb_imageIO::readImage(char* img, const klb_ROI* ROI, int /*numThreads*/)
+{
+	std::vector<uint8_t> payload;
+	int rc = read_file(filename, header, payload);
+	if (rc) return rc;
+	return decompress_core(header, payload.data(), payload.size(), (uint16_t*)img, ROI);
+}
+
+// ------------------------------------------------------------------------------------------------ extension C ABI
+extern "C" {
+
+int lfmSetPredictorWay(int way) { int prev = current_way(); if (way < 0 || way > 2) return -1; g_set.way = way; return prev; }
+int lfmGetPredictorWay(void) { return current_way(); }
+int lfmSetDevices(int first_device, int count)
+{
+	int vis = visible_devices();
+	if (first_device < 0) first_device = 0;
+	g_set.first_device = first_device;
+	g_set.ndev = std::max(1, count);
+	return std::max(0, std::min(g_set.ndev, vis - first_device));
+}
+
+int writeLFMstackEx(const void* im, const char* filename, const uint32_t xyzct[5], enum KLB_DATA_TYPE dataType, int numThreads,
+                    const float32_t pixelSize[5], const uint32_t blockSize[5], enum KLB_COMPRESSION_TYPE compressionType,
+                    const char metadata[256], uint8_t headerVersion, uint8_t Nnum)
+{
+	if (!filename || !*filename) return LFM_ERR_OPEN;
+	klb_imageIO io{ std::string(filename) };
+	io.header.setHeader(xyzct, dataType, pixelSize, blockSize, compressionType, metadata, headerVersion, Nnum);
+	return io.writeImage((const char*)im, numThreads);
+}
+
+int readLFMheaderEx(const char* filename, uint8_t* headerVersion, uint8_t* Nnum)
+{
+	klb_image_header h;
+	int err = h.readHeader(filename);
+	if (err) return err;
+	if (headerVersion) *headerVersion = h.headerVersion;
+	if (Nnum) *Nnum = h.Nnum;
+	return 0;
+}
+
+int lfmCompressToMemory(const void* im, const uint32_t xyzct[5], const uint32_t blockSize[5], uint8_t headerVersion, uint8_t Nnum,
+                        void** file_bytes, uint64_t* file_size)
+{
+	klb_imageIO io;
+	io.header.setHeader(xyzct, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize, KLB_COMPRESSION_TYPE::BZIP2, NULL, headerVersion, Nnum);
+	std::string bytes;
+	int rc = io.writeImageToMemory((const char*)im, bytes);
+	if (rc) return rc;
+	void* p = malloc(bytes.size() ? bytes.size() : 1);
+	if (!p) return LFM_ERR_CREATE;
+	memcpy(p, bytes.data(), bytes.size());
+	*file_bytes = p; *file_size = bytes.size();
+	return 0;
+}
+
+int lfmDecompressFromMemory(const void* file_bytes, uint64_t file_size, void* im)
+{
+	klb_imageIO io;
+	return io.readImageFromMemory((const char*)file_bytes, (size_t)file_size, (char*)im, NULL);
+}
+
+uint64_t lfmNumBlocks(const uint32_t xyzct[5], const uint32_t blockSize[5])
+{
+	klb_image_header h;
+	h.setHeader(xyzct, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize);
+	for (int d = 0; d < 5; d++) { if (h.xyzct[d] == 0) return 0; h.blockSize[d] = std::min(h.blockSize[d], h.xyzct[d]); }
+	return h.calculateNumBlocks();
+}
+
+int lfmCompressDevice(const void* d_im, const uint32_t xyzct[5], const uint32_t blockSize[5], uint8_t headerVersion, uint8_t Nnum,
+                      uint8_t* storedHeaderVersion, uint64_t* blockOffset, uint64_t numBlocks, const void** d_payload, uint64_t* payload_bytes)
+{
+	klb_image_header h;
+	h.setHeader(xyzct, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize, KLB_COMPRESSION_TYPE::BZIP2, NULL, headerVersion, Nnum);
+	int rc = validate(h, true);
+	if (rc) return rc;
+	if (current_ndev() <= 0) return LFM_ERR_CUDA;
+	for (int d = 0; d < 5; d++) h.blockSize[d] = std::min(h.blockSize[d], h.xyzct[d]);
+	const Layout L = make_layout(h);
+	if (numBlocks != L.Nb) return LFM_ERR_OPEN;
+	const int way = current_way();
+	const StackDesc desc = make_desc(h, way);
+	Engine& e = Engine::for_device(g_set.first_device);
+	cudaSetDevice(e.device());
+	memset(&g_stats, 0, sizeof(g_stats));
+	const int video = (headerVersion & 0x80) ? 1 : 0;
+	int k;
+	if ((headerVersion & 0x7F) < NUM_PREDICTORS) {
+		rc = e.select_mode((const uint16_t*)d_im, desc, g_stats.entropy, &k);
+		if (rc) return rc;
+		g_stats.selected = 1; g_stats.gpu_launches += 10;
+	} else { k = headerVersion & 0x77 & 0x7F; if (k > 7) return LFM_ERR_UNSUPPORTED; }
+	if (k != 0 && video && way != 0) return LFM_ERR_UNSUPPORTED;
+	if (storedHeaderVersion) *storedHeaderVersion = (uint8_t)((headerVersion & 0x80) | k);
+	g_stats.predictor = k;
+	static thread_local DevMem* symbuf = nullptr; static thread_local size_t symcap = 0;
+	const uint16_t* sym = (const uint16_t*)d_im;
+	CompressStats st;
+	if (k != 0) {
+		size_t need = L.F * L.fpx * 2;
+		if (!symbuf || symcap < need) { delete symbuf; symbuf = new DevMem(); if (symbuf->alloc(need)) { delete symbuf; symbuf = nullptr; symcap = 0; return LFM_ERR_CUDA; } symcap = need; }
+		rc = e.predict((const uint16_t*)d_im, (uint16_t*)symbuf->p, desc, k, video, 0, (uint32_t)L.F);
+		if (rc) return rc;
+		st.launches++;
+		sym = (const uint16_t*)symbuf->p;
+	}
+	std::vector<uint32_t> sizes(L.Nb);
+	const uint8_t* dpay = nullptr; uint64_t pb = 0;
+	rc = e.compress_blocks(sym, desc, 0, L.Nb, sizes.data(), &dpay, &pb, &st);
+	if (rc) { g_err = e.last_error(); return rc; }
+	uint64_t acc = 0;
+	for (uint64_t i = 0; i < L.Nb; i++) { acc += sizes[i]; blockOffset[i] = acc; }
+	*d_payload = dpay; *payload_bytes = pb;
+	g_stats.ms_rle = st.ms_rle; g_stats.ms_bwt = st.ms_bwt; g_stats.ms_mtf = st.ms_mtf; g_stats.ms_huff = st.ms_huff;
+	g_stats.gpu_launches += st.launches; g_stats.periodic_blocks = st.periodic_blocks; g_stats.payload_bytes = pb;
+	return 0;
+}
+
+int lfmDecompressDevice(const void* d_payload, const uint64_t* blockOffset, uint64_t numBlocks, const uint32_t xyzct[5],
+                        const uint32_t blockSize[5], uint8_t storedHeaderVersion, uint8_t Nnum, void* d_out)
+{
+	klb_image_header h;
+	h.setHeader(xyzct, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize, KLB_COMPRESSION_TYPE::BZIP2, NULL, storedHeaderVersion, Nnum);
+	int rc = validate(h, false);
+	if (rc) return rc;
+	if (current_ndev() <= 0) return LFM_ERR_CUDA;
+	for (int d = 0; d < 5; d++) h.blockSize[d] = std::min(h.blockSize[d], h.xyzct[d]);
+	const Layout L = make_layout(h);
+	if (numBlocks != L.Nb) return LFM_ERR_OPEN;
+	const int way = current_way();
+	const StackDesc desc = make_desc(h, way);
+	const int k = storedHeaderVersion & 0x7F, video = (storedHeaderVersion & 0x80) ? 1 : 0;
+	if (k > 7 || (k != 0 && video && way != 0)) return LFM_ERR_UNSUPPORTED;
+	Engine& e = Engine::for_device(g_set.first_device);
+	cudaSetDevice(e.device());
+	memset(&g_stats, 0, sizeof(g_stats));
+	std::vector<uint64_t> ids(L.Nb), beg(L.Nb), end(L.Nb);
+	for (uint64_t i = 0; i < L.Nb; i++) { ids[i] = i; beg[i] = i ? blockOffset[i - 1] : 0; end[i] = blockOffset[i]; }
+	static thread_local DevMem* symbuf = nullptr; static thread_local size_t symcap = 0;
+	uint16_t* sym = (uint16_t*)d_out;
+	if (k != 0) {
+		size_t need = L.F * L.fpx * 2;
+		if (!symbuf || symcap < need) { delete symbuf; symbuf = new DevMem(); if (symbuf->alloc(need)) { delete symbuf; symbuf = nullptr; symcap = 0; return LFM_ERR_CUDA; } symcap = need; }
+		sym = (uint16_t*)symbuf->p;
+	}
+	DecompressStats st;
+	rc = e.decompress_blocks((const uint8_t*)d_payload, beg.data(), end.data(), ids.data(), L.Nb, sym, desc, &st);
+	if (rc) { g_err = e.last_error(); return rc; }
+	if (k != 0) {
+		rc = e.unpredict(sym, (uint16_t*)d_out, desc, k, video, 0, (uint32_t)L.F);
+		if (rc) return rc;
+		st.launches += video ? 2 : 1;
+		cudaStreamSynchronize((cudaStream_t)e.stream());
+		if (cudaGetLastError() != cudaSuccess) return LFM_ERR_CUDA;
+	}
+	g_stats.predictor = k;
+	g_stats.ms_decode = st.ms_decode; g_stats.ms_ibwt = st.ms_ibwt; g_stats.ms_unrle = st.ms_unrle;
+	g_stats.gpu_launches = st.launches;
+	return 0;
+}
+
+int lfmGetLastStats(lfm_stats* out) { if (!out) return 1; *out = g_stats; return 0; }
+const char* lfmLastError(void) { return g_err.c_str(); }
+
+int lfmDebugEncodeBlock(const void* bytes, uint32_t n, uint8_t* rle1, uint8_t* bwt, uint16_t* mtfv, uint8_t* stream, uint32_t info[8])
+{
+	if (n == 0 || (n & 1)) return LFM_ERR_OPEN;
+	if (current_ndev() <= 0) return LFM_ERR_CUDA;
+	Engine& e = Engine::for_device(g_set.first_device);
+	cudaSetDevice(e.device());
+	StackDesc s;
+	const uint32_t xyzct[5] = { n / 2, 1, 1, 1, 1 };
+	for (int d = 0; d < 5; d++) { s.xyzct[d] = xyzct[d]; s.blockSize[d] = xyzct[d]; }
+	s.Nnum = 13; s.way = 0;
+	DevMem dimg;
+	if (dimg.alloc(n)) return LFM_ERR_CUDA;
+	cudaMemcpy(dimg.p, bytes, n, cudaMemcpyHostToDevice);
+	uint32_t size = 0; const uint8_t* dpay = nullptr; uint64_t pb = 0;
+	int rc = e.compress_blocks((const uint16_t*)dimg.p, s, 0, 1, &size, &dpay, &pb, nullptr);
+	if (rc) { g_err = e.last_error(); return rc; }
+	Engine::EncodeTrace t;
+	rc = e.fetch_encode_trace(t);
+	if (rc) return rc;
+	const uint32_t* J = (const uint32_t*)t.jobs.data();   // EncJob fields in declaration order
+	const uint32_t nblock = J[1];
+	memcpy(rle1, t.txt.data(), nblock); memcpy(bwt, t.bwt.data(), nblock);
+	memcpy(mtfv, t.mtfv.data(), (size_t)J[4] * 2);
+	cudaMemcpy(stream, dpay, pb, cudaMemcpyDeviceToHost);
+	info[0] = nblock; info[1] = J[2]; info[2] = J[3]; info[3] = J[5]; info[4] = J[4]; info[5] = J[6]; info[6] = J[7]; info[7] = (uint32_t)pb;
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// Shared device-side definitions for the B200 LFM engine (sm_100a).
+// Data layout in HBM (see DESIGN.md "Data layout"):
+//   image / symbol image : uint16 [frames][H][W], x fastest (the caller's layout, klb_imageIO.cpp:133-183)
+//   per KLB-block ("job") working arrays are strided by `cap` = max post-RLE1 length rounded to 16
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lfm {
+
+constexpr int kMaxAlpha = 258;
+constexpr int kGroups   = 6;
+constexpr int kGSize    = 50;
+constexpr int kMaxSel   = 18002;     // compress.c:456 (2 + 900000/50)
+
+// geometry of the KLB block grid (klb_imageIO.cpp:97-183)
+struct Geom {
+	uint32_t xyzct[5];
+	uint32_t bs[5];
+	uint32_t nb[5];
+	uint64_t stride[5];   // in pixels
+};
+
+// one KLB block = one bzip2 stream; in this version exactly one bzip2 block per stream
+struct EncJob {
+	uint32_t raw_bytes;    // bytes gathered from the image (gcount, klb_imageIO.cpp:146-151)
+	uint32_t n;            // post-RLE1 length (nblock)
+	uint32_t crc;          // block CRC over the pre-RLE bytes
+	uint32_t orig_ptr;
+	uint32_t n_mtf;
+	uint32_t n_in_use;
+	uint32_t n_groups;
+	uint32_t n_sel;
+	uint32_t total_bits;   // bits of the whole stream before byte padding
+	uint32_t out_bytes;    // stream size
+	uint32_t periodic;
+	uint32_t status;       // 0 ok
+	uint32_t in_use[8];    // 256-bit map
+};
+
+struct DecJob {
+	uint32_t n;            // post-RLE1 length of the bzip2 block
+	uint32_t orig_ptr;
+	uint32_t stored_crc;
+	uint32_t out_bytes;    // bytes produced by un-RLE1
+	uint32_t status;       // 0 ok, 1 bad magic, 2 corrupt, 3 crc mismatch, 4 unsupported (multi-block / randomised)
+	uint32_t level;
+	uint32_t cftab[257];
+};
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
+
+// block coordinates of KLB block `id`: origin c0[5] and clamped extent ext[5]
+__device__ __forceinline__ void block_box(const Geom& g, uint64_t id, uint32_t c0[5], uint32_t ext[5])
+{
+	#pragma unroll
+	for (int i = 0; i < 5; i++) {
+		uint32_t c = (uint32_t)(id % g.nb[i]); id /= g.nb[i];
+		c0[i] = c * g.bs[i];
+		uint32_t rem = g.xyzct[i] - c0[i];
+		ext[i] = rem < g.bs[i] ? rem : g.bs[i];
+	}
+}
+
+// ---- block-wide scans over one value per thread; `red` is a shared array of >= 33 uint32_t ----
+// returns the inclusive scan; *total = sum over the block. Contains __syncthreads: call from all threads.
+template <int NT>
+__device__ __forceinline__ uint32_t block_scan_add(uint32_t v, uint32_t* red, uint32_t* total)
+{
+	uint32_t lane = lane_id(), w = warp_id();
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+	__syncthreads();
+	if (lane == 31) red[w] = v;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t s = lane < NT / 32 ? red[lane] : 0;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+		red[lane] = s;
+	}
+	__syncthreads();
+	uint32_t off = w ? red[w - 1] : 0;
+	*total = red[NT / 32 - 1];
+	return v + off;
+}
+template <int NT>
+__device__ __forceinline__ uint32_t block_scan_max(uint32_t v, uint32_t* red)
+{
+	uint32_t lane = lane_id(), w = warp_id();
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = max(v, t); }
+	__syncthreads();
+	if (lane == 31) red[w] = v;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t s = lane < NT / 32 ? red[lane] : 0;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s = max(s, t); }
+		red[lane] = s;
+	}
+	__syncthreads();
+	uint32_t off = w ? red[w - 1] : 0;
+	return max(v, off);
+}
+
+// exclusive scan of 256 counters held in shared memory (in place); NT >= 256. *total receives the sum.
+template <int NT>
+__device__ __forceinline__ void scan256_excl(uint32_t* arr, uint32_t* red)
+{
+	uint32_t v = threadIdx.x < 256 ? arr[threadIdx.x] : 0, tot;
+	uint32_t inc = block_scan_add<NT>(v, red, &tot);
+	if (threadIdx.x < 256) arr[threadIdx.x] = inc - v;
+	__syncthreads();
+}
+
+// bzip2 CRC-32 table (poly 0x04C11DB7, MSB first; crctable.c) computed on the fly
+__device__ __forceinline__ uint32_t crc_table_entry(uint32_t i)
+{
+	uint32_t c = i << 24;
+	#pragma unroll
+	for (int k = 0; k < 8; k++) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : (c << 1);
+	return c;
+}
+
+}  // namespace lfm

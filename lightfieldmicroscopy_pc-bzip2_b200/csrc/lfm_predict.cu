@@ -1,0 +1,109 @@
+// lfm_predict.cu -- forward predictor + symbolize, and the inverse (unsymbolize + wavefront un-predict).
+//
+// Forward replaces _predictorN_{tiles,angle,space} + symbolizeKernel + the per-frame cudaMemcpy loop of
+// klb_imageIO::Predictor_{both,angle,space}[_GPU] (src/klb_imageIO.cpp:1227-1746): one fused launch over all frames.
+// Inverse replaces unsymbolizeKernel + the single-threaded HOST loops unPredictorN_* (src/lfm_Predictors.cu:1470-2739,
+// src/klb_imageIO.cpp:1748-1821) with a GPU wavefront over w = tx+ty+u+v (every operand of the prediction has a
+// strictly smaller w), one CTA per frame, frames in parallel.
+#include "lfm_device.cuh"
+#include "lfm_predict.cuh"
+
+namespace lfm {
+
+constexpr int PF_NT = 256;
+
+__global__ void __launch_bounds__(PF_NT)
+k_predict_fwd(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int W, int H, int T, int way, int k,
+              int video, uint32_t z0, uint32_t nz)
+{
+	const uint64_t fpx = (uint64_t)W * H;
+	const uint64_t idx = (uint64_t)blockIdx.x * PF_NT + threadIdx.x;
+	if (idx >= fpx * nz) return;
+	const uint32_t zi = (uint32_t)(idx / fpx);
+	const uint32_t rem = (uint32_t)(idx - (uint64_t)zi * fpx);
+	const int y = (int)(rem / (uint32_t)W), x = (int)(rem - (uint32_t)y * (uint32_t)W);
+	const uint32_t z = z0 + zi;
+	const uint16_t* cur = img + (uint64_t)z * fpx;
+	const int tx = x / T, ty = y / T, u = x - tx * T, v = y - ty * T;
+	auto px = [&](int dx, int dy) { return (int)__ldg(cur + (size_t)(y + dy) * W + (x + dx)); };
+	int p = predict0(px, T, way, k, tx, ty, u, v);
+	if (video & (int)z & 1) {                       // `i_or_v & z`: only odd frames look back (klb_imageIO.cpp:1243)
+		int P = (int)__ldg(cur - fpx + (size_t)y * W + x);
+		p = (x == 0 && y == 0) ? P : ((p + P) >> 1);
+	}
+	sym[(uint64_t)z * fpx + rem] = symbolize16(px(0, 0) - p);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+constexpr int UP_NT = 1024;
+
+__global__ void __launch_bounds__(UP_NT, 1)
+k_unpredict(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T, int way, int k, int video,
+            uint32_t z_start, uint32_t z_step)
+{
+	__shared__ uint32_t pre[512];
+	__shared__ uint32_t red[64];
+	const uint32_t tid = threadIdx.x;
+	const uint32_t z = z_start + blockIdx.x * z_step;
+	const uint64_t fpx = (uint64_t)W * H;
+	const uint16_t* s = sym + (uint64_t)z * fpx;
+	uint16_t* o = out + (uint64_t)z * fpx;
+	const bool zflag = (video & (int)z & 1) != 0;
+	const int tilesX = (W + T - 1) / T, tilesY = (H + T - 1) / T;
+	const int nr = 2 * T - 1;                         // pixel anti-diagonals inside a tile (<= 509)
+	const int nsteps = tilesX + tilesY - 1 + nr - 1;
+
+	for (int w = 0; w < nsteps; w++) {
+		uint32_t c = 0;
+		if ((int)tid < nr) {
+			int r = (int)tid, sd = w - r;
+			if (sd >= 0 && sd <= tilesX + tilesY - 2) {
+				int lo = max(0, sd - (tilesY - 1)), hi = min(sd, tilesX - 1);
+				int np = min(r, 2 * T - 2 - r) + 1;
+				c = (uint32_t)((hi - lo + 1) * np);
+			}
+		}
+		uint32_t total; uint32_t inc = block_scan_add<UP_NT>(c, red, &total);
+		if ((int)tid < nr) pre[tid] = inc - c;
+		__syncthreads();
+		for (uint32_t i = tid; i < total; i += UP_NT) {
+			int lo_r = 0, hi_r = nr - 1;                 // last r with pre[r] <= i
+			while (lo_r < hi_r) { int mid = (lo_r + hi_r + 1) >> 1; if (pre[mid] <= i) lo_r = mid; else hi_r = mid - 1; }
+			const int r = lo_r, sd = w - r;
+			const uint32_t j = i - pre[r];
+			const int np = min(r, 2 * T - 2 - r) + 1;
+			const int ti = (int)(j / (uint32_t)np), pi = (int)(j - (uint32_t)ti * (uint32_t)np);
+			const int tx = max(0, sd - (tilesY - 1)) + ti, ty = sd - tx;
+			const int u = max(0, r - (T - 1)) + pi, v = r - u;
+			const int x = tx * T + u, y = ty * T + v;
+			if (x < W && y < H) {
+				auto px = [&](int dx, int dy) { return (int)o[(size_t)(y + dy) * W + (x + dx)]; };
+				int p = predict0(px, T, way, k, tx, ty, u, v);
+				if (zflag) {
+					int P = (int)o[(size_t)y * W + x - fpx];   // previous (even) frame, already reconstructed
+					p = (x == 0 && y == 0) ? P : ((p + P) >> 1);
+				}
+				o[(size_t)y * W + x] = (uint16_t)(unsymbolize16(s[(size_t)y * W + x]) + p);
+			}
+		}
+		__syncthreads();
+	}
+}
+
+void launch_predict_fwd(const uint16_t* img, uint16_t* sym, int W, int H, int T, int way, int k, int video,
+                        uint32_t z0, uint32_t nz, cudaStream_t st)
+{
+	uint64_t total = (uint64_t)W * H * nz;
+	uint64_t blocks = (total + PF_NT - 1) / PF_NT;
+	k_predict_fwd<<<(unsigned)blocks, PF_NT, 0, st>>>(img, sym, W, H, T, way, k, video, z0, nz);
+}
+
+// frames z_start, z_start+z_step, ... (count of them); video stacks: even frames first, then odd frames
+void launch_unpredict(const uint16_t* sym, uint16_t* out, int W, int H, int T, int way, int k, int video,
+                      uint32_t z_start, uint32_t z_step, uint32_t count, cudaStream_t st)
+{
+	if (count == 0) return;
+	k_unpredict<<<count, UP_NT, 0, st>>>(sym, out, W, H, T, way, k, video, z_start, z_step);
+}
+
+}  // namespace lfm

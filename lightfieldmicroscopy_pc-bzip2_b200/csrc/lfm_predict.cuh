@@ -1,0 +1,135 @@
+// lfm_predict.cuh -- the light-field DPCM prediction rules, one device function shared by the forward
+// (lfm_predict.cu: k_predict_fwd) and the inverse (k_unpredict) kernels.
+//
+// Behavioural spec: the 21 reference kernels _predictorN_{tiles,angle,space}
+//   src/lfm_Predictors.cu:35-1334, src/lfm_Predictors_angle.cu:17-1279, src/lfm_Predictors_space.cu:17-1213
+// (z == 0 branches; the z != 0 branch of way "tiles" adds the previous frame, see predict_px()).
+// T = Nnum; tile (tx,ty), in-tile (u,v); px(dx,dy) fetches the pixel at (x+dx, y+dy) of the current frame.
+// Every operand sits at strictly smaller tx+ty+u+v, which is what the inverse wavefront relies on.
+#pragma once
+#include <cstdint>
+
+namespace lfm {
+
+template <class Fetch>
+__device__ __forceinline__ int predict0(Fetch px, int T, int way, int k, int tx, int ty, int u, int v)
+{
+	const bool t00 = (tx == 0 && ty == 0), tcol0 = (tx == 0 && ty != 0), trow0 = (tx != 0 && ty == 0);
+	if (t00) {                                    // first tile: plain intra-tile DPCM borders, all ways
+		if (u == 0 && v == 0) return 0;
+		if (u == 0) return px(0, -1);
+		if (v == 0) return px(-1, 0);
+	}
+	if (way == 2 && !t00) {                       // space: the same sub-aperture pixel of neighbouring microlenses
+		if (tcol0) return px(0, -T);
+		if (trow0) return px(-T, 0);
+		switch (k) {
+		case 1: return px(-T, 0);
+		case 2: return px(0, -T);
+		case 3: return px(-T, -T);
+		case 4: return px(0, -T) + px(-T, 0) - px(-T, -T);
+		case 5: return px(0, -T) + ((px(-T, 0) - px(-T, -T)) >> 1);
+		case 6: return px(-T, 0) + ((px(0, -T) - px(-T, -T)) >> 1);
+		default: return (u > 0 && v > 0) ? ((px(0, -T) + px(-T, 0)) >> 1) : (px(0, -T) + px(-T, 0) - px(-T, -T));
+		}
+	}
+	if (way == 1 || (way == 2 && t00)) {          // angle: neighbours under the same microlens; DC from the next tile
+		if (u == 0 && v == 0) {
+			if (tcol0) return px(0, -T);
+			if (trow0) return px(-T, 0);
+			switch (k) {
+			case 1: return px(-T, 0);
+			case 2: return px(0, -T);
+			case 3: return px(-T, -T);
+			case 4: case 7: return px(0, -T) + px(-T, 0) - px(-T, -T);
+			case 5: return px(0, -T) + ((px(-T, 0) - px(-T, -T)) >> 1);
+			default: return px(-T, 0) + ((px(0, -T) - px(-T, -T)) >> 1);
+			}
+		}
+		if (u == 0) return px(0, -1);
+		const bool tin = !(t00 || tcol0 || trow0);
+		if (v == 0) return (k == 2 && tin) ? px(0, -1) : px(-1, 0);
+		int kk = k;
+		if (tin && (k == 5 || k == 6)) kk = 11 - k;           // 5 and 6 trade places in interior tiles
+		switch (kk) {
+		case 1: return px(-1, 0);
+		case 2: return px(0, -1);
+		case 3: return px(-1, -1);
+		case 4: return px(-1, 0) + px(0, -1) - px(-1, -1);
+		case 5: return px(-1, 0) + ((px(0, -1) - px(-1, -1)) >> 1);
+		case 6: return px(0, -1) + ((px(-1, 0) - px(-1, -1)) >> 1);
+		default: return (px(-1, 0) + px(0, -1)) >> 1;
+		}
+	}
+	// way 0: "tiles" = blend of both
+	const bool a = (u == 0 && v > 0), b = (u == 0 && v == 0), c = (u > 0 && v == 0);
+	if (t00) {
+		switch (k) {
+		case 1: return px(-1, 0);
+		case 2: return px(0, -1);
+		case 3: return px(-1, -1);
+		case 4: return px(-1, 0) + px(0, -1) - px(-1, -1);
+		case 5: return (px(-1, 0) + (px(0, -1) - px(-1, -1))) >> 1;    // sic: the shift binds last (lfm_Predictors.cu:744)
+		case 6: return px(0, -1) + ((px(-1, 0) - px(-1, -1)) >> 1);
+		default: return (px(-1, 0) + px(0, -1)) >> 1;
+		}
+	}
+	if (k == 1) {
+		if (tcol0) return a ? px(0, -1) : b ? px(0, -T) : px(-1, 0);
+		return (a || b) ? px(-T, 0) : ((px(-1, 0) + px(-T, 0)) >> 1);
+	}
+	if (k == 2) {
+		if (tcol0) return (b || c) ? px(0, -T) : ((px(0, -1) + px(0, -T)) >> 1);
+		if (trow0) return b ? px(-T, 0) : c ? px(-1, 0) : px(0, -1);
+		return (a || b) ? px(0, -T) : ((px(0, -1) + px(0, -T)) >> 1);
+	}
+	if (k == 3) {
+		const int far = tcol0 ? px(0, -T) : trow0 ? px(-T, 0) : px(-T, -T);
+		if (b) return far;
+		const int near = a ? px(0, -1) : c ? px(-1, 0) : px(-1, -1);
+		return (near + far) >> 1;
+	}
+	if (tcol0 || trow0) {
+		const int far = tcol0 ? px(0, -T) : px(-T, 0);
+		if (b) return far;
+		if (a) return (px(0, -1) + far) >> 1;
+		if (c) return (px(-1, 0) + far) >> 1;
+		switch (k) {
+		case 4: return (px(-1, 0) + px(0, -1) - px(-1, -1) + far) >> 1;
+		case 5: return (px(-1, 0) + ((px(0, -1) - px(-1, -1)) >> 1) + far) >> 1;
+		case 6: return (px(0, -1) + ((px(-1, 0) - px(-1, -1)) >> 1) + far) >> 1;
+		default:
+			if (tcol0) return (px(-1, 0) + px(0, -1) + px(-1, -T) + px(0, -T - 1)) >> 2;
+			return (px(-1, 0) + px(0, -1) + px(-T, -1) + px(-T - 1, 0)) >> 2;
+		}
+	}
+	int g;
+	switch (k) {
+	case 4: case 7: g = px(0, -T) + px(-T, 0) - px(-T, -T); break;
+	case 5: g = px(0, -T) + ((px(-T, 0) - px(-T, -T)) >> 1); break;
+	default: g = px(-T, 0) + ((px(0, -T) - px(-T, -T)) >> 1); break;
+	}
+	if (b) return g;
+	if (a) return (g + px(0, -1)) >> 1;
+	if (c) return (g + px(-1, 0)) >> 1;
+	switch (k) {
+	case 4: return (g + px(0, -1) + px(-1, 0) - px(-1, -1)) >> 1;
+	case 5: return (g + px(0, -1) + ((px(-1, 0) - px(-1, -1)) >> 1)) >> 1;
+	case 6: return (g + px(-1, 0) + ((px(0, -1) - px(-1, -1)) >> 1)) >> 1;
+	default: return (px(0, -T - 1) + px(-T - 1, 0) + px(0, -1) + px(-1, 0)) >> 2;
+	}
+}
+
+// zig-zag residual <-> symbol map (lfm_Predictors.cu:16-33), on the int16-truncated residual
+__device__ __forceinline__ uint16_t symbolize16(int residual)
+{
+	int r = (int)(int16_t)residual;
+	return (uint16_t)(2 * abs(r) + (r >> 31));
+}
+__device__ __forceinline__ int unsymbolize16(uint16_t s)
+{
+	int neg = s & 1;
+	return (int)(int16_t)((1 - 2 * neg) * (((int)s + neg) / 2));
+}
+
+}  // namespace lfm
