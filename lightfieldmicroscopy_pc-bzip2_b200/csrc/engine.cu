@@ -2,6 +2,7 @@
 #include "engine.h"
 #include "kernels.h"
 #include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <map>
 #include <mutex>
@@ -201,6 +202,9 @@ int Engine::unpredict(const uint16_t* d_sym, uint16_t* d_out, const StackDesc& s
 	if (video && s.way != 0) return LFM_ERR_UNSUPPORTED;
 	cudaStream_t st = (cudaStream_t)stream_;
 	const int W = (int)s.xyzct[0], H = (int)s.xyzct[1];
+	// test aid: a wrong wavefront order must not be masked by stale, accidentally correct data in a recycled buffer
+	static const bool poison = getenv("LFM_B200_DEBUG_POISON") != nullptr;
+	if (poison) cudaMemsetAsync(d_out + (size_t)z0 * W * H, 0xAB, (size_t)nz * W * H * 2, st);
 	if (!video) launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 0, z0, 1, nz, st);
 	else {
 		// odd frames need the decoded even frame before them: evens first, then odds (z0 must be even)

@@ -3,8 +3,12 @@
 // Forward replaces _predictorN_{tiles,angle,space} + symbolizeKernel + the per-frame cudaMemcpy loop of
 // klb_imageIO::Predictor_{both,angle,space}[_GPU] (src/klb_imageIO.cpp:1227-1746): one fused launch over all frames.
 // Inverse replaces unsymbolizeKernel + the single-threaded HOST loops unPredictorN_* (src/lfm_Predictors.cu:1470-2739,
-// src/klb_imageIO.cpp:1748-1821) with a GPU wavefront over w = tx+ty+u+v (every operand of the prediction has a
-// strictly smaller w), one CTA per frame, frames in parallel.
+// src/klb_imageIO.cpp:1748-1821) with a GPU wavefront, one CTA per frame, frames in parallel:
+//   * schedule A, w = tx+ty+u+v (~ tilesX+tilesY+2T steps): valid whenever the near neighbours L/U/UL are only used
+//     inside a tile -- every way/predictor except predictor 2 of the ways "tiles" and "angle";
+//   * schedule B, row by row (H steps): predictor 2 of those two ways reads U across the tile border (first tile row
+//     of interior tiles), which makes every image column one long chain. Rows then only depend on earlier rows, plus
+//     short left-to-right chains inside the first tile column / the first image row, which one thread walks.
 #include "lfm_device.cuh"
 #include "lfm_predict.cuh"
 
@@ -53,6 +57,29 @@ k_unpredict(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T
 	const int nr = 2 * T - 1;                         // pixel anti-diagonals inside a tile (<= 509)
 	const int nsteps = tilesX + tilesY - 1 + nr - 1;
 
+	auto decode_px = [&](int x, int y, int tx, int ty, int u, int v) {
+		auto px = [&](int dx, int dy) { return (int)o[(size_t)(y + dy) * W + (x + dx)]; };
+		int p = predict0(px, T, way, k, tx, ty, u, v);
+		if (zflag) {
+			int P = (int)o[(size_t)y * W + x - fpx];       // previous (even) frame, already reconstructed
+			p = (x == 0 && y == 0) ? P : ((p + P) >> 1);
+		}
+		o[(size_t)y * W + x] = (uint16_t)(unsymbolize16(s[(size_t)y * W + x]) + p);
+	};
+
+	if (k == 2 && way != 2) {
+		// ---- schedule B: rows
+		for (int y = 0; y < H; y++) {
+			const int ty = y / T, v = y - ty * T;
+			const int seq = (y == 0) ? W : min(T, W);        // leading pixels with left-neighbour chains: one thread
+			if (tid == 0) for (int x = 0; x < seq; x++) decode_px(x, y, x / T, ty, x % T, v);
+			for (int x = seq + (int)tid - 1; x < W; x += UP_NT - 1) if (tid > 0) decode_px(x, y, x / T, ty, x % T, v);
+			__syncthreads();
+		}
+		return;
+	}
+
+	// ---- schedule A: 4-D wavefront
 	for (int w = 0; w < nsteps; w++) {
 		uint32_t c = 0;
 		if ((int)tid < nr) {
@@ -76,15 +103,7 @@ k_unpredict(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T
 			const int tx = max(0, sd - (tilesY - 1)) + ti, ty = sd - tx;
 			const int u = max(0, r - (T - 1)) + pi, v = r - u;
 			const int x = tx * T + u, y = ty * T + v;
-			if (x < W && y < H) {
-				auto px = [&](int dx, int dy) { return (int)o[(size_t)(y + dy) * W + (x + dx)]; };
-				int p = predict0(px, T, way, k, tx, ty, u, v);
-				if (zflag) {
-					int P = (int)o[(size_t)y * W + x - fpx];   // previous (even) frame, already reconstructed
-					p = (x == 0 && y == 0) ? P : ((p + P) >> 1);
-				}
-				o[(size_t)y * W + x] = (uint16_t)(unsymbolize16(s[(size_t)y * W + x]) + p);
-			}
+			if (x < W && y < H) decode_px(x, y, tx, ty, u, v);
 		}
 		__syncthreads();
 	}
