@@ -1,0 +1,296 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the .lfm compress + decompress hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3s]
+
+Workload at N=1 (BASELINE.json configs[1]): one synthetic 2048x2048 uint16 light-field frame, Nnum=15, predictor way
+"space", fixed predictor 4 + bzip2, default 96x96x1 blocks (484 KLB blocks). One STEP = compress the frame, then
+decompress it again (a round trip); metric = raw bytes / (t_compress + t_decompress), in GB/s of raw uint16.
+For N>1 (torchrun, one rank per GPU) every rank round-trips its own frames (time points of a video stack are
+independent objects): weak scaling, no collective on the data path, value = all ranks' bytes / max-over-ranks time.
+
+  value     device-resident: lfmCompressDevice / lfmDecompressDevice on frames already in HBM
+  e2e       host buffers through the reference-facing C ABI (lfmCompressToMemory / lfmDecompressFromMemory =
+            writeImage/readImageFull without the disk), H2D + D2H inside the timed region
+  roofline  dominant kernel (k_bwt): algorithmic bytes (post-RLE1 block in + last column out = 2 n per block) per
+            launch / mean launch time from CUDA events on the engine stream; peak = MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref, its CUDA predictor + threaded CPU bzip2,
+            all host cores) on the same frame, file on /dev/shm; falls back to the oracle port if oracle/_ref is absent.
+Inputs rotate through a pool larger than L2 (24 frames = 201 MB > 126 MB), so no step finds its input in L2.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (frames per step, H, W, Nnum, way, headerVersion, description)
+    "c2": (1, 2048, 2048, 15, 2, 8 + 4, "configs[1]: synthetic 2048x2048 uint16 LF frame, Nnum=15, space predictor 4 + bzip2, 96x96x1 blocks"),
+    "c3s": (16, 2048, 2048, 13, 1, 0, "configs[2] slice: 2048x2048x16 uint16 z-stack, Nnum=13, angle predictor, 2-D entropy selection, 96x96x8 blocks"),
+}
+POOL = 24
+
+
+def synth_pool(nframes, H, W, nnum, count, rank):
+    """LF-synth v1; one pattern, `count` independent noise realisations (cheap to generate)"""
+    from conftest import lf_synth
+    base = lf_synth((nframes, H, W), nnum, seed=12345 + rank)
+    rng = np.random.default_rng(777 + rank)
+    pool = [base]
+    m = base.astype(np.float32)
+    for _ in range(count - 1):
+        pool.append(np.clip(np.rint(m + rng.normal(0, 1, m.shape).astype(np.float32) * np.sqrt(np.maximum(m, 1)) * 0.5), 0, 65535).astype(np.uint16))
+    return pool
+
+
+class ClockSampler:
+    def __init__(self, gpu):
+        self.rows = []; self.proc = None; self.gpu = gpu
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                                          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def load_reference(way):
+    """the real reference (GPU build: its CUDA predictor + threaded CPU bzip2); else its CPU-shim build; else None"""
+    for kind in ("gpu", "cpu"):
+        so = os.path.join(ROOT, "oracle", "_ref", "liblfmref_%s_way%d.so" % (kind, way))
+        if os.path.exists(so):
+            try:
+                return C.CDLL(so), kind
+            except OSError:
+                continue
+    return None, None
+
+
+def reference_round_trip(pool, nnum, way, hv, steps, warmup):
+    """time K round trips of the reference's writeImage + readImageFull (test/mainTest_lfmIO.cxx:96-126) on /dev/shm"""
+    cores = os.cpu_count() or 1
+    lib, kind = load_reference(way)
+    tmp = "/dev/shm/lfm_bench_ref_%d.lfm" % os.getpid() if os.path.isdir("/dev/shm") else "/tmp/lfm_bench_ref_%d.lfm" % os.getpid()
+    a0 = pool[0]
+    Z, H, W = a0.shape
+    raw = a0.nbytes
+    xyzct = (C.c_uint32 * 5)(W, H, Z, 1, 1)
+    tc = td = 0.0
+    if lib is not None:
+        if kind == "cpu" and (hv & 0x7F) < 8:
+            hv = 8 + 4              # the CPU-shim build runs the predictor kernels on one core: keep selection out of it
+        out = np.empty_like(a0)
+        for i in range(warmup + steps):
+            a = pool[i % len(pool)]
+            shv = C.c_int()
+            t0 = time.perf_counter()
+            rc = lib.ref_write(a.ctypes.data_as(C.c_void_p), tmp.encode(), xyzct, None, hv, nnum, -1, C.byref(shv))
+            t1 = time.perf_counter()
+            rc2 = lib.ref_read_full(tmp.encode(), out.ctypes.data_as(C.c_void_p), -1)
+            t2 = time.perf_counter()
+            assert rc == 0 and rc2 == 0 and np.array_equal(out, a), "reference round trip failed"
+            if i >= warmup:
+                tc += t1 - t0; td += t2 - t1
+        os.remove(tmp)
+        label = "reference" if kind == "gpu" else "reference"
+        sample = "%d round trips of the same %dx%dx%d frame set through the unmodified reference (%s build: %s), %d threads, file on %s" % (
+            steps, W, H, Z, kind, "its CUDA predictor on the GPU + threaded CPU bzip2" if kind == "gpu" else "its kernels emulated on one CPU core + threaded CPU bzip2",
+            cores, os.path.dirname(tmp))
+        return dict(kind=label, cores=cores, sample=sample, tc=tc, td=td, raw=raw * steps)
+    # oracle port, single thread, bounded sample: a quarter of one frame
+    from conftest import Oracle
+    ora = Oracle()
+    a = np.ascontiguousarray(pool[0][:1, :H // 2, :W // 2])
+    fn = tmp
+    t0 = time.perf_counter(); rc, _ = ora.write(a, fn, 8 + 4, nnum, way); t1 = time.perf_counter()
+    rc2, back = ora.read(fn, a.shape, way); t2 = time.perf_counter()
+    assert rc == 0 and rc2 == 0 and np.array_equal(back, a)
+    os.remove(fn)
+    return dict(kind="port", cores=1, sample="one %dx%d quarter frame through the oracle port (oracle/_ref absent), 1 thread" % (W // 2, H // 2),
+                tc=t1 - t0, td=t2 - t1, raw=a.nbytes)
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    nfr, H, W, nnum, way, hv, desc = WORKLOADS[args.workload]
+    metric = "compress+decompress round-trip GB/s (raw uint16)"
+    config = {"workload": desc, "frames_per_step_per_gpu": nfr, "step": "compress then decompress one frame set",
+              "l2": "inputs rotate through a %d-set pool (%.0f MB per GPU) larger than the 126 MB L2" % (POOL, POOL * nfr * H * W * 2 / 1e6),
+              "sharding": "one rank per GPU, independent frame sets per rank, no data-path collective"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        pool = synth_pool(nfr, H, W, nnum, 4, 0)
+        steps = min(args.steps, 8)
+        r = reference_round_trip(pool, nnum, way, hv, steps, 1)
+        val = r["raw"] / (r["tc"] + r["td"]) / 1e9
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+                "ms_per_step": (r["tc"] + r["td"]) / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u16", "data": "synthetic", "config": config,
+                "compress_gbs": r["raw"] / r["tc"] / 1e9, "decompress_gbs": r["raw"] / r["td"] / 1e9,
+                "cpu_baseline": {"value": val, "unit": "GB/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = importlib.import_module("lightfieldmicroscopy_pc-bzip2_b200")
+    L.set_devices(local, 1)
+    L.set_way(way)
+    pool = synth_pool(nfr, H, W, nnum, POOL, rank)
+    dpool = [torch.from_numpy(a.view(np.int16)).cuda() for a in pool]
+    raw = pool[0].nbytes
+    xyzct = L._u32x5(W, H, nfr, 1, 1)
+    nb = L.lib.lfmNumBlocks(xyzct, None)
+    off = np.zeros(nb, np.uint64)
+    dout = torch.empty_like(dpool[0])
+    shv = C.c_uint8(); dp = C.c_void_p(); pb = C.c_uint64()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    acc = dict(tc=0.0, td=0.0, bwt=0.0, rle=0.0, mtf=0.0, huff=0.0, dec=0.0, ibwt=0.0, unrle=0.0, launches=0, payload=0)
+
+    def step_device(i, timed):
+        d = dpool[i % POOL]
+        t0 = time.perf_counter()
+        rc = L.lib.lfmCompressDevice(d.data_ptr(), xyzct, None, hv, nnum, C.byref(shv), off.ctypes.data, nb, C.byref(dp), C.byref(pb))
+        t1 = time.perf_counter()
+        assert rc == 0, "lfmCompressDevice rc=%d %s" % (rc, L.lib.lfmLastError())
+        sc = L.stats()
+        rc = L.lib.lfmDecompressDevice(dp, off.ctypes.data, nb, xyzct, None, shv.value, nnum, dout.data_ptr())
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        assert rc == 0, "lfmDecompressDevice rc=%d" % rc
+        sd = L.stats()
+        if timed:
+            acc["tc"] += t1 - t0; acc["td"] += t2 - t1
+            acc["bwt"] += sc.ms_bwt; acc["rle"] += sc.ms_rle; acc["mtf"] += sc.ms_mtf; acc["huff"] += sc.ms_huff
+            acc["dec"] += sd.ms_decode; acc["ibwt"] += sd.ms_ibwt; acc["unrle"] += sd.ms_unrle
+            acc["launches"] += sc.gpu_launches + sd.gpu_launches; acc["payload"] += pb.value
+        return d
+
+    for i in range(args.warmup):
+        d = step_device(i, False)
+    assert torch.equal(dout, d), "device round trip mismatch"
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(); t_start = time.perf_counter()
+    for i in range(args.steps):
+        step_device(args.warmup + i, True)
+    ev1.record(); barrier(); t_all = time.perf_counter() - t_start
+    ev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+
+    # ---- e2e through the C ABI with host buffers
+    e2e = dict(tc=0.0, td=0.0, h2d=0, d2h=0)
+    for i in range(2 + args.steps):
+        a = pool[i % POOL]
+        t0 = time.perf_counter()
+        blob = L.compress_to_bytes(a, header_version=hv, nnum=nnum, way=way)
+        t1 = time.perf_counter()
+        back = L.decompress_from_bytes(blob, a.shape, way=way)
+        t2 = time.perf_counter()
+        if i == 0:
+            assert np.array_equal(back, a), "e2e round trip mismatch"
+        if i >= 2:
+            e2e["tc"] += t1 - t0; e2e["td"] += t2 - t1
+            e2e["h2d"] += a.nbytes + len(blob); e2e["d2h"] += len(blob) + a.nbytes
+    barrier()
+
+    t_step = torch.tensor([t_all, e2e["tc"] + e2e["td"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_step, op=dist.ReduceOp.MAX)
+    t_max, t_e2e_max = float(t_step[0]), float(t_step[1])
+    total_raw = raw * args.steps * world
+    value = total_raw / t_max / 1e9
+    e2e_value = total_raw / t_e2e_max / 1e9
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        ratio = raw * args.steps / max(acc["payload"], 1)
+        n_post_rle = raw                        # LF-synth frames have no long runs: post-RLE1 length == raw length within 0.1 %
+        bwt_ms = acc["bwt"] / args.steps
+        achieved = 2.0 * n_post_rle / (bwt_ms * 1e-3) / 1e9 if bwt_ms > 0 else 0.0
+        stage_ms = {k: acc[k] / args.steps for k in ("rle", "bwt", "mtf", "huff", "dec", "ibwt", "unrle")}
+        try:
+            rb = reference_round_trip(pool[:4], nnum, way, hv, 3, 1)
+            cpu = {"value": rb["raw"] / (rb["tc"] + rb["td"]) / 1e9, "unit": "GB/s", "cores": rb["cores"], "kind": rb["kind"], "sample": rb["sample"],
+                   "compress_gbs": rb["raw"] / rb["tc"] / 1e9, "decompress_gbs": rb["raw"] / rb["td"] / 1e9}
+        except Exception as ex:            # the baseline must never take the bench line down
+            cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (ex,)}
+        line = {"metric": metric, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u16", "data": "synthetic", "config": config,
+                "compress_gbs": raw * args.steps / acc["tc"] / 1e9, "decompress_gbs": raw * args.steps / acc["td"] / 1e9,
+                "compression_ratio": ratio, "event_ms_per_step": ev_ms / args.steps, "stage_ms_per_step": stage_ms,
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": e2e["h2d"] // args.steps, "d2h_bytes_per_step": e2e["d2h"] // args.steps,
+                        "compress_gbs": raw * args.steps / e2e["tc"] / 1e9, "decompress_gbs": raw * args.steps / e2e["td"] / 1e9},
+                "gpu_launches": int(acc["launches"]),
+                "roofline": {"bound": "hbm", "kernel": "k_bwt (rotation sort of all 96x96 blocks of the frame set, one launch)",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": 2 * n_post_rle, "launch_ms": bwt_ms},
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
