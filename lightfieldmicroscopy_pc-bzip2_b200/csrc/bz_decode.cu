@@ -10,195 +10,376 @@
 //   k_unrle       inverse of the initial run-length coding + CRC check (bzlib.c:561-728) fused with the scatter
 //                 of the block into the symbol image
 #include "lfm_radix.cuh"
+#include <algorithm>
 
 namespace lfm {
 
 // =====================================================================================================
-// k_decode : one warp per KLB block stream; lane 0 decodes (sequential by nature), blocks in parallel
+// k_huff_decode : one warp per KLB block stream -- ONLY the inherently sequential part.
+//   * the compressed stream is staged once into shared memory as big-endian words (coalesced copy by the warp);
+//   * every lane runs the same (uniform) parser, so nothing has to be broadcast;
+//   * a 64-bit bit buffer lives in registers; symbols of <= DEC_LB bits come out of a per-table lookup (one shared
+//     load per symbol on the critical path); longer ones use bzip2's limit/base/perm walk (decompress.c GET_MTF_VAL);
+//   * decoded symbols (RUNA/RUNB/rank+1/EOB) are gathered 32 at a time and stored coalesced.
+// Inverse move-to-front and run expansion are done in parallel by k_imtf.
 // =====================================================================================================
-constexpr int DEC_NT = 128;
-constexpr int DEC_NW = DEC_NT / 32;
+constexpr int DEC_LB = 10;                       // lookup bits
+constexpr int DEC_LUT = 1 << DEC_LB;
 
-struct BitReader {
-	const uint8_t* p; uint64_t nbytes; uint64_t pos; uint64_t buf; uint32_t cnt; bool overrun;
-	__device__ void init(const uint8_t* p_, uint64_t n_) { p = p_; nbytes = n_; pos = 0; buf = 0; cnt = 0; overrun = false; }
-	__device__ __forceinline__ void refill() {
-		while (cnt <= 56) {
-			uint32_t b = 0;
-			if (pos < nbytes) b = __ldg(p + pos); else if (pos >= nbytes + 8) overrun = true;
-			pos++;
-			buf |= (uint64_t)b << (56 - cnt);
-			cnt += 8;
-		}
-	}
-	__device__ __forceinline__ uint32_t get(uint32_t nb) {    // nb <= 32
-		if (cnt < nb) refill();
-		uint32_t v = (uint32_t)(buf >> (64 - nb));
-		buf <<= nb; cnt -= nb;
-		return v;
-	}
-	__device__ __forceinline__ uint32_t peek(uint32_t nb) { if (cnt < nb) refill(); return (uint32_t)(buf >> (64 - nb)); }
-	__device__ __forceinline__ void skip(uint32_t nb) { buf <<= nb; cnt -= nb; }
-	__device__ uint64_t bits_used() const { return pos * 8 - cnt; }
+struct DecWarpSmem {
+	uint16_t lut[kGroups][DEC_LUT];              // sym | len << 9   (0: longer than DEC_LB bits)
+	int32_t  limit[kGroups][24];
+	int32_t  base[kGroups][24];
+	uint16_t perm[kGroups][kMaxAlpha + 2];
+	uint8_t  len[kGroups][kMaxAlpha + 2];
+	int32_t  minlen[kGroups];
 };
 
-__global__ void __launch_bounds__(DEC_NT)
-k_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ begin, const uint64_t* __restrict__ end,
-         uint32_t njobs, DecJob* __restrict__ jobs, uint8_t* __restrict__ bwt_all, uint32_t cap,
-         uint8_t* __restrict__ sel_all, uint32_t selcap)
+extern __shared__ __align__(16) uint8_t dec_smem[];
+
+__global__ void __launch_bounds__(128)
+k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ begin, const uint64_t* __restrict__ end,
+              uint32_t njobs, DecJob* __restrict__ jobs, uint16_t* __restrict__ mtfv_all, uint32_t mcap, uint32_t cap,
+              uint32_t selcap, uint32_t stream_words /* per-warp staging capacity */)
 {
-	__shared__ int32_t  s_limit[DEC_NW][kGroups][24];
-	__shared__ int32_t  s_base[DEC_NW][kGroups][24];
-	__shared__ uint16_t s_perm[DEC_NW][kGroups][kMaxAlpha + 2];
-	__shared__ uint8_t  s_len[DEC_NW][kMaxAlpha + 2];
-	__shared__ uint8_t  s_unseq[DEC_NW][256];
-	__shared__ uint8_t  s_mtf[DEC_NW][256];
-	__shared__ uint32_t s_cnt[DEC_NW][256];
-	__shared__ int32_t  s_minlen[DEC_NW][kGroups];
-
-	const uint32_t w = warp_id();
-	const uint32_t job = blockIdx.x * DEC_NW + w;
-	if (job >= njobs || lane_id() != 0) return;
+	const uint32_t lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
+	const uint32_t job = blockIdx.x * nw + w;
+	if (job >= njobs) return;
+	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)stream_words * 4;
+	DecWarpSmem& S = *reinterpret_cast<DecWarpSmem*>(dec_smem + (size_t)w * per_warp);
+	uint8_t* selector = dec_smem + (size_t)w * per_warp + sizeof(DecWarpSmem);
+	uint32_t* sw = reinterpret_cast<uint32_t*>(selector + selcap);
 	DecJob& J = jobs[job];
-	uint8_t* L = bwt_all + (size_t)job * cap;
-	uint8_t* selector = sel_all + (size_t)job * selcap;
-	BitReader br; br.init(payload + begin[job], end[job] - begin[job]);
-	J.n = 0; J.out_bytes = 0; J.orig_ptr = 0; J.stored_crc = 0;
-	#define FAIL(code) do { J.status = (code); return; } while (0)
+	uint16_t* mtfv = mtfv_all + (size_t)job * mcap;
+	const uint8_t* src = payload + begin[job];
+	const uint64_t nbytes = end[job] - begin[job];
+	#define FAIL(code) do { if (lane == 0) { J.status = (code); J.n = 0; J.n_mtf = 0; } return; } while (0)
+	if (lane == 0) { J.n = 0; J.n_mtf = 0; J.out_bytes = 0; J.orig_ptr = 0; J.stored_crc = 0; J.status = 0; }
 
-	if (br.get(8) != 'B' || br.get(8) != 'Z' || br.get(8) != 'h') FAIL(1);
-	int level = (int)br.get(8) - '0';
+	// ---- stage the stream: word i = bytes 4i..4i+3, big endian; bytes past the end read as 0
+	const uint32_t nwords = (uint32_t)((nbytes + 3) / 4);
+	if (nwords + 3 > stream_words) FAIL(4);              // host sizes the staging area from the largest stream
+	{
+		const uint32_t mis = (uint32_t)((uintptr_t)src & 3);
+		const uint32_t* a32 = reinterpret_cast<const uint32_t*>(src - mis);   // payload base is 256-byte aligned: never below it
+		for (uint32_t i = lane; i < nwords + 3; i += 32) {
+			const uint64_t b0 = (uint64_t)i * 4;
+			uint32_t v = 0;
+			if (b0 + 8 <= nbytes) {                       // bulk: two aligned words cover stream bytes 4i .. 4i+3
+				uint32_t lo = a32[i], hi = a32[i + 1];
+				v = mis ? __funnelshift_r(lo, hi, mis * 8) : lo;
+				v = __byte_perm(v, 0, 0x0123);
+			} else {                                      // tail: byte by byte, zero past the end
+				#pragma unroll
+				for (int k = 0; k < 4; k++) v = (v << 8) | (b0 + k < nbytes ? (uint32_t)src[b0 + k] : 0u);
+			}
+			sw[i] = v;
+		}
+	}
+	__syncwarp();
+
+	// ---- uniform bit reader: bb holds bc >= 32 valid bits, left aligned; wi = next word to load
+	uint64_t bb = ((uint64_t)sw[0] << 32) | sw[1];
+	uint32_t bc = 64, wi = 2;
+	const uint32_t wi_limit = nwords + 3;
+	bool overrun = false;
+	auto drop = [&](uint32_t nb) {                        // nb <= 32
+		bb <<= nb; bc -= nb;
+		if (bc < 32) {
+			uint32_t v = 0;
+			if (wi < wi_limit) v = sw[wi]; else overrun = true;
+			wi++;
+			bb |= (uint64_t)v << (32 - bc); bc += 32;
+		}
+	};
+	auto peek = [&](uint32_t nb) -> uint32_t { return (uint32_t)(bb >> (64 - nb)); };
+	auto get = [&](uint32_t nb) -> uint32_t { uint32_t v = peek(nb); drop(nb); return v; };
+
+	if (get(8) != 'B' || get(8) != 'Z' || get(8) != 'h') FAIL(1);
+	const int level = (int)get(8) - '0';
 	if (level < 1 || level > 9) FAIL(1);
-	J.level = (uint32_t)level;
 	const uint32_t max_block = min((uint32_t)(100000 * level), cap);
-	uint32_t m1 = br.get(24), m2 = br.get(24);
-	if (m1 == 0x177245 && m2 == 0x385090) { J.status = 0; for (int i = 0; i <= 256; i++) J.cftab[i] = 0; return; }   // empty stream
+	uint32_t m1 = get(24), m2 = get(24);
+	if (m1 == 0x177245 && m2 == 0x385090) { if (lane == 0) J.level = (uint32_t)level; return; }      // empty stream
 	if (m1 != 0x314159 || m2 != 0x265359) FAIL(2);
-	J.stored_crc = br.get(32);
-	if (br.get(1)) FAIL(4);                                   // randomised blocks are never produced (compress.c:629)
-	const uint32_t orig_ptr = br.get(24);
+	const uint32_t stored_crc = get(32);
+	if (get(1)) FAIL(4);                                   // randomised blocks are never produced (compress.c:629)
+	const uint32_t orig_ptr = get(24);
+	uint32_t iu[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 	uint32_t n_in_use = 0;
 	{
-		uint32_t used16 = br.get(16);
+		uint32_t used16 = get(16);
 		for (int i = 0; i < 16; i++) if (used16 & (0x8000u >> i)) {
-			uint32_t bits = br.get(16);
-			for (int j = 0; j < 16; j++) if (bits & (0x8000u >> j)) s_unseq[w][n_in_use++] = (uint8_t)(i * 16 + j);
+			uint32_t bits = get(16);
+			uint32_t rev = __brev(bits) >> 16;             // bit j <-> byte value 16 i + j
+			#pragma unroll
+			for (int k = 0; k < 8; k++) if ((i >> 1) == k) iu[k] |= rev << ((i & 1) * 16);
+			n_in_use += __popc(bits);
 		}
 	}
 	if (n_in_use == 0) FAIL(2);
 	const int alpha = (int)n_in_use + 2;
-	const int n_groups = (int)br.get(3);
-	const int n_sel = (int)br.get(15);
+	const int n_groups = (int)get(3);
+	const int n_sel = (int)get(15);
 	if (n_groups < 2 || n_groups > 6 || n_sel < 1 || (uint32_t)n_sel > selcap) FAIL(2);
 	{
-		uint8_t pos[kGroups];
-		for (int i = 0; i < n_groups; i++) pos[i] = (uint8_t)i;
+		uint32_t pos = 0x543210u;                          // 6 nibbles: move-to-front list of table ids
 		for (int i = 0; i < n_sel; i++) {
-			int j = 0;
-			while (br.get(1)) { j++; if (j >= n_groups) FAIL(2); }
-			uint8_t t = pos[j];
-			for (; j > 0; j--) pos[j] = pos[j - 1];
-			pos[0] = t; selector[i] = t;
+			uint32_t v = peek(6);                          // unary: count leading ones (at most n_groups-1)
+			int j = __clz(~(v << 26));
+			if (j >= n_groups) FAIL(2);
+			drop((uint32_t)j + 1);
+			uint32_t t = (pos >> (4 * j)) & 15u;
+			uint32_t lowmask = (1u << (4 * j)) - 1u;
+			pos = (pos & ~((lowmask << 4) | 15u)) | ((pos & lowmask) << 4) | t;
+			if (lane == 0) selector[i] = (uint8_t)t;
+			if (overrun) FAIL(2);
 		}
 	}
 	for (int t = 0; t < n_groups; t++) {
-		int curr = (int)br.get(5);
+		int curr = (int)get(5);
 		for (int i = 0; i < alpha; i++) {
 			for (;;) {
 				if (curr < 1 || curr > 20) FAIL(2);
-				if (!br.get(1)) break;
-				if (br.get(1)) curr--; else curr++;
+				uint32_t two = peek(2);
+				if (!(two & 2)) { drop(1); break; }
+				drop(2);
+				curr += (two & 1) ? -1 : 1;
 			}
-			s_len[w][i] = (uint8_t)curr;
+			if (lane == 0) S.len[t][i] = (uint8_t)curr;
 		}
-		// decode tables (huffman.c:170-205); perm by counting sort on the length (stable in the symbol)
+		if (overrun) FAIL(2);
+	}
+	__syncwarp();
+	// ---- decode tables: lane t builds table t (huffman.c:170-205 + the lookup)
+	if ((int)lane < n_groups) {
+		const int t = (int)lane;
 		int mn = 32, mx = 0;
-		int32_t* base = s_base[w][t]; int32_t* limit = s_limit[w][t];
+		int32_t* base = S.base[t]; int32_t* limit = S.limit[t];
 		for (int i = 0; i < 24; i++) { base[i] = 0; limit[i] = 0; }
-		for (int i = 0; i < alpha; i++) { int l = s_len[w][i]; mx = l > mx ? l : mx; mn = l < mn ? l : mn; base[l + 1]++; }
+		for (int i = 0; i < alpha; i++) { int l = S.len[t][i]; mx = l > mx ? l : mx; mn = l < mn ? l : mn; base[l + 1]++; }
 		for (int i = 1; i < 23; i++) base[i] += base[i - 1];
 		{
 			int32_t nxt[24];
 			for (int i = 0; i < 24; i++) nxt[i] = base[i];
-			for (int i = 0; i < alpha; i++) { int l = s_len[w][i]; s_perm[w][t][nxt[l]++] = (uint16_t)i; }
+			for (int i = 0; i < alpha; i++) { int l = S.len[t][i]; S.perm[t][nxt[l]++] = (uint16_t)i; }
+		}
+		// lookup: symbols in (length, symbol) order own consecutive, left-to-right ranges of the DEC_LB-bit code space
+		{
+			uint32_t fill = 0;
+			for (int p = 0; p < alpha; p++) {
+				int sym = S.perm[t][p], l = S.len[t][sym];
+				if (l > DEC_LB) break;
+				uint32_t span = 1u << (DEC_LB - l);
+				uint16_t e = (uint16_t)(sym | (l << 9));
+				for (uint32_t q = 0; q < span && fill + q < (uint32_t)DEC_LUT; q++) S.lut[t][fill + q] = e;
+				fill += span;
+			}
+			for (; fill < (uint32_t)DEC_LUT; fill++) S.lut[t][fill] = 0;
 		}
 		int vec = 0;
 		for (int i = mn; i <= mx; i++) { vec += base[i + 1] - base[i]; limit[i] = vec - 1; vec <<= 1; }
 		for (int i = mn + 1; i <= mx; i++) base[i] = ((limit[i - 1] + 1) << 1) - base[i];
-		s_minlen[w][t] = mn;
+		S.minlen[t] = mn;
 	}
-	if (br.overrun) FAIL(2);
+	__syncwarp();
 
-	// ---- MTF / run decoding (decompress.c:349-487)
-	for (int i = 0; i < 256; i++) { s_mtf[w][i] = (uint8_t)i; s_cnt[w][i] = 0; }
-	const int EOB = (int)n_in_use + 1;
-	uint32_t nblock = 0, acc = 0;
-	auto put = [&](uint32_t b) {
-		acc |= b << ((nblock & 3) * 8);
-		nblock++;
-		if ((nblock & 3) == 0) { *reinterpret_cast<uint32_t*>(L + nblock - 4) = acc; acc = 0; }
-	};
-	int grp = -1, left = 0, t = 0;
-	uint32_t run = 0, run_w = 1; bool in_run = false;
-	const int32_t* limit = nullptr; const int32_t* base = nullptr; const uint16_t* perm = nullptr; int mn = 0;
+	// ---- symbols (decompress.c:349-487 without the MTF): append until EOB
+	const uint32_t EOB = n_in_use + 1;
+	uint32_t nsym = 0, obuf = 0;
+	int grp = 0, left = kGSize, t = selector[0];
+	if (t >= n_groups) FAIL(2);
+	const uint16_t* lut = S.lut[t];
 	for (;;) {
-		if (left == 0) {
-			grp++; if (grp >= n_sel) FAIL(2);
-			left = kGSize; t = selector[grp];
-			limit = s_limit[w][t]; base = s_base[w][t]; perm = s_perm[w][t]; mn = s_minlen[w][t];
+		uint32_t sym;
+		const uint32_t e = lut[(uint32_t)(bb >> (64 - DEC_LB))];
+		if (e) { sym = e & 511u; drop(e >> 9); }
+		else {
+			const uint32_t window = peek(20);
+			const int32_t* limit = S.limit[t]; const int32_t* base = S.base[t];
+			int zn = S.minlen[t]; int32_t zvec = (int32_t)(window >> (20 - zn));
+			for (;;) {
+				if (zn > 20) FAIL(2);
+				if (zvec <= limit[zn]) break;
+				zn++;
+				if (zn <= 20) zvec = (int32_t)(window >> (20 - zn));
+			}
+			drop((uint32_t)zn);
+			int32_t idx = zvec - base[zn];
+			if (idx < 0 || idx >= kMaxAlpha) FAIL(2);
+			sym = S.perm[t][idx];
 		}
-		left--;
-		uint32_t window = br.peek(20);
-		int zn = mn; int32_t zvec = (int32_t)(window >> (20 - zn));
-		for (;;) {
-			if (zn > 20) FAIL(2);
-			if (zvec <= limit[zn]) break;
-			zn++;
-			if (zn <= 20) zvec = (int32_t)(window >> (20 - zn));
-		}
-		br.skip((uint32_t)zn);
-		int32_t idx = zvec - base[zn];
-		if (idx < 0 || idx >= kMaxAlpha) FAIL(2);
-		int sym = perm[idx];
-		if (sym <= 1) {
-			if (!in_run) { in_run = true; run = 0; run_w = 1; }
-			run += (uint32_t)(sym + 1) * run_w; run_w <<= 1;
-			if (run > max_block) FAIL(2);
-			continue;
-		}
-		if (in_run) {
-			uint32_t uc = s_unseq[w][s_mtf[w][0]];
-			if (nblock + run > max_block) FAIL(2);
-			s_cnt[w][uc] += run;
-			for (uint32_t i = 0; i < run; i++) put(uc);
-			in_run = false;
-		}
+		if (lane == (nsym & 31u)) obuf = sym;
+		nsym++;
+		if ((nsym & 31u) == 0) mtfv[nsym - 32 + lane] = (uint16_t)obuf;
 		if (sym == EOB) break;
-		if (nblock >= max_block) FAIL(2);
-		{
-			int p = sym - 1; uint8_t v = s_mtf[w][p];
-			for (; p > 0; p--) s_mtf[w][p] = s_mtf[w][p - 1];
-			s_mtf[w][0] = v;
-			uint32_t uc = s_unseq[w][v];
-			s_cnt[w][uc]++; put(uc);
+		if (nsym >= mcap || overrun) FAIL(2);
+		if (--left == 0) {
+			grp++; if (grp >= n_sel) FAIL(2);
+			left = kGSize; t = selector[grp]; if (t >= n_groups) FAIL(2);
+			lut = S.lut[t];
 		}
-		if (br.overrun) FAIL(2);
 	}
-	const uint32_t n = nblock;
-	while (nblock & 3) put(0);
-	if (orig_ptr >= n) FAIL(2);
+	if (nsym & 31u) { if (lane < (nsym & 31u)) mtfv[(nsym & ~31u) + lane] = (uint16_t)obuf; }
 	// the stream must end here: end-of-stream magic + combined CRC (single block: == block CRC)
-	uint32_t e1 = br.get(24), e2 = br.get(24);
+	uint32_t e1 = get(24), e2 = get(24);
 	if (e1 == 0x314159 && e2 == 0x265359) FAIL(4);            // multi-block stream: not supported in this version
 	if (e1 != 0x177245 || e2 != 0x385090) FAIL(2);
-	uint32_t combined = br.get(32);
-	if (combined != J.stored_crc) FAIL(3);
-	uint32_t s = 0;
-	for (int i = 0; i < 256; i++) { J.cftab[i] = s; s += s_cnt[w][i]; }
-	J.cftab[256] = s;
-	J.n = n; J.orig_ptr = orig_ptr; J.status = 0;
+	if (get(32) != stored_crc) FAIL(3);
+	if (lane == 0) {
+		J.n_mtf = nsym; J.n_in_use = n_in_use; J.orig_ptr = orig_ptr; J.stored_crc = stored_crc; J.level = (uint32_t)level; J.status = 0;
+		J.max_block = max_block;
+		for (int k = 0; k < 8; k++) J.in_use[k] = iu[k];
+	}
 	#undef FAIL
 }
+
+// =====================================================================================================
+// k_imtf : one CTA per block -- run expansion + inverse move-to-front, in parallel over chunks of symbols.
+// A chunk's effect on the list is a permutation that does not depend on the list it starts from, so
+//   A. thread t runs the inverse MTF over its symbols on an IDENTITY list: each symbol yields an index q into the
+//      (unknown) list at the chunk start; the final list is the chunk's permutation P(t);
+//   B. the chunk-start lists follow by composition   start(t+1)[j] = start(t)[P(t)[j]]   (128 cheap CTA-wide steps);
+//   C. thread t replays its symbols: output byte = seqToUnseq[start(t)[q]], RUNA/RUNB runs repeat the front symbol.
+// Output offsets come from a block scan of the per-chunk output counts. (decompress.c:349-487)
+// =====================================================================================================
+constexpr int IM_NT = 128;
+constexpr int IM_STS = IM_NT + 1;         // word row stride of the packed per-thread lists
+constexpr int IM_SLS = IM_NT + 4;         // byte row stride of the chunk-start lists
+
+extern __shared__ __align__(16) uint8_t im_smem[];
+
+__global__ void __launch_bounds__(IM_NT)
+k_imtf(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, DecJob* __restrict__ jobs, uint32_t njobs,
+       uint8_t* __restrict__ q_all /* scratch slot per block (the text slot, free until the inverse BWT) */,
+       uint8_t* __restrict__ bwt_all, uint32_t cap)
+{
+	uint32_t* st = reinterpret_cast<uint32_t*>(im_smem);                               // [64][STS] packed lists
+	uint8_t* sl = im_smem + 64 * IM_STS * 4;                                            // [256][SLS] chunk-start lists
+	uint32_t* red = reinterpret_cast<uint32_t*>(sl + 256 * IM_SLS);                     // [64]
+	uint32_t* s_start = red + 64;                                                       // [NT + 1] chunk boundaries (symbol index)
+	uint8_t* unseq = reinterpret_cast<uint8_t*>(s_start + IM_NT + 4);                   // [256]
+	uint8_t* st8 = reinterpret_cast<uint8_t*>(st);
+	#define ST_BYTE(pos, t) st8[(((pos) >> 2) * IM_STS + (t)) * 4 + ((pos) & 3)]
+
+	const uint32_t tid = threadIdx.x;
+	const uint32_t job = blockIdx.x;
+	if (job >= njobs) return;
+	DecJob& J = jobs[job];
+	if (J.status != 0) return;
+	const uint32_t n_mtf = J.n_mtf;
+	if (n_mtf == 0) return;                                                             // empty stream
+	const uint16_t* mtfv = mtfv_all + (size_t)job * mcap;
+	uint8_t* qs = q_all + (size_t)job * cap;
+	uint8_t* L = bwt_all + (size_t)job * cap;
+	const uint32_t EOB = J.n_in_use + 1, max_block = J.max_block;
+	const uint32_t nsym = n_mtf - 1;                                                    // without EOB
+	if (nsym > cap) { if (tid == 0) J.status = 2; return; }                            // every symbol yields >= 1 byte
+
+	// seqToUnseq from the inUse map
+	{
+		uint32_t below = 0, acc = 0;
+		for (int v = 0; v < 2; v++) {
+			const uint32_t val = tid + v * IM_NT;
+			acc = 0; below = 0;
+			for (int k = 0; k < 8; k++) {
+				uint32_t wv = J.in_use[k];
+				if ((val >> 5) == (uint32_t)k) below = acc + __popc(wv & ((1u << (val & 31)) - 1u));
+				acc += __popc(wv);
+			}
+			if ((J.in_use[val >> 5] >> (val & 31)) & 1u) unseq[below] = (uint8_t)val;
+		}
+	}
+	// chunk boundaries: never inside a RUNA/RUNB run
+	const uint32_t CS = (nsym + IM_NT - 1) / IM_NT;
+	{
+		uint32_t a = min(nsym, tid * CS);
+		if (a > 0) while (a < nsym && mtfv[a] <= 1 && mtfv[a - 1] <= 1) a++;
+		s_start[tid] = a;
+		if (tid == 0) s_start[IM_NT] = nsym;
+	}
+	// identity list
+	#pragma unroll 4
+	for (int wv = 0; wv < 64; wv++) st[wv * IM_STS + tid] = (uint32_t)(4 * wv) * 0x01010101u + 0x03020100u;
+	__syncthreads();
+	const uint32_t a0 = s_start[tid], a1 = max(a0, s_start[tid + 1]);
+
+	// ---- A. inverse MTF on the identity list; q per symbol, output count per chunk
+	uint32_t outc = 0;
+	bool bad = false;
+	{
+		uint32_t* my = st + tid;
+		uint32_t i = a0;
+		while (i < a1) {
+			const uint32_t sym = mtfv[i];
+			if (sym <= 1) {                                   // a whole run: bijective base 2
+				uint32_t run = 0, wgt = 1;
+				while (i < a1 && mtfv[i] <= 1) { run += (mtfv[i] + 1u) * wgt; wgt <<= 1; i++; if (run > max_block) { bad = true; break; } }
+				if (bad) break;
+				outc += run;
+				continue;
+			}
+			if (sym >= EOB) { bad = true; break; }
+			const uint32_t r = sym - 1, wj = r >> 2, j = r & 3;
+			uint32_t carry = 0;
+			// words below wj shift up by one byte; the entry at (wj, j) goes to the front
+			const uint32_t target = my[wj * IM_STS];
+			const uint32_t v = (target >> (8 * j)) & 255u;
+			carry = v;
+			for (uint32_t ww = 0; ww < wj; ww++) {
+				const uint32_t word = my[ww * IM_STS];
+				my[ww * IM_STS] = (word << 8) | carry;
+				carry = word >> 24;
+			}
+			{
+				const uint32_t low = j ? (target & (0xFFFFFFFFu >> (32 - 8 * j))) : 0u;
+				const uint32_t keep = (j == 3) ? 0u : (target & (0xFFFFFFFFu << (8 * (j + 1))));
+				my[wj * IM_STS] = keep | (low << 8) | carry;
+			}
+			qs[i] = (uint8_t)v;
+			outc++;
+			i++;
+		}
+	}
+	uint32_t total; const uint32_t inc = block_scan_add<IM_NT>(outc, red, &total);
+	if (__syncthreads_or(bad || total > max_block || total > cap)) { if (tid == 0) J.status = 2; return; }
+
+	// ---- B. chunk-start lists by composition; thread j owns positions j and j + NT
+	{
+		uint32_t cur0 = tid, cur1 = tid + IM_NT;              // start(0) = identity
+		for (uint32_t t = 0; t < IM_NT; t++) {
+			sl[tid * IM_SLS + t] = (uint8_t)cur0; sl[(tid + IM_NT) * IM_SLS + t] = (uint8_t)cur1;
+			__syncthreads();
+			const uint32_t p0 = ST_BYTE(tid, t), p1 = ST_BYTE(tid + IM_NT, t);
+			cur0 = sl[p0 * IM_SLS + t]; cur1 = sl[p1 * IM_SLS + t];      // column t is not written again: no second barrier
+		}
+		__syncthreads();
+	}
+
+	// ---- C. replay: bytes out
+	{
+		uint32_t o = inc - outc;
+		uint32_t front = unseq[sl[0 * IM_SLS + tid]];
+		uint32_t i = a0;
+		while (i < a1) {
+			const uint32_t sym = mtfv[i];
+			if (sym <= 1) {
+				uint32_t run = 0, wgt = 1;
+				while (i < a1 && mtfv[i] <= 1) { run += (mtfv[i] + 1u) * wgt; wgt <<= 1; i++; }
+				for (uint32_t k = 0; k < run; k++) L[o + k] = (uint8_t)front;
+				o += run;
+				continue;
+			}
+			front = unseq[sl[(uint32_t)qs[i] * IM_SLS + tid]];
+			L[o++] = (uint8_t)front;
+			i++;
+		}
+	}
+	#undef ST_BYTE
+	if (tid == 0) { J.n = total; if (J.orig_ptr >= total) J.status = 2; }
+}
+
+size_t imtf_smem_bytes() { return (size_t)64 * IM_STS * 4 + (size_t)256 * IM_SLS + 64 * 4 + (IM_NT + 4) * 4 + 256 + 64; }
 
 // =====================================================================================================
 // k_inv_bwt : one CTA per block
@@ -212,6 +393,7 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 {
 	__shared__ uint32_t wcnt[BWT_NW][256];
 	__shared__ uint32_t run[256];
+	__shared__ uint32_t red[64];
 	__shared__ uint32_t s_next[IB_MAXS + 2];
 	__shared__ uint32_t s_len[IB_MAXS + 2];
 	__shared__ uint32_t s_nvis;
@@ -227,8 +409,7 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 		uint8_t* txt = txt_all + (size_t)job * cap;
 
 		// ---- LF mapping: T[pos] = i for the i-th occurrence ... stable counting sort of positions by byte
-		if (tid < 256) run[tid] = J.cftab[tid];
-		__syncthreads();
+		digit_starts(n, run, wcnt, red, [&](uint32_t e) { return (uint32_t)L[e]; });     // cftab (decompress.c:494-510)
 		radix_scatter<uint32_t>(n, run, wcnt,
 			[&](uint32_t e) { return (e << 8) | (uint32_t)L[e]; },
 			[&](uint32_t p) { return p & 255u; },
@@ -323,10 +504,22 @@ k_unrle(const uint8_t* __restrict__ txt_all, uint32_t cap, DecJob* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-void launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t* end, uint32_t njobs, DecJob* jobs,
-                   uint8_t* bwt, uint32_t cap, uint8_t* sel, uint32_t selcap, cudaStream_t st)
+// max_stream_bytes: the largest (end - begin) in the batch; sizes the per-warp staging area
+int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t* end, uint32_t njobs, DecJob* jobs,
+                  uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap,
+                  uint64_t max_stream_bytes, cudaStream_t st)
 {
-	k_decode<<<(njobs + DEC_NW - 1) / DEC_NW, DEC_NT, 0, st>>>(payload, begin, end, njobs, jobs, bwt, cap, sel, selcap);
+	const uint32_t stream_words = (uint32_t)((max_stream_bytes + 3) / 4 + 4);   // + zero words the bit buffer may prefetch
+	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)stream_words * 4;
+	int nw = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
+	if (nw < 1) return 1;                                   // a single stream larger than shared memory
+	const size_t smem = per_warp * nw;
+	cudaFuncSetAttribute(k_huff_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	k_huff_decode<<<(njobs + nw - 1) / nw, nw * 32, smem, st>>>(payload, begin, end, njobs, jobs, mtfv, mcap, cap, selcap, stream_words);
+	const size_t smem2 = imtf_smem_bytes();
+	cudaFuncSetAttribute(k_imtf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+	k_imtf<<<njobs, IM_NT, smem2, st>>>(mtfv, mcap, jobs, njobs, q_scratch, bwt, cap);
+	return 0;
 }
 size_t inv_bwt_scratch_elems(int grid, uint32_t cap) { return (size_t)grid * cap + (size_t)grid * 2 * IB_VIS; }
 void launch_inv_bwt(const uint8_t* bwt, uint32_t cap, DecJob* jobs, uint32_t njobs, uint32_t* tt_scratch, uint8_t* txt,

@@ -13,167 +13,357 @@
 namespace lfm {
 
 // =====================================================================================================
-// k_rle1 : one warp per KLB block; lane 0 walks the block (v1: latency bound, parallel over blocks)
+// k_rle1 : one CTA per KLB block.
+//   A. gather the block's rows from the symbol image into shared memory (into the block's still unused BWT
+//      slot in global memory when it does not fit);
+//   B. thread t owns a contiguous chunk (chunks right-aligned: only the first non-empty one is short);
+//      run heads (byte != previous byte) are located per chunk, a forward max-scan / backward min-scan over
+//      the threads tells every chunk where the run it starts in began and where the run it ends in stops;
+//   C. bzip2's run rule in closed form: a run of length R (positions r = 0..R-1) emits byte r when r % 255 < 4
+//      and a count byte after every r % 255 == 3  -> outputs(r0..r1) = g(r1) - g(r0), g(x) = 5 (x / 255) + h(x % 255);
+//      block scan of the chunk totals gives the output offsets, then every thread writes its part;
+//   D. CRC-32: per-chunk table CRC, combined in a binary tree with carry-less multiplications by x^(8 len) mod P.
+// (bzlib.c:216-354 ADD_CHAR_TO_BLOCK / add_pair_to_block / flush_RL; bzlib_private.h:157-171)
 // =====================================================================================================
-constexpr int RLE_NT = 128;
+constexpr int RLE_NT = 256;
+constexpr uint32_t kCrcPoly = 0x04C11DB7u;
+
+__device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b)      // a * b in GF(2)[x] / P, bit k <-> x^k
+{
+	uint32_t r = 0;
+	#pragma unroll 8
+	for (int i = 31; i >= 0; i--) {
+		r = (r << 1) ^ ((r & 0x80000000u) ? kCrcPoly : 0u);
+		if ((b >> i) & 1u) r ^= a;
+	}
+	return r;
+}
+__device__ __forceinline__ uint32_t crc_xpow8(uint32_t nbytes)              // x^(8 nbytes) mod P
+{
+	uint32_t e = nbytes * 8u, r = 1u;
+	for (int i = 31 - __clz(e | 1u); i >= 0; i--) {
+		r = crc_mulmod(r, r);
+		if ((e >> i) & 1u) r = (r << 1) ^ ((r & 0x80000000u) ? kCrcPoly : 0u);
+	}
+	return r;
+}
+__device__ __forceinline__ uint32_t rle_g(uint32_t x)                        // outputs produced by run positions [0, x)
+{
+	uint32_t m = x % 255u;
+	return (x / 255u) * 5u + min(m, 4u) + (m >= 4u ? 1u : 0u);
+}
+
+extern __shared__ __align__(16) uint8_t rle_smem[];
 
 __global__ void __launch_bounds__(RLE_NT)
 k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t njobs,
-       uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jobs)
+       uint8_t* __restrict__ txt_all, uint8_t* __restrict__ raw_all /* = BWT slots, free at this point */, uint32_t cap,
+       EncJob* __restrict__ jobs, int stage_in_smem)
 {
 	__shared__ uint32_t crc_tab[256];
-	for (uint32_t i = threadIdx.x; i < 256; i += RLE_NT) crc_tab[i] = crc_table_entry(i);
-	__syncthreads();
-	uint32_t job = blockIdx.x * (RLE_NT / 32) + warp_id();
-	if (job >= njobs || lane_id() != 0) return;
+	__shared__ uint32_t red[64];
+	__shared__ uint32_t s_a[RLE_NT], s_b[RLE_NT];
+	__shared__ uint32_t s_inuse[8];
+	const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+	const uint32_t job = blockIdx.x;
+	if (job >= njobs) return;
+	crc_tab[tid] = crc_table_entry(tid);
+	if (tid < 8) s_inuse[tid] = 0;
 
 	uint32_t c0[5], ext[5];
 	block_box(g, first_block + job, c0, ext);
+	const uint32_t rows = ext[1] * ext[2] * ext[3] * ext[4], rowpx = ext[0];
+	const uint32_t gcount = rows * rowpx * 2;
 	uint8_t* out = txt_all + (size_t)job * cap;
-	uint32_t nout = 0, acc = 0;
-	uint64_t first8 = 0;               // the first 8 output bytes, replayed after the block as wrap-around
-	uint32_t crc = 0xFFFFFFFFu;
-	uint32_t in_use[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-	int run_ch = -1; uint32_t run_len = 0;
+	uint8_t* stage = stage_in_smem ? rle_smem : raw_all + (size_t)job * cap;
 
-	auto put = [&](uint32_t b) {
-		if (nout < 8) first8 |= (uint64_t)b << (nout * 8);
-		acc |= b << ((nout & 3) * 8);
-		nout++;
-		if ((nout & 3) == 0) { *reinterpret_cast<uint32_t*>(out + nout - 4) = acc; acc = 0; }
-	};
-	auto mark = [&](uint32_t b) {
-		#pragma unroll
-		for (int k = 0; k < 8; k++) if ((b >> 5) == (uint32_t)k) in_use[k] |= 1u << (b & 31);
-	};
-	auto flush_run = [&]() {
-		if (run_ch < 0) return;
-		mark((uint32_t)run_ch);
-		uint32_t k = run_len < 4 ? run_len : 4;
-		for (uint32_t i = 0; i < k; i++) put((uint32_t)run_ch);
-		if (run_len >= 4) { put(run_len - 4); mark(run_len - 4); }
-	};
-	auto feed = [&](uint32_t b) {
-		crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ b];
-		if ((int)b != run_ch || run_len == 255) { flush_run(); run_ch = (int)b; run_len = 1; }
-		else run_len++;
-	};
-
-	uint32_t raw = 0;
-	for (uint32_t t = 0; t < ext[4]; t++) for (uint32_t c = 0; c < ext[3]; c++)
-	for (uint32_t z = 0; z < ext[2]; z++) for (uint32_t y = 0; y < ext[1]; y++) {
+	// ---- A. gather (one row per warp at a time)
+	for (uint32_t r = wid; r < rows; r += RLE_NT / 32) {
+		uint32_t y = r % ext[1], q = r / ext[1];
+		uint32_t z = q % ext[2]; q /= ext[2];
+		uint32_t c = q % ext[3], t = q / ext[3];
 		const uint16_t* row = sym + (c0[0] + (uint64_t)(c0[1] + y) * g.stride[1] + (uint64_t)(c0[2] + z) * g.stride[2]
 		                             + (uint64_t)(c0[3] + c) * g.stride[3] + (uint64_t)(c0[4] + t) * g.stride[4]);
-		for (uint32_t x = 0; x < ext[0]; x++) {
-			uint32_t v = __ldg(row + x);
-			feed(v & 255u); feed(v >> 8);
-		}
-		raw += ext[0] * 2;
+		uint16_t* dst = reinterpret_cast<uint16_t*>(stage) + (size_t)r * rowpx;
+		for (uint32_t x = lane; x < rowpx; x += 32) dst[x] = __ldg(row + x);
 	}
-	flush_run();
-	uint32_t n = nout;
-	// 8 wrap-around bytes after the block (the sort reads text[i + 0..7])
-	if (n > 0) for (uint32_t k = 0; k < 8; k++) put((uint32_t)(first8 >> ((k % n) * 8)) & 255u);
-	while (nout & 3) put(0);
+	__syncthreads();
+	const uint8_t* b = stage;
 
-	EncJob& J = jobs[job];
-	J.raw_bytes = raw; J.n = n; J.crc = ~crc; J.status = 0; J.periodic = 0; J.orig_ptr = 0;
-	uint32_t niu = 0;
-	#pragma unroll
-	for (int k = 0; k < 8; k++) { J.in_use[k] = in_use[k]; niu += __popc(in_use[k]); }
-	J.n_in_use = niu;
+	// ---- B. chunks (right aligned) and run boundaries
+	uint32_t CH = ((gcount + RLE_NT - 1) / RLE_NT + 3) & ~3u;              // whole words, and an odd number of them:
+	if (((CH >> 2) & 1u) == 0) CH += 4;                                 // threads then hit distinct shared-memory banks
+	const uint32_t after = (RLE_NT - 1 - tid) * CH;                     // bytes owned by later threads
+	const uint32_t e1 = gcount > after ? gcount - after : 0;
+	const uint32_t e0 = e1 > CH ? e1 - CH : 0;
+	const uint32_t NONE = 0xFFFFFFFFu;
+	uint32_t first_head = NONE, last_head = NONE;
+	for (uint32_t i = e0; i < e1; i++) {
+		if (i == 0 || b[i] != b[i - 1]) { if (first_head == NONE) first_head = i; last_head = i; }
+	}
+	// start of the run that is open at my chunk start = last head before e0 (max-scan; heads ascend with the thread)
+	const uint32_t incl = block_scan_max<RLE_NT>(last_head == NONE ? 0u : last_head + 1u, red);     // +1 so that 0 = none
+	uint32_t prev_incl = __shfl_up_sync(0xffffffffu, incl, 1);
+	if (lane == 0) prev_incl = wid ? red[wid - 1] : 0;
+	const uint32_t open_start = prev_incl ? prev_incl - 1u : 0u;
+	// first head after my chunk (gcount if none): reverse min-scan done through shared memory
+	s_a[tid] = first_head;
+	__syncthreads();
+	if (tid == 0) { uint32_t nh = gcount; for (int t = RLE_NT - 1; t >= 0; t--) { uint32_t f = s_a[t]; s_b[t] = nh; if (f != NONE) nh = f; } }
+	__syncthreads();
+	const uint32_t next_head = s_b[tid];
+
+	// ---- C. count, scan, write. Walk the chunk run segment by run segment.
+	uint32_t outc = 0;
+	{
+		uint32_t i = e0, rs = open_start;
+		while (i < e1) {
+			if (i == 0 || b[i] != b[i - 1]) rs = i;
+			uint32_t e = i + 1;
+			while (e < e1 && b[e] == b[e - 1]) e++;
+			outc += rle_g(e - rs) - rle_g(i - rs);
+			i = e;
+		}
+	}
+	uint32_t total; const uint32_t incs = block_scan_add<RLE_NT>(outc, red, &total);
+	const uint32_t n = total;
+	uint32_t crc = 0;
+	{
+		uint32_t o = incs - outc, i = e0, rs = open_start;
+		uint32_t iu[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+		auto mark = [&](uint32_t v) {
+			#pragma unroll
+			for (int k = 0; k < 8; k++) if ((v >> 5) == (uint32_t)k) iu[k] |= 1u << (v & 31);
+		};
+		while (i < e1) {
+			if (i == 0 || b[i] != b[i - 1]) rs = i;
+			const uint32_t ch = b[i];
+			uint32_t e = i + 1;
+			while (e < e1 && b[e] == b[e - 1]) e++;
+			const uint32_t run_end = (e < e1) ? e : next_head;       // where the whole run stops
+			const uint32_t run_len = run_end - rs;
+			mark(ch);
+			uint32_t p = i;
+			while (p < e) {
+				const uint32_t r = p - rs, q = r % 255u;
+				if (q < 4) {
+					out[o++] = (uint8_t)ch;
+					if (q == 3) { uint32_t reclen = min(255u, run_len - (r - 3)); out[o++] = (uint8_t)(reclen - 4); mark(reclen - 4); }
+					p++;
+				} else p += 255u - q;                                   // the rest of this 255-record emits nothing
+			}
+			i = e;
+		}
+		#pragma unroll
+		for (int k = 0; k < 8; k++) if (iu[k]) atomicOr(&s_inuse[k], iu[k]);
+		// ---- D. chunk CRC (the first non-empty chunk carries the 0xFFFFFFFF start value)
+		if (e1 > e0) {
+			crc = (e0 == 0) ? 0xFFFFFFFFu : 0u;
+			for (uint32_t j = e0; j < e1; j++) crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ b[j]];
+		}
+	}
+	s_a[tid] = crc;
+	__syncthreads();
+	{
+		uint32_t M = crc_xpow8(CH);                                     // x^(8 CH): shift by one full chunk
+		for (uint32_t stride = 1; stride < RLE_NT; stride <<= 1) {
+			if ((tid & (2 * stride - 1)) == 0) s_a[tid] = crc_mulmod(s_a[tid], M) ^ s_a[tid + stride];
+			M = crc_mulmod(M, M);
+			__syncthreads();
+		}
+	}
+	// 8 wrap-around bytes after the block (the sort reads text[i + 0..7]) and zero padding to a multiple of 4
+	__syncthreads();
+	if (tid < 12 && n > 0) {
+		uint32_t pos = n + tid;
+		if (tid < 8) out[pos] = out[tid % n];
+		else if (pos < ((n + 8 + 3) & ~3u)) out[pos] = 0;
+	}
+	if (tid == 0) {
+		EncJob& J = jobs[job];
+		J.raw_bytes = gcount; J.n = n; J.crc = ~s_a[0]; J.status = 0; J.periodic = 0; J.orig_ptr = 0;
+		uint32_t niu = 0;
+		for (int k = 0; k < 8; k++) { J.in_use[k] = s_inuse[k]; niu += __popc(s_inuse[k]); }
+		J.n_in_use = niu;
+	}
 }
 
 // =====================================================================================================
-// k_mtf : one warp per block.  The first 32 entries of the move-to-front list live one per lane,
-// the tail in shared memory; the scan over the BWT output is sequential, parallel over blocks.
+// k_mtf : one CTA per block, move-to-front made parallel by chunking.
+//   1. thread t scans its chunk of the BWT column backwards -> the chunk's recency list (distinct symbols, most
+//      recent first) + membership bitmap;
+//   2. the list state at the start of every chunk follows from   S(t+1) = recency(t) ++ (S(t) \ recency(t))
+//      -- 256 cheap CTA-wide steps (one list entry per thread, a ballot-compaction per step);
+//   3. thread t runs the ordinary sequential move-to-front over its chunk from S(t), lists interleaved in
+//      shared memory ([position][thread], conflict-free), ranks go to a per-block scratch slot;
+//   4. zero runs -> RUNA/RUNB (bijective base 2) with the run carried across chunk borders, output offsets by a
+//      block scan, symbols written to mtfv.   (compress.c:121-232)
 // =====================================================================================================
 constexpr int MTF_NT = 128;
-constexpr int MTF_NW = MTF_NT / 32;
+constexpr int MTF_RLS = MTF_NT + 4;        // byte row stride of the recency lists (bank-conflict-free both ways)
+constexpr int MTF_STS = MTF_NT + 1;        // word row stride of the packed start states
+
+extern __shared__ __align__(16) uint8_t mtf_smem[];
 
 __global__ void __launch_bounds__(MTF_NT)
-k_mtf(const uint8_t* __restrict__ bwt_all, uint32_t cap, EncJob* __restrict__ jobs, uint32_t njobs,
-      uint16_t* __restrict__ mtfv_all, uint32_t mcap)
+k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scratch, one slot per block */, uint32_t cap,
+      EncJob* __restrict__ jobs, uint32_t njobs, uint16_t* __restrict__ mtfv_all, uint32_t mcap)
 {
-	__shared__ uint8_t s_seq[MTF_NW][256];
-	__shared__ uint8_t s_list[MTF_NW][256];
-	const uint32_t lane = lane_id(), w = warp_id();
-	const uint32_t job = blockIdx.x * MTF_NW + w;
+	uint8_t* rl = mtf_smem;                                                                 // [256][RLS] recency lists, byte (pos, t)
+	uint32_t* st = reinterpret_cast<uint32_t*>(mtf_smem + 256 * MTF_RLS);                   // [64][STS] lists, 4 positions per word
+	uint32_t* seen = st + 64 * MTF_STS;                                                     // [8][NT] membership bitmaps
+	uint32_t* cnt = seen + 8 * MTF_NT;                                                      // [NT]
+	uint32_t* zin = cnt + MTF_NT;                                                           // [NT]
+	uint32_t* red = zin + MTF_NT;                                                           // [64]
+	uint8_t* seqmap = reinterpret_cast<uint8_t*>(red + 64);                                 // [256]
+	uint8_t* tmp = seqmap + 256;                                                            // [256]
+	uint8_t* st8 = reinterpret_cast<uint8_t*>(st);
+	#define ST_BYTE(pos, t) st8[(((pos) >> 2) * MTF_STS + (t)) * 4 + ((pos) & 3)]
+
+	const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+	const uint32_t job = blockIdx.x;
 	if (job >= njobs) return;
 	const uint32_t n = jobs[job].n;
 	const uint8_t* bwt = bwt_all + (size_t)job * cap;
+	uint8_t* rk = rank_all + (size_t)job * cap;
 	uint16_t* mtfv = mtfv_all + (size_t)job * mcap;
 
-	// unseqToSeq (compress.c:105-116): rank of each used byte value
-	uint32_t iu[8];
-	#pragma unroll
-	for (int k = 0; k < 8; k++) iu[k] = jobs[job].in_use[k];
+	// unseqToSeq (compress.c:105-116); each thread fills two entries
 	uint32_t n_in_use = 0;
-	#pragma unroll
-	for (int k = 0; k < 8; k++) {
-		uint32_t c = k * 32 + lane;
-		uint32_t below = n_in_use + __popc(iu[k] & ((1u << lane) - 1u));
-		s_seq[w][c] = (uint8_t)below;
-		s_list[w][c] = (uint8_t)c;
-		n_in_use += __popc(iu[k]);
+	{
+		uint32_t below0 = 0, below1 = 0;
+		const uint32_t v0 = tid, v1 = tid + MTF_NT;
+		for (int k = 0; k < 8; k++) {
+			uint32_t wv = jobs[job].in_use[k];
+			if ((v0 >> 5) == (uint32_t)k) below0 = n_in_use + __popc(wv & ((1u << (v0 & 31)) - 1u));
+			if ((v1 >> 5) == (uint32_t)k) below1 = n_in_use + __popc(wv & ((1u << (v1 & 31)) - 1u));
+			n_in_use += __popc(wv);
+		}
+		seqmap[v0] = (uint8_t)below0; seqmap[v1] = (uint8_t)below1;
 	}
-	__syncwarp();
+	__syncthreads();
 	const uint32_t EOB = n_in_use + 1;
+	const uint32_t CH = (n + MTF_NT - 1) / MTF_NT;
+	const uint32_t c0 = min(n, tid * CH), c1 = min(n, c0 + CH);
 
-	uint32_t y0 = lane;            // list positions 0..31
-	uint32_t front = 0;
-	uint32_t zpend = 0, wr = 0, buf = 0;
-	auto emit = [&](uint32_t v) {
-		if (lane == (wr & 31)) buf = v;
-		wr++;
-		if ((wr & 31) == 0) mtfv[wr - 32 + lane] = (uint16_t)buf;
-	};
-	auto flush_zeros = [&]() {
-		if (zpend == 0) return;
-		uint32_t z = zpend - 1;
-		for (;;) { emit(z & 1u); if (z < 2) break; z = (z - 2) >> 1; }
-		zpend = 0;
-	};
+	// ---- 1. recency list of the chunk
+	#pragma unroll
+	for (int k = 0; k < 8; k++) seen[k * MTF_NT + tid] = 0;
+	uint32_t my_cnt = 0;
+	for (uint32_t i = c1; i > c0; i--) {
+		uint32_t c = seqmap[bwt[i - 1]];
+		uint32_t wv = seen[(c >> 5) * MTF_NT + tid], bit = 1u << (c & 31);
+		if (!(wv & bit)) { seen[(c >> 5) * MTF_NT + tid] = wv | bit; rl[my_cnt * MTF_RLS + tid] = (uint8_t)c; my_cnt++; }
+	}
+	cnt[tid] = my_cnt;
+	__syncthreads();
 
-	for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-		uint32_t mine = (b0 + lane < n) ? s_seq[w][bwt[b0 + lane]] : 0;
-		uint32_t cnt = min(32u, n - b0);
-		for (uint32_t t = 0; t < cnt; t++) {
-			uint32_t c = __shfl_sync(0xffffffffu, mine, t);
-			if (c == front) { zpend++; continue; }
-			flush_zeros();
-			uint32_t pos;
-			uint32_t bal = __ballot_sync(0xffffffffu, y0 == c);
-			uint32_t up = __shfl_up_sync(0xffffffffu, y0, 1);
-			if (bal) {
-				pos = __ffs(bal) - 1;
-				if (lane == 0) y0 = c; else if (lane <= pos) y0 = up;
-			} else {
-				uint32_t carry = __shfl_sync(0xffffffffu, y0, 31);
-				if (lane == 0) y0 = c; else y0 = up;
-				pos = 0;
-				for (uint32_t ch = 1; ch < 8; ch++) {
-					uint32_t v = s_list[w][ch * 32 + lane];
-					uint32_t hit = __ballot_sync(0xffffffffu, v == c);
-					uint32_t nextc = __shfl_sync(0xffffffffu, v, 31);
-					uint32_t upv = __shfl_up_sync(0xffffffffu, v, 1);
-					if (lane == 0) upv = carry;
-					uint32_t limit = hit ? (uint32_t)(__ffs(hit) - 1) : 31u;
-					if (lane <= limit) s_list[w][ch * 32 + lane] = (uint8_t)upv;
-					carry = nextc;
-					if (hit) { pos = ch * 32 + limit; break; }
+	// ---- 2. start state of every chunk; thread j owns list positions j and j + NT
+	uint32_t mine0 = tid, mine1 = tid + MTF_NT;               // initial list: yy[i] = i
+	for (uint32_t t = 0; t < MTF_NT; t++) {
+		ST_BYTE(tid, t) = (uint8_t)mine0; ST_BYTE(tid + MTF_NT, t) = (uint8_t)mine1;
+		const uint32_t ct = cnt[t];
+		if (ct == 0) continue;                                // empty chunk (only past the end of the block)
+		const bool keep0 = !((seen[(mine0 >> 5) * MTF_NT + t] >> (mine0 & 31)) & 1u);
+		const bool keep1 = !((seen[(mine1 >> 5) * MTF_NT + t] >> (mine1 & 31)) & 1u);
+		const uint32_t bal0 = __ballot_sync(0xffffffffu, keep0), bal1 = __ballot_sync(0xffffffffu, keep1);
+		if (lane == 0) { red[wid] = __popc(bal0); red[4 + wid] = __popc(bal1); }
+		__syncthreads();
+		uint32_t before0 = 0, before1 = 0;
+		#pragma unroll
+		for (int ww = 0; ww < 4; ww++) { uint32_t a0 = red[ww], a1 = red[4 + ww]; if ((uint32_t)ww < wid) { before0 += a0; before1 += a1; } before1 += a0; }
+		const uint32_t lt = (1u << lane) - 1u;
+		if (keep0) tmp[ct + before0 + __popc(bal0 & lt)] = (uint8_t)mine0;
+		if (keep1) tmp[ct + before1 + __popc(bal1 & lt)] = (uint8_t)mine1;
+		if (tid < ct) tmp[tid] = rl[tid * MTF_RLS + t];
+		if (tid + MTF_NT < ct) tmp[tid + MTF_NT] = rl[(tid + MTF_NT) * MTF_RLS + t];
+		__syncthreads();
+		mine0 = tmp[tid]; mine1 = tmp[tid + MTF_NT];
+	}
+	__syncthreads();
+
+	// ---- 3. sequential move-to-front per chunk on the packed list (4 positions per word)
+	{
+		uint32_t* my = st + tid;                               // word w of my list: my[w * STS]
+		uint32_t front = my[0] & 255u;
+		for (uint32_t i = c0; i < c1; i++) {
+			const uint32_t c = seqmap[bwt[i]];
+			uint32_t r = 0;
+			if (c != front) {
+				const uint32_t pat = c * 0x01010101u;
+				uint32_t carry = c;
+				for (uint32_t w = 0; ; w++) {
+					const uint32_t word = my[w * MTF_STS];
+					const uint32_t m = __vcmpeq4(word, pat);
+					if (m) {
+						const uint32_t j = (uint32_t)(__ffs(m) - 1) >> 3;                  // byte holding c
+						const uint32_t low = j ? (word & (0xFFFFFFFFu >> (32 - 8 * j))) : 0u;   // bytes below it
+						const uint32_t keep = (j == 3) ? 0u : (word & (0xFFFFFFFFu << (8 * (j + 1))));
+						my[w * MTF_STS] = keep | (low << 8) | carry;
+						r = 4 * w + j;
+						break;
+					}
+					my[w * MTF_STS] = (word << 8) | carry;
+					carry = word >> 24;
 				}
-				__syncwarp();
+				front = c;
 			}
-			front = c;
-			emit(pos + 1);
+			rk[i] = (uint8_t)r;
 		}
 	}
-	flush_zeros();
-	emit(EOB);
-	if (wr & 31) { if (lane < (wr & 31)) mtfv[(wr & ~31u) + lane] = (uint16_t)buf; }
-	if (lane == 0) { jobs[job].n_mtf = wr; jobs[job].n_in_use = n_in_use; }
+	#undef ST_BYTE
+	// ---- 4. zero-run coding. A run is emitted by the chunk in which it ends.
+	uint32_t lead = 0, trail = 0;                            // leading / trailing zero ranks of my chunk
+	{
+		uint32_t i = c0;
+		while (i < c1 && rk[i] == 0) { lead++; i++; }
+		if (lead < c1 - c0) { uint32_t j = c1; while (j > c0 && rk[j - 1] == 0) { trail++; j--; } }
+	}
+	cnt[tid] = (lead == c1 - c0) ? 0xFFFFFFFFu : trail;     // all zero: passes the incoming run on
+	__syncthreads();
+	if (tid == 0) {
+		uint32_t z = 0;
+		for (uint32_t t = 0; t < MTF_NT; t++) {
+			zin[t] = z;
+			uint32_t a0 = min(n, t * CH), a1 = min(n, a0 + CH);
+			if (cnt[t] == 0xFFFFFFFFu) z += a1 - a0; else z = cnt[t];
+		}
+		red[40] = z;                                        // run still pending at the end of the block
+	}
+	__syncthreads();
+	const uint32_t zpend_end = red[40];
+	auto ndigits = [](uint32_t r) { return r ? (uint32_t)(31 - __clz(r + 1)) : 0u; };
+	uint32_t outc = 0;
+	{
+		uint32_t z = zin[tid];
+		for (uint32_t i = c0; i < c1; i++) {
+			if (rk[i] == 0) z++;
+			else { outc += ndigits(z) + 1; z = 0; }
+		}
+	}
+	// the thread that owns the last byte also flushes the final run and writes EOB
+	const bool owner_of_end = (n == 0) ? (tid == 0) : (c0 < n && c1 == n);
+	if (owner_of_end) outc += ndigits(zpend_end) + 1;
+	uint32_t total; uint32_t inc = block_scan_add<MTF_NT>(outc, red, &total);
+	uint32_t o = inc - outc;
+	{
+		uint32_t z = zin[tid];
+		auto put_run = [&](uint32_t zz) {
+			if (!zz) return;
+			uint32_t q = zz - 1;
+			for (;;) { mtfv[o++] = (uint16_t)(q & 1u); if (q < 2) break; q = (q - 2) >> 1; }
+		};
+		for (uint32_t i = c0; i < c1; i++) {
+			uint32_t r = rk[i];
+			if (r == 0) z++;
+			else { put_run(z); z = 0; mtfv[o++] = (uint16_t)(r + 1); }
+		}
+		if (owner_of_end) { put_run(zpend_end); mtfv[o++] = (uint16_t)EOB; }
+	}
+	if (tid == 0) { jobs[job].n_mtf = total; jobs[job].n_in_use = n_in_use; }
 }
+
+size_t mtf_smem_bytes() { return (size_t)256 * MTF_RLS + (size_t)64 * MTF_STS * 4 + 8 * MTF_NT * 4 + (MTF_NT * 2 + 64) * 4 + 512; }
 
 // =====================================================================================================
 // k_huff_pack : one CTA per block
@@ -472,15 +662,19 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-void launch_rle1(const uint16_t* sym, const Geom& g, uint64_t first_block, uint32_t njobs, uint8_t* txt, uint32_t cap,
-                 EncJob* jobs, cudaStream_t st)
+void launch_rle1(const uint16_t* sym, const Geom& g, uint64_t first_block, uint32_t njobs, uint8_t* txt, uint8_t* raw_scratch,
+                 uint32_t cap, uint32_t max_raw_bytes, EncJob* jobs, cudaStream_t st)
 {
-	uint32_t per = RLE_NT / 32;
-	k_rle1<<<(njobs + per - 1) / per, RLE_NT, 0, st>>>(sym, g, first_block, njobs, txt, cap, jobs);
+	const int in_smem = max_raw_bytes + 16 <= 200 * 1024;
+	const size_t smem = in_smem ? (size_t)max_raw_bytes + 16 : 0;
+	cudaFuncSetAttribute(k_rle1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	k_rle1<<<njobs, RLE_NT, smem, st>>>(sym, g, first_block, njobs, txt, raw_scratch, cap, jobs, in_smem);
 }
-void launch_mtf(const uint8_t* bwt, uint32_t cap, EncJob* jobs, uint32_t njobs, uint16_t* mtfv, uint32_t mcap, cudaStream_t st)
+void launch_mtf(const uint8_t* bwt, uint8_t* rank_scratch, uint32_t cap, EncJob* jobs, uint32_t njobs, uint16_t* mtfv, uint32_t mcap, cudaStream_t st)
 {
-	k_mtf<<<(njobs + MTF_NW - 1) / MTF_NW, MTF_NT, 0, st>>>(bwt, cap, jobs, njobs, mtfv, mcap);
+	size_t smem = mtf_smem_bytes();
+	cudaFuncSetAttribute(k_mtf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	k_mtf<<<njobs, MTF_NT, smem, st>>>(bwt, rank_scratch, cap, jobs, njobs, mtfv, mcap);
 }
 void launch_huff_pack(const uint16_t* mtfv, uint32_t mcap, EncJob* jobs, uint32_t njobs, uint8_t* sel, uint32_t selcap,
                       uint8_t* out, uint32_t ocap, int level, cudaStream_t st)

@@ -205,15 +205,17 @@ int Engine::unpredict(const uint16_t* d_sym, uint16_t* d_out, const StackDesc& s
 	// test aid: a wrong wavefront order must not be masked by stale, accidentally correct data in a recycled buffer
 	static const bool poison = getenv("LFM_B200_DEBUG_POISON") != nullptr;
 	if (poison) cudaMemsetAsync(d_out + (size_t)z0 * W * H, 0xAB, (size_t)nz * W * H * 2, st);
-	if (!video) launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 0, z0, 1, nz, st);
+	int bad = 0;
+	if (!video) bad |= launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 0, z0, 1, nz, sm_count_, st);
 	else {
 		// odd frames need the decoded even frame before them: evens first, then odds (z0 must be even)
 		uint32_t first_even = z0 + (z0 & 1), first_odd = z0 + 1 - (z0 & 1);
 		uint32_t n_even = first_even < z0 + nz ? (z0 + nz - first_even + 1) / 2 : 0;
 		uint32_t n_odd = first_odd < z0 + nz ? (z0 + nz - first_odd + 1) / 2 : 0;
-		launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 1, first_even, 2, n_even, st);
-		launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 1, first_odd, 2, n_odd, st);
+		bad |= launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 1, first_even, 2, n_even, sm_count_, st);
+		bad |= launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 1, first_odd, 2, n_odd, sm_count_, st);
 	}
+	if (bad) { cudaGetLastError(); err_ = "cooperative launch of k_unpredict failed"; return LFM_ERR_CUDA; }
 	return check("unpredict");
 }
 
@@ -230,7 +232,7 @@ int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t 
 		return LFM_ERR_UNSUPPORTED;
 	}
 	if (count == 0) { *d_payload = nullptr; *payload_bytes = 0; return LFM_OK; }
-	const size_t per_job = (size_t)z.cap * 2 + (size_t)z.mcap * 2 + z.selcap + z.ocap + sizeof(EncJob);
+	const size_t per_job = (size_t)z.cap * 3 + (size_t)z.mcap * 2 + z.selcap + z.ocap + sizeof(EncJob);
 	uint64_t B = std::min<uint64_t>(count, std::max<uint64_t>(1, ((size_t)6 << 30) / per_job));
 	B = std::min<uint64_t>(B, 16384);
 	const int grid = (int)std::min<uint64_t>(B, (uint64_t)sm_count_);
@@ -240,6 +242,7 @@ int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t 
 	if ((rc = reserve(jobs_, B * sizeof(EncJob)))) return rc;
 	if ((rc = reserve(txt_, B * z.cap))) return rc;
 	if ((rc = reserve(bwt_, B * z.cap))) return rc;
+	if ((rc = reserve(rank_, B * z.cap))) return rc;
 	if ((rc = reserve(mtfv_, B * (size_t)z.mcap * 2))) return rc;
 	if ((rc = reserve(sel_, B * z.selcap))) return rc;
 	if ((rc = reserve(out_, B * (size_t)z.ocap + 16))) return rc;
@@ -256,12 +259,12 @@ int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t 
 	for (uint64_t b0 = 0; b0 < count; b0 += B) {
 		const uint32_t nj = (uint32_t)std::min<uint64_t>(B, count - b0);
 		mark();
-		launch_rle1(d_sym, g, first + b0, nj, (uint8_t*)txt_.p, z.cap, (EncJob*)jobs_.p, st);
+		launch_rle1(d_sym, g, first + b0, nj, (uint8_t*)txt_.p, (uint8_t*)bwt_.p, z.cap, (uint32_t)blockBytes, (EncJob*)jobs_.p, st);
 		mark();
 		launch_bwt((uint8_t*)txt_.p, z.cap, (EncJob*)jobs_.p, nj, (uint8_t*)bwt_.p, (uint32_t*)scratch_.p,
 		           (int)std::min<uint32_t>(nj, (uint32_t)grid), z.text_in_smem, st);
 		mark();
-		launch_mtf((uint8_t*)bwt_.p, z.cap, (EncJob*)jobs_.p, nj, (uint16_t*)mtfv_.p, z.mcap, st);
+		launch_mtf((uint8_t*)bwt_.p, (uint8_t*)rank_.p, z.cap, (EncJob*)jobs_.p, nj, (uint16_t*)mtfv_.p, z.mcap, st);
 		mark();
 		launch_huff_pack((uint16_t*)mtfv_.p, z.mcap, (EncJob*)jobs_.p, nj, (uint8_t*)sel_.p, z.selcap, (uint8_t*)out_.p, z.ocap, z.level, st);
 		k_offsets<<<1, 1024, 0, st>>>((EncJob*)jobs_.p, nj, tot, (uint64_t*)offs_.p, (uint32_t*)sizes_.p + b0, pcap);
@@ -320,7 +323,7 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 	const Geom g = make_geom(s);
 	const EncSizes z = enc_sizes(s);
 	if (!z.single_block_ok) { err_ = "block size needs multi-block bzip2 streams (not implemented)"; return LFM_ERR_UNSUPPORTED; }
-	const size_t per_job = (size_t)z.cap * 2 + z.selcap + sizeof(DecJob) + 24;
+	const size_t per_job = (size_t)z.cap * 2 + (size_t)z.mcap * 2 + sizeof(DecJob) + 24;
 	uint64_t B = std::min<uint64_t>(count, std::max<uint64_t>(1, ((size_t)6 << 30) / per_job));
 	B = std::min<uint64_t>(B, 32768);
 	const int grid = (int)std::min<uint64_t>(B, (uint64_t)sm_count_);
@@ -328,7 +331,7 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 	if ((rc = reserve(djobs_, B * sizeof(DecJob) + 16))) return rc;
 	if ((rc = reserve(bwt_, B * z.cap))) return rc;
 	if ((rc = reserve(txt_, B * z.cap))) return rc;
-	if ((rc = reserve(sel_, B * z.selcap))) return rc;
+	if ((rc = reserve(mtfv_, B * (size_t)z.mcap * 2))) return rc;
 	if ((rc = reserve(tt_, inv_bwt_scratch_elems(grid, z.cap) * 4))) return rc;
 	if ((rc = reserve(dbegin_, count * 8))) return rc;
 	if ((rc = reserve(dend_, count * 8))) return rc;
@@ -344,8 +347,10 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 	for (uint64_t b0 = 0; b0 < count; b0 += B) {
 		const uint32_t nj = (uint32_t)std::min<uint64_t>(B, count - b0);
 		mark();
-		launch_decode(d_payload, (uint64_t*)dbegin_.p + b0, (uint64_t*)dend_.p + b0, nj, (DecJob*)djobs_.p, (uint8_t*)bwt_.p, z.cap,
-		              (uint8_t*)sel_.p, z.selcap, st);
+		uint64_t max_stream = 0;
+		for (uint64_t i = b0; i < b0 + nj; i++) max_stream = std::max(max_stream, end[i] - begin[i]);
+		if (launch_decode(d_payload, (uint64_t*)dbegin_.p + b0, (uint64_t*)dend_.p + b0, nj, (DecJob*)djobs_.p, (uint16_t*)mtfv_.p, z.mcap,
+		                  (uint8_t*)txt_.p, (uint8_t*)bwt_.p, z.cap, z.selcap, max_stream, st)) { err_ = "compressed block larger than the decoder staging area"; return LFM_ERR_UNSUPPORTED; }
 		mark();
 		launch_inv_bwt((uint8_t*)bwt_.p, z.cap, (DecJob*)djobs_.p, nj, (uint32_t*)tt_.p, (uint8_t*)txt_.p,
 		               (int)std::min<uint32_t>(nj, (uint32_t)grid), st);
@@ -353,7 +358,7 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 		launch_unrle((uint8_t*)txt_.p, z.cap, (DecJob*)djobs_.p, nj, d_sym, g, (uint64_t*)dids_.p + b0, st);
 		k_dec_status<<<(nj + 255) / 256, 256, 0, st>>>((DecJob*)djobs_.p, nj, flag);
 		mark();
-		launches += 4;
+		launches += 5;
 	}
 	uint32_t hflag = 0;
 	cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st);

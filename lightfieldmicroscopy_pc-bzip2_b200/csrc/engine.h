@@ -92,7 +92,7 @@ private:
 	void* stream_ = nullptr;
 	std::string err_;
 	// workspace
-	Buf jobs_, txt_, bwt_, mtfv_, sel_, out_, scratch_, payload_, sizes_, offs_;
+	Buf jobs_, txt_, bwt_, rank_, mtfv_, sel_, out_, scratch_, payload_, sizes_, offs_;
 	Buf djobs_, dbegin_, dend_, dids_, tt_;
 	Buf sel_sorted_, sel_hist_, sel_e_, sel_cand_;
 	uint32_t last_cap_ = 0, last_mcap_ = 0, last_njobs_ = 0;

@@ -136,7 +136,9 @@ int compress_core(const FrameSource& src, klb_image_header& h, std::vector<Shard
 		cudaSetDevice(e.device());
 		DevMem f0;
 		if (f0.alloc(L.fpx * 2)) return LFM_ERR_CUDA;
-		cudaMemcpy(f0.p, src.frame(0, L.fpx), L.fpx * 2, cudaMemcpyHostToDevice);
+		// stream-ordered copy: a default-stream cudaMemcpy from pageable memory may return before the DMA has landed,
+		// and the engine's non-blocking stream does not wait for the default stream
+		cudaMemcpyAsync(f0.p, src.frame(0, L.fpx), L.fpx * 2, cudaMemcpyHostToDevice, (cudaStream_t)e.stream());
 		double t0 = now_ms();
 		rc = e.select_mode((const uint16_t*)f0.p, desc, g_stats.entropy, &k);
 		if (rc) { g_err = e.last_error(); return rc; }
@@ -624,7 +626,7 @@ int lfmDebugEncodeBlock(const void* bytes, uint32_t n, uint8_t* rle1, uint8_t* b
 	s.Nnum = 13; s.way = 0;
 	DevMem dimg;
 	if (dimg.alloc(n)) return LFM_ERR_CUDA;
-	cudaMemcpy(dimg.p, bytes, n, cudaMemcpyHostToDevice);
+	cudaMemcpyAsync(dimg.p, bytes, n, cudaMemcpyHostToDevice, (cudaStream_t)e.stream());
 	uint32_t size = 0; const uint8_t* dpay = nullptr; uint64_t pb = 0;
 	int rc = e.compress_blocks((const uint16_t*)dimg.p, s, 0, 1, &size, &dpay, &pb, nullptr);
 	if (rc) { g_err = e.last_error(); return rc; }
@@ -635,7 +637,8 @@ int lfmDebugEncodeBlock(const void* bytes, uint32_t n, uint8_t* rle1, uint8_t* b
 	const uint32_t nblock = J[1];
 	memcpy(rle1, t.txt.data(), nblock); memcpy(bwt, t.bwt.data(), nblock);
 	memcpy(mtfv, t.mtfv.data(), (size_t)J[4] * 2);
-	cudaMemcpy(stream, dpay, pb, cudaMemcpyDeviceToHost);
+	cudaMemcpyAsync(stream, dpay, pb, cudaMemcpyDeviceToHost, (cudaStream_t)e.stream());
+	cudaStreamSynchronize((cudaStream_t)e.stream());
 	info[0] = nblock; info[1] = J[2]; info[2] = J[3]; info[3] = J[5]; info[4] = J[4]; info[5] = J[6]; info[6] = J[7]; info[7] = (uint32_t)pb;
 	return 0;
 }

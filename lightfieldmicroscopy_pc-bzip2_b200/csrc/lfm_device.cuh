@@ -40,12 +40,16 @@ struct EncJob {
 
 struct DecJob {
 	uint32_t n;            // post-RLE1 length of the bzip2 block
+	uint32_t n_mtf;        // Huffman-coded symbols incl. EOB
+	uint32_t n_in_use;
 	uint32_t orig_ptr;
 	uint32_t stored_crc;
 	uint32_t out_bytes;    // bytes produced by un-RLE1
 	uint32_t status;       // 0 ok, 1 bad magic, 2 corrupt, 3 crc mismatch, 4 unsupported (multi-block / randomised)
 	uint32_t level;
-	uint32_t cftab[257];
+	uint32_t max_block;
+	uint32_t pad[3];
+	uint32_t in_use[8];    // 256-bit symbol map of the block
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }

@@ -9,8 +9,12 @@
 //   * schedule B, row by row (H steps): predictor 2 of those two ways reads U across the tile border (first tile row
 //     of interior tiles), which makes every image column one long chain. Rows then only depend on earlier rows, plus
 //     short left-to-right chains inside the first tile column / the first image row, which one thread walks.
+#include <algorithm>
+#include <cooperative_groups.h>
 #include "lfm_device.cuh"
 #include "lfm_predict.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace lfm {
 
@@ -39,47 +43,55 @@ k_predict_fwd(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-constexpr int UP_NT = 1024;
+// Inverse predictor: ONE cooperative launch over all frames of the call. Every wavefront step handles the ready
+// pixels of all frames, spread over the whole grid; steps are separated by a grid-wide barrier. Neighbours written
+// by other SMs are read with ld.global.cg (L2), never through the non-coherent L1.
+constexpr int UP_NT = 512;
 
-__global__ void __launch_bounds__(UP_NT, 1)
+__global__ void __launch_bounds__(UP_NT, 2)
 k_unpredict(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T, int way, int k, int video,
-            uint32_t z_start, uint32_t z_step)
+            uint32_t z_start, uint32_t z_step, uint32_t nframes)
 {
+	cg::grid_group grid = cg::this_grid();
 	__shared__ uint32_t pre[512];
 	__shared__ uint32_t red[64];
 	const uint32_t tid = threadIdx.x;
-	const uint32_t z = z_start + blockIdx.x * z_step;
+	const uint64_t gtid = (uint64_t)blockIdx.x * UP_NT + tid, gsize = (uint64_t)gridDim.x * UP_NT;
 	const uint64_t fpx = (uint64_t)W * H;
-	const uint16_t* s = sym + (uint64_t)z * fpx;
-	uint16_t* o = out + (uint64_t)z * fpx;
-	const bool zflag = (video & (int)z & 1) != 0;
 	const int tilesX = (W + T - 1) / T, tilesY = (H + T - 1) / T;
 	const int nr = 2 * T - 1;                         // pixel anti-diagonals inside a tile (<= 509)
 	const int nsteps = tilesX + tilesY - 1 + nr - 1;
 
-	auto decode_px = [&](int x, int y, int tx, int ty, int u, int v) {
-		auto px = [&](int dx, int dy) { return (int)o[(size_t)(y + dy) * W + (x + dx)]; };
+	auto decode_px = [&](uint32_t f, int x, int y, int tx, int ty, int u, int v) {
+		const uint32_t z = z_start + f * z_step;
+		const uint16_t* s = sym + (uint64_t)z * fpx;
+		uint16_t* o = out + (uint64_t)z * fpx;
+		auto px = [&](int dx, int dy) { return (int)__ldcg(o + (size_t)(y + dy) * W + (x + dx)); };
 		int p = predict0(px, T, way, k, tx, ty, u, v);
-		if (zflag) {
-			int P = (int)o[(size_t)y * W + x - fpx];       // previous (even) frame, already reconstructed
+		if (video & (int)z & 1) {
+			int P = (int)__ldcg(o + (size_t)y * W + x - fpx);    // previous (even) frame, reconstructed by an earlier launch
 			p = (x == 0 && y == 0) ? P : ((p + P) >> 1);
 		}
-		o[(size_t)y * W + x] = (uint16_t)(unsymbolize16(s[(size_t)y * W + x]) + p);
+		o[(size_t)y * W + x] = (uint16_t)(unsymbolize16(__ldg(s + (size_t)y * W + x)) + p);
 	};
 
 	if (k == 2 && way != 2) {
-		// ---- schedule B: rows
+		// ---- schedule B: rows. Leading pixels with left-neighbour chains are walked by one thread per frame.
 		for (int y = 0; y < H; y++) {
 			const int ty = y / T, v = y - ty * T;
-			const int seq = (y == 0) ? W : min(T, W);        // leading pixels with left-neighbour chains: one thread
-			if (tid == 0) for (int x = 0; x < seq; x++) decode_px(x, y, x / T, ty, x % T, v);
-			for (int x = seq + (int)tid - 1; x < W; x += UP_NT - 1) if (tid > 0) decode_px(x, y, x / T, ty, x % T, v);
-			__syncthreads();
+			const int seq = (y == 0) ? W : min(T, W);
+			if (gtid < nframes) for (int x = 0; x < seq; x++) decode_px((uint32_t)gtid, x, y, x / T, ty, x % T, v);
+			const uint64_t par = (uint64_t)(W - seq) * nframes;
+			for (uint64_t i = gtid; i < par; i += gsize) {
+				uint32_t f = (uint32_t)(i / (uint32_t)(W - seq)); int x = seq + (int)(i - (uint64_t)f * (W - seq));
+				decode_px(f, x, y, x / T, ty, x % T, v);
+			}
+			grid.sync();
 		}
 		return;
 	}
 
-	// ---- schedule A: 4-D wavefront
+	// ---- schedule A: 4-D wavefront w = tx + ty + u + v
 	for (int w = 0; w < nsteps; w++) {
 		uint32_t c = 0;
 		if ((int)tid < nr) {
@@ -93,7 +105,9 @@ k_unpredict(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T
 		uint32_t total; uint32_t inc = block_scan_add<UP_NT>(c, red, &total);
 		if ((int)tid < nr) pre[tid] = inc - c;
 		__syncthreads();
-		for (uint32_t i = tid; i < total; i += UP_NT) {
+		const uint64_t all = (uint64_t)total * nframes;
+		for (uint64_t ii = gtid; ii < all; ii += gsize) {
+			const uint32_t f = (uint32_t)(ii / total), i = (uint32_t)(ii - (uint64_t)f * total);
 			int lo_r = 0, hi_r = nr - 1;                 // last r with pre[r] <= i
 			while (lo_r < hi_r) { int mid = (lo_r + hi_r + 1) >> 1; if (pre[mid] <= i) lo_r = mid; else hi_r = mid - 1; }
 			const int r = lo_r, sd = w - r;
@@ -103,9 +117,9 @@ k_unpredict(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T
 			const int tx = max(0, sd - (tilesY - 1)) + ti, ty = sd - tx;
 			const int u = max(0, r - (T - 1)) + pi, v = r - u;
 			const int x = tx * T + u, y = ty * T + v;
-			if (x < W && y < H) decode_px(x, y, tx, ty, u, v);
+			if (x < W && y < H) decode_px(f, x, y, tx, ty, u, v);
 		}
-		__syncthreads();
+		grid.sync();
 	}
 }
 
@@ -117,12 +131,24 @@ void launch_predict_fwd(const uint16_t* img, uint16_t* sym, int W, int H, int T,
 	k_predict_fwd<<<(unsigned)blocks, PF_NT, 0, st>>>(img, sym, W, H, T, way, k, video, z0, nz);
 }
 
-// frames z_start, z_start+z_step, ... (count of them); video stacks: even frames first, then odd frames
-void launch_unpredict(const uint16_t* sym, uint16_t* out, int W, int H, int T, int way, int k, int video,
-                      uint32_t z_start, uint32_t z_step, uint32_t count, cudaStream_t st)
+// frames z_start, z_start+z_step, ... (count of them); video stacks: even frames first, then odd frames.
+// Returns 0, or 1 if the cooperative launch is not possible.
+int launch_unpredict(const uint16_t* sym, uint16_t* out, int W, int H, int T, int way, int k, int video,
+                     uint32_t z_start, uint32_t z_step, uint32_t count, int sm_count, cudaStream_t st)
 {
-	if (count == 0) return;
-	k_unpredict<<<count, UP_NT, 0, st>>>(sym, out, W, H, T, way, k, video, z_start, z_step);
+	if (count == 0) return 0;
+	int per_sm = 0;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_unpredict, UP_NT, 0);
+	if (per_sm < 1) return 1;
+	const int max_grid = per_sm * sm_count;
+	const int tilesX = (W + T - 1) / T, tilesY = (H + T - 1) / T;
+	const uint64_t steps = (k == 2 && way != 2) ? (uint64_t)H : (uint64_t)(tilesX + tilesY + 2 * T);
+	uint64_t per_step = ((uint64_t)W * H * count + steps - 1) / steps;            // mean ready pixels per step
+	uint64_t want = (per_step + UP_NT - 1) / UP_NT;                                // about one pixel per thread per step
+	int grid = (int)std::min<uint64_t>((uint64_t)max_grid, std::max<uint64_t>(1, want));
+	void* args[] = { (void*)&sym, (void*)&out, (void*)&W, (void*)&H, (void*)&T, (void*)&way, (void*)&k, (void*)&video,
+	                 (void*)&z_start, (void*)&z_step, (void*)&count };
+	return cudaLaunchCooperativeKernel((void*)k_unpredict, dim3(grid), dim3(UP_NT), args, 0, st) == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace lfm
