@@ -455,52 +455,143 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 }
 
 // =====================================================================================================
-// k_unrle : one warp per block, lane 0 (v1)
+// k_unrle : one CTA per block -- inverse of bzip2's initial run-length coding, CRC check, scatter into the image.
+// The decoder is a 5-state machine (state = equal bytes seen in a row, 4 = "next byte is a repeat count",
+// 0 = fresh start; bzlib.c:561-728).  Parallel form:
+//   1. thread t runs the machine over its chunk of the text for all 5 possible entry states -> (exit state, bytes out);
+//   2. the entry state and output offset of every chunk follow from composing those maps in chunk order;
+//   3. thread t replays its chunk from the now known entry state, writing into a staging copy of the block
+//      (shared memory; the block's dead BWT slot when it does not fit);
+//   4. CRC-32 of the staged block: per-chunk table CRC + binary tree of carry-less multiplications (as in k_rle1);
+//   5. rows are copied to the symbol image, one warp per row.
 // =====================================================================================================
-constexpr int UR_NT = 128;
+constexpr int UR_NT = 256;
+
+__device__ __forceinline__ uint32_t ur_mulmod(uint32_t a, uint32_t b)
+{
+	uint32_t r = 0;
+	#pragma unroll 8
+	for (int i = 31; i >= 0; i--) {
+		r = (r << 1) ^ ((r & 0x80000000u) ? 0x04C11DB7u : 0u);
+		if ((b >> i) & 1u) r ^= a;
+	}
+	return r;
+}
+__device__ __forceinline__ uint32_t ur_xpow8(uint32_t nbytes)
+{
+	uint32_t e = nbytes * 8u, r = 1u;
+	for (int i = 31 - __clz(e | 1u); i >= 0; i--) {
+		r = ur_mulmod(r, r);
+		if ((e >> i) & 1u) r = (r << 1) ^ ((r & 0x80000000u) ? 0x04C11DB7u : 0u);
+	}
+	return r;
+}
+
+extern __shared__ __align__(16) uint8_t ur_smem[];
+
 __global__ void __launch_bounds__(UR_NT)
-k_unrle(const uint8_t* __restrict__ txt_all, uint32_t cap, DecJob* __restrict__ jobs, uint32_t njobs,
-        uint16_t* __restrict__ sym, Geom g, const uint64_t* __restrict__ block_ids)
+k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* = BWT slots, dead by now */, uint32_t cap,
+        DecJob* __restrict__ jobs, uint32_t njobs, uint16_t* __restrict__ sym, Geom g, const uint64_t* __restrict__ block_ids,
+        int stage_in_smem)
 {
 	__shared__ uint32_t crc_tab[256];
-	for (uint32_t i = threadIdx.x; i < 256; i += UR_NT) crc_tab[i] = crc_table_entry(i);
-	__syncthreads();
-	uint32_t job = blockIdx.x * (UR_NT / 32) + warp_id();
-	if (job >= njobs || lane_id() != 0) return;
+	__shared__ uint32_t s_fn[UR_NT];          // packed transition map of each chunk: 5 x 3 bits
+	__shared__ uint32_t s_cnt[UR_NT][5];      // bytes produced by each chunk for each entry state
+	__shared__ uint32_t s_in[UR_NT], s_off[UR_NT];
+	__shared__ uint32_t s_crc[UR_NT];
+	__shared__ uint32_t s_total;
+	const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+	const uint32_t job = blockIdx.x;
+	if (job >= njobs) return;
 	DecJob& J = jobs[job];
 	if (J.status != 0) return;
+	crc_tab[tid] = crc_table_entry(tid);
 	const uint8_t* txt = txt_all + (size_t)job * cap;
 	const uint32_t n = J.n;
 	uint32_t c0[5], ext[5];
 	block_box(g, block_ids[job], c0, ext);
-	const uint32_t row_bytes = ext[0] * 2;
-	const uint64_t total = (uint64_t)row_bytes * ext[1] * ext[2] * ext[3] * ext[4];
-	uint32_t y = 0, z = 0, c = 0, t = 0, xb = 0;           // position of the next output byte
-	uint16_t* row = sym + (c0[0] + (uint64_t)c0[1] * g.stride[1] + (uint64_t)c0[2] * g.stride[2] + (uint64_t)c0[3] * g.stride[3] + (uint64_t)c0[4] * g.stride[4]);
-	uint64_t produced = 0; uint32_t lo = 0, crc = 0xFFFFFFFFu;
-	bool overflow = false;
-	auto emit = [&](uint32_t b) {
-		if (produced >= total) { overflow = true; return; }
-		crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ b];
-		if (xb & 1) row[xb >> 1] = (uint16_t)(lo | (b << 8)); else lo = b;
-		xb++; produced++;
-		if (xb == row_bytes) {
-			xb = 0;
-			if (++y == ext[1]) { y = 0; if (++z == ext[2]) { z = 0; if (++c == ext[3]) { c = 0; ++t; } } }
-			row = sym + (c0[0] + (uint64_t)(c0[1] + y) * g.stride[1] + (uint64_t)(c0[2] + z) * g.stride[2]
-			             + (uint64_t)(c0[3] + c) * g.stride[3] + (uint64_t)(c0[4] + t) * g.stride[4]);
+	const uint32_t rows = ext[1] * ext[2] * ext[3] * ext[4], rowpx = ext[0];
+	const uint32_t gcount = rows * rowpx * 2;
+	uint8_t* stage = stage_in_smem ? ur_smem : stage_all + (size_t)job * cap;
+
+	// ---- 1. chunk maps
+	const uint32_t CH = (n + UR_NT - 1) / UR_NT;
+	const uint32_t a0 = min(n, tid * CH), a1 = min(n, a0 + CH);
+	{
+		// all five entry states in one pass over the chunk (each byte is loaded once)
+		uint32_t st[5] = { 0, 1, 2, 3, 4 }, cn[5] = { 0, 0, 0, 0, 0 };
+		uint32_t prev = a0 > 0 ? txt[a0 - 1] : 0x100u;
+		for (uint32_t i = a0; i < a1; i++) {
+			const uint32_t ch = txt[i];
+			const bool eq = (ch == prev);
+			#pragma unroll
+			for (int m = 0; m < 5; m++) {
+				if (st[m] == 4) { cn[m] += ch; st[m] = 0; }
+				else { st[m] = (st[m] >= 1 && eq) ? st[m] + 1 : 1; cn[m]++; }
+			}
+			prev = ch;
 		}
-	};
-	int prev = -1; uint32_t cnt = 0;
-	for (uint32_t i = 0; i < n; i++) {
-		uint32_t ch = txt[i];
-		if (cnt == 4) { for (uint32_t k = 0; k < ch; k++) emit((uint32_t)prev); cnt = 0; prev = -1; continue; }
-		if ((int)ch == prev) cnt++; else { prev = (int)ch; cnt = 1; }
-		emit(ch);
+		uint32_t fn = 0;
+		#pragma unroll
+		for (int m = 0; m < 5; m++) { fn |= st[m] << (3 * m); s_cnt[tid][m] = cn[m]; }
+		s_fn[tid] = fn;
 	}
-	J.out_bytes = (uint32_t)produced;
-	if (overflow || produced != total) J.status = 2;
-	else if (~crc != J.stored_crc) J.status = 3;
+	__syncthreads();
+	// ---- 2. entry state / output offset of every chunk
+	if (tid == 0) {
+		uint32_t st = 0, off = 0;
+		for (uint32_t t = 0; t < UR_NT; t++) {
+			s_in[t] = st; s_off[t] = off;
+			off += s_cnt[t][st];
+			st = (s_fn[t] >> (3 * st)) & 7u;
+		}
+		s_total = off;
+	}
+	__syncthreads();
+	if (s_total != gcount) { if (tid == 0) { J.status = 2; J.out_bytes = s_total; } return; }
+	// ---- 3. replay into the staging copy
+	{
+		uint32_t st = s_in[tid], o = s_off[tid];
+		for (uint32_t i = a0; i < a1; i++) {
+			const uint32_t ch = txt[i];
+			if (st == 4) { const uint32_t pv = txt[i - 1]; for (uint32_t k = 0; k < ch; k++) stage[o + k] = (uint8_t)pv; o += ch; st = 0; }
+			else { st = (st >= 1 && i > 0 && ch == txt[i - 1]) ? st + 1 : 1; stage[o++] = (uint8_t)ch; }
+		}
+	}
+	__syncthreads();
+	// ---- 4. CRC of the staged block (chunks right aligned: only the first non-empty one is short)
+	{
+		uint32_t CC = ((gcount + UR_NT - 1) / UR_NT + 3) & ~3u;
+		if (((CC >> 2) & 1u) == 0) CC += 4;
+		const uint32_t after = (UR_NT - 1 - tid) * CC;
+		const uint32_t e1 = gcount > after ? gcount - after : 0;
+		const uint32_t e0 = e1 > CC ? e1 - CC : 0;
+		uint32_t crc = 0;
+		if (e1 > e0) {
+			crc = (e0 == 0) ? 0xFFFFFFFFu : 0u;
+			for (uint32_t j = e0; j < e1; j++) crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ stage[j]];
+		}
+		s_crc[tid] = crc;
+		__syncthreads();
+		uint32_t M = ur_xpow8(CC);
+		for (uint32_t stride = 1; stride < UR_NT; stride <<= 1) {
+			if ((tid & (2 * stride - 1)) == 0) s_crc[tid] = ur_mulmod(s_crc[tid], M) ^ s_crc[tid + stride];
+			M = ur_mulmod(M, M);
+			__syncthreads();
+		}
+	}
+	if (~s_crc[0] != J.stored_crc) { if (tid == 0) J.status = 3; return; }
+	// ---- 5. scatter rows into the image
+	for (uint32_t r = wid; r < rows; r += UR_NT / 32) {
+		uint32_t y = r % ext[1], q = r / ext[1];
+		uint32_t z = q % ext[2]; q /= ext[2];
+		uint32_t c = q % ext[3], t = q / ext[3];
+		uint16_t* row = sym + (c0[0] + (uint64_t)(c0[1] + y) * g.stride[1] + (uint64_t)(c0[2] + z) * g.stride[2]
+		                       + (uint64_t)(c0[3] + c) * g.stride[3] + (uint64_t)(c0[4] + t) * g.stride[4]);
+		const uint16_t* srcrow = reinterpret_cast<const uint16_t*>(stage) + (size_t)r * rowpx;
+		for (uint32_t x = lane; x < rowpx; x += 32) row[x] = srcrow[x];
+	}
+	if (tid == 0) J.out_bytes = gcount;
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -527,11 +618,13 @@ void launch_inv_bwt(const uint8_t* bwt, uint32_t cap, DecJob* jobs, uint32_t njo
 {
 	k_inv_bwt<<<grid, BWT_NT, 0, st>>>(bwt, cap, jobs, njobs, tt_scratch, txt);
 }
-void launch_unrle(const uint8_t* txt, uint32_t cap, DecJob* jobs, uint32_t njobs, uint16_t* sym, const Geom& g,
-                  const uint64_t* block_ids, cudaStream_t st)
+void launch_unrle(const uint8_t* txt, uint8_t* stage_scratch, uint32_t cap, uint32_t max_raw_bytes, DecJob* jobs, uint32_t njobs,
+                  uint16_t* sym, const Geom& g, const uint64_t* block_ids, cudaStream_t st)
 {
-	uint32_t per = UR_NT / 32;
-	k_unrle<<<(njobs + per - 1) / per, UR_NT, 0, st>>>(txt, cap, jobs, njobs, sym, g, block_ids);
+	const int in_smem = max_raw_bytes + 16 <= 200 * 1024;
+	const size_t smem = in_smem ? (size_t)max_raw_bytes + 16 : 0;
+	cudaFuncSetAttribute(k_unrle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	k_unrle<<<njobs, UR_NT, smem, st>>>(txt, stage_scratch, cap, jobs, njobs, sym, g, block_ids, in_smem);
 }
 
 }  // namespace lfm

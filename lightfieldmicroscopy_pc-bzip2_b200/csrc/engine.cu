@@ -323,6 +323,7 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 	const Geom g = make_geom(s);
 	const EncSizes z = enc_sizes(s);
 	if (!z.single_block_ok) { err_ = "block size needs multi-block bzip2 streams (not implemented)"; return LFM_ERR_UNSUPPORTED; }
+	uint64_t blockBytes = 2; for (int i = 0; i < 5; i++) blockBytes *= s.blockSize[i];
 	const size_t per_job = (size_t)z.cap * 2 + (size_t)z.mcap * 2 + sizeof(DecJob) + 24;
 	uint64_t B = std::min<uint64_t>(count, std::max<uint64_t>(1, ((size_t)6 << 30) / per_job));
 	B = std::min<uint64_t>(B, 32768);
@@ -355,7 +356,7 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 		launch_inv_bwt((uint8_t*)bwt_.p, z.cap, (DecJob*)djobs_.p, nj, (uint32_t*)tt_.p, (uint8_t*)txt_.p,
 		               (int)std::min<uint32_t>(nj, (uint32_t)grid), st);
 		mark();
-		launch_unrle((uint8_t*)txt_.p, z.cap, (DecJob*)djobs_.p, nj, d_sym, g, (uint64_t*)dids_.p + b0, st);
+		launch_unrle((uint8_t*)txt_.p, (uint8_t*)bwt_.p, z.cap, (uint32_t)blockBytes, (DecJob*)djobs_.p, nj, d_sym, g, (uint64_t*)dids_.p + b0, st);
 		k_dec_status<<<(nj + 255) / 256, 256, 0, st>>>((DecJob*)djobs_.p, nj, flag);
 		mark();
 		launches += 5;
