@@ -35,17 +35,19 @@ struct DecWarpSmem {
 	int32_t  minlen[kGroups];
 };
 
+constexpr uint32_t DEC_RING = 256;               // staged stream words per warp (power of two)
+
 extern __shared__ __align__(16) uint8_t dec_smem[];
 
 __global__ void __launch_bounds__(128)
 k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ begin, const uint64_t* __restrict__ end,
               uint32_t njobs, DecJob* __restrict__ jobs, uint16_t* __restrict__ mtfv_all, uint32_t mcap, uint32_t cap,
-              uint32_t selcap, uint32_t stream_words /* per-warp staging capacity */)
+              uint32_t selcap)
 {
 	const uint32_t lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
 	const uint32_t job = blockIdx.x * nw + w;
 	if (job >= njobs) return;
-	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)stream_words * 4;
+	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)DEC_RING * 4;
 	DecWarpSmem& S = *reinterpret_cast<DecWarpSmem*>(dec_smem + (size_t)w * per_warp);
 	uint8_t* selector = dec_smem + (size_t)w * per_warp + sizeof(DecWarpSmem);
 	uint32_t* sw = reinterpret_cast<uint32_t*>(selector + selcap);
@@ -56,41 +58,37 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	#define FAIL(code) do { if (lane == 0) { J.status = (code); J.n = 0; J.n_mtf = 0; } return; } while (0)
 	if (lane == 0) { J.n = 0; J.n_mtf = 0; J.out_bytes = 0; J.orig_ptr = 0; J.stored_crc = 0; J.status = 0; }
 
-	// ---- stage the stream: word i = bytes 4i..4i+3, big endian; bytes past the end read as 0
+	// ---- the stream is staged through a ring of big-endian words: word i = bytes 4i..4i+3, zero past the end
 	const uint32_t nwords = (uint32_t)((nbytes + 3) / 4);
-	if (nwords + 3 > stream_words) FAIL(4);              // host sizes the staging area from the largest stream
-	{
-		const uint32_t mis = (uint32_t)((uintptr_t)src & 3);
-		const uint32_t* a32 = reinterpret_cast<const uint32_t*>(src - mis);   // payload base is 256-byte aligned: never below it
-		for (uint32_t i = lane; i < nwords + 3; i += 32) {
-			const uint64_t b0 = (uint64_t)i * 4;
-			uint32_t v = 0;
-			if (b0 + 8 <= nbytes) {                       // bulk: two aligned words cover stream bytes 4i .. 4i+3
-				uint32_t lo = a32[i], hi = a32[i + 1];
-				v = mis ? __funnelshift_r(lo, hi, mis * 8) : lo;
-				v = __byte_perm(v, 0, 0x0123);
-			} else {                                      // tail: byte by byte, zero past the end
-				#pragma unroll
-				for (int k = 0; k < 4; k++) v = (v << 8) | (b0 + k < nbytes ? (uint32_t)src[b0 + k] : 0u);
-			}
-			sw[i] = v;
+	const uint32_t mis = (uint32_t)((uintptr_t)src & 3);
+	const uint32_t* a32 = reinterpret_cast<const uint32_t*>(src - mis);       // payload base is 256-byte aligned: never below it
+	auto load_word = [&](uint32_t i) -> uint32_t {
+		const uint64_t b0 = (uint64_t)i * 4;
+		uint32_t v = 0;
+		if (b0 + 8 <= nbytes) {                           // bulk: two aligned words cover stream bytes 4i .. 4i+3
+			uint32_t lo = a32[i], hi = a32[i + 1];
+			v = mis ? __funnelshift_r(lo, hi, mis * 8) : lo;
+			v = __byte_perm(v, 0, 0x0123);
+		} else if (b0 < nbytes) {                         // tail: byte by byte
+			#pragma unroll
+			for (int k = 0; k < 4; k++) v = (v << 8) | (b0 + k < nbytes ? (uint32_t)src[b0 + k] : 0u);
 		}
-	}
-	__syncwarp();
+		return v;
+	};
+	uint32_t staged_end = 0, wi = 0;                       // words [wi, staged_end) are in the ring, not yet consumed
+	auto top_up = [&]() {                                  // uniform; never overwrites an unconsumed word
+		while (staged_end + 32 <= wi + DEC_RING) { sw[(staged_end + lane) & (DEC_RING - 1)] = load_word(staged_end + lane); staged_end += 32; }
+		__syncwarp();
+	};
+	top_up();
 
-	// ---- uniform bit reader: bb holds bc >= 32 valid bits, left aligned; wi = next word to load
+	// ---- uniform bit reader: bb holds bc >= 32 valid bits, left aligned; wi = next word to pull from the ring
 	uint64_t bb = ((uint64_t)sw[0] << 32) | sw[1];
-	uint32_t bc = 64, wi = 2;
-	const uint32_t wi_limit = nwords + 3;
-	bool overrun = false;
-	auto drop = [&](uint32_t nb) {                        // nb <= 32
+	uint32_t bc = 64; wi = 2;
+	const uint32_t wi_limit = nwords + 4;                  // a well-formed stream never needs words beyond this
+	auto drop = [&](uint32_t nb) {                         // nb <= 32
 		bb <<= nb; bc -= nb;
-		if (bc < 32) {
-			uint32_t v = 0;
-			if (wi < wi_limit) v = sw[wi]; else overrun = true;
-			wi++;
-			bb |= (uint64_t)v << (32 - bc); bc += 32;
-		}
+		if (bc < 32) { bb |= (uint64_t)sw[wi & (DEC_RING - 1)] << (32 - bc); bc += 32; wi++; }
 	};
 	auto peek = [&](uint32_t nb) -> uint32_t { return (uint32_t)(bb >> (64 - nb)); };
 	auto get = [&](uint32_t nb) -> uint32_t { uint32_t v = peek(nb); drop(nb); return v; };
@@ -125,6 +123,7 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	{
 		uint32_t pos = 0x543210u;                          // 6 nibbles: move-to-front list of table ids
 		for (int i = 0; i < n_sel; i++) {
+			if ((i & 63) == 0) { top_up(); if (wi > wi_limit) FAIL(2); }
 			uint32_t v = peek(6);                          // unary: count leading ones (at most n_groups-1)
 			int j = __clz(~(v << 26));
 			if (j >= n_groups) FAIL(2);
@@ -133,12 +132,12 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 			uint32_t lowmask = (1u << (4 * j)) - 1u;
 			pos = (pos & ~((lowmask << 4) | 15u)) | ((pos & lowmask) << 4) | t;
 			if (lane == 0) selector[i] = (uint8_t)t;
-			if (overrun) FAIL(2);
 		}
 	}
 	for (int t = 0; t < n_groups; t++) {
 		int curr = (int)get(5);
 		for (int i = 0; i < alpha; i++) {
+			if ((i & 15) == 0) { top_up(); if (wi > wi_limit) FAIL(2); }
 			for (;;) {
 				if (curr < 1 || curr > 20) FAIL(2);
 				uint32_t two = peek(2);
@@ -148,7 +147,6 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 			}
 			if (lane == 0) S.len[t][i] = (uint8_t)curr;
 		}
-		if (overrun) FAIL(2);
 	}
 	__syncwarp();
 	// ---- decode tables: lane t builds table t (huffman.c:170-205 + the lookup)
@@ -183,41 +181,45 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 		S.minlen[t] = mn;
 	}
 	__syncwarp();
+	top_up();
 
-	// ---- symbols (decompress.c:349-487 without the MTF): append until EOB
+	// ---- symbols (decompress.c:349-487 without the MTF): append until EOB. One lookup per symbol; the rare events
+	// (code longer than DEC_LB bits, 32-symbol flush + ring top-up, next selector) stay off the common path.
 	const uint32_t EOB = n_in_use + 1;
 	uint32_t nsym = 0, obuf = 0;
-	int grp = 0, left = kGSize, t = selector[0];
-	if (t >= n_groups) FAIL(2);
-	const uint16_t* lut = S.lut[t];
-	for (;;) {
-		uint32_t sym;
-		const uint32_t e = lut[(uint32_t)(bb >> (64 - DEC_LB))];
-		if (e) { sym = e & 511u; drop(e >> 9); }
-		else {
-			const uint32_t window = peek(20);
-			const int32_t* limit = S.limit[t]; const int32_t* base = S.base[t];
-			int zn = S.minlen[t]; int32_t zvec = (int32_t)(window >> (20 - zn));
-			for (;;) {
-				if (zn > 20) FAIL(2);
-				if (zvec <= limit[zn]) break;
-				zn++;
-				if (zn <= 20) zvec = (int32_t)(window >> (20 - zn));
+	bool done = false;
+	for (int grp = 0; !done; grp++) {
+		if (grp >= n_sel) FAIL(2);
+		const int t = selector[grp];
+		if (t >= n_groups) FAIL(2);
+		const uint16_t* lut = S.lut[t];
+		#pragma unroll 1
+		for (int k = 0; k < kGSize; k++) {
+			uint32_t e = lut[(uint32_t)(bb >> (64 - DEC_LB))];
+			if (e == 0) {
+				const uint32_t window = peek(20);
+				const int32_t* limit = S.limit[t]; const int32_t* base = S.base[t];
+				int zn = S.minlen[t]; int32_t zvec = (int32_t)(window >> (20 - zn));
+				for (;;) {
+					if (zn > 20) FAIL(2);
+					if (zvec <= limit[zn]) break;
+					zn++;
+					if (zn <= 20) zvec = (int32_t)(window >> (20 - zn));
+				}
+				int32_t idx = zvec - base[zn];
+				if (idx < 0 || idx >= kMaxAlpha) FAIL(2);
+				e = (uint32_t)S.perm[t][idx] | ((uint32_t)zn << 9);
 			}
-			drop((uint32_t)zn);
-			int32_t idx = zvec - base[zn];
-			if (idx < 0 || idx >= kMaxAlpha) FAIL(2);
-			sym = S.perm[t][idx];
-		}
-		if (lane == (nsym & 31u)) obuf = sym;
-		nsym++;
-		if ((nsym & 31u) == 0) mtfv[nsym - 32 + lane] = (uint16_t)obuf;
-		if (sym == EOB) break;
-		if (nsym >= mcap || overrun) FAIL(2);
-		if (--left == 0) {
-			grp++; if (grp >= n_sel) FAIL(2);
-			left = kGSize; t = selector[grp]; if (t >= n_groups) FAIL(2);
-			lut = S.lut[t];
+			const uint32_t sym = e & 511u;
+			drop(e >> 9);
+			if (lane == (nsym & 31u)) obuf = sym;
+			nsym++;
+			if ((nsym & 31u) == 0) {
+				mtfv[nsym - 32 + lane] = (uint16_t)obuf;
+				if (nsym + 32 >= mcap || wi > wi_limit) FAIL(2);
+				top_up();
+			}
+			if (sym == EOB) { done = true; break; }
 		}
 	}
 	if (nsym & 31u) { if (lane < (nsym & 31u)) mtfv[(nsym & ~31u) + lane] = (uint16_t)obuf; }
@@ -226,6 +228,7 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	if (e1 == 0x314159 && e2 == 0x265359) FAIL(4);            // multi-block stream: not supported in this version
 	if (e1 != 0x177245 || e2 != 0x385090) FAIL(2);
 	if (get(32) != stored_crc) FAIL(3);
+	if (wi > wi_limit) FAIL(2);
 	if (lane == 0) {
 		J.n_mtf = nsym; J.n_in_use = n_in_use; J.orig_ptr = orig_ptr; J.stored_crc = stored_crc; J.level = (uint32_t)level; J.status = 0;
 		J.max_block = max_block;
@@ -595,18 +598,15 @@ k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* 
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-// max_stream_bytes: the largest (end - begin) in the batch; sizes the per-warp staging area
 int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t* end, uint32_t njobs, DecJob* jobs,
-                  uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap,
-                  uint64_t max_stream_bytes, cudaStream_t st)
+                  uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap, cudaStream_t st)
 {
-	const uint32_t stream_words = (uint32_t)((max_stream_bytes + 3) / 4 + 4);   // + zero words the bit buffer may prefetch
-	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)stream_words * 4;
+	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)DEC_RING * 4;
 	int nw = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
-	if (nw < 1) return 1;                                   // a single stream larger than shared memory
+	if (nw < 1) return 1;
 	const size_t smem = per_warp * nw;
 	cudaFuncSetAttribute(k_huff_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	k_huff_decode<<<(njobs + nw - 1) / nw, nw * 32, smem, st>>>(payload, begin, end, njobs, jobs, mtfv, mcap, cap, selcap, stream_words);
+	k_huff_decode<<<(njobs + nw - 1) / nw, nw * 32, smem, st>>>(payload, begin, end, njobs, jobs, mtfv, mcap, cap, selcap);
 	const size_t smem2 = imtf_smem_bytes();
 	cudaFuncSetAttribute(k_imtf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
 	k_imtf<<<njobs, IM_NT, smem2, st>>>(mtfv, mcap, jobs, njobs, q_scratch, bwt, cap);

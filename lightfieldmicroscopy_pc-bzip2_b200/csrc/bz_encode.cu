@@ -366,66 +366,84 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 size_t mtf_smem_bytes() { return (size_t)256 * MTF_RLS + (size_t)64 * MTF_STS * 4 + 8 * MTF_NT * 4 + (MTF_NT * 2 + 64) * 4 + 512; }
 
 // =====================================================================================================
-// k_huff_pack : one CTA per block
+// k_huff_pack : one CTA (8 warps) per block; warp t owns coding table t.
+//   * symbol histogram, number of tables, initial partition                      (compress.c:268-316)
+//   * 4 refinement passes: cost of every 50-symbol group under every table in parallel over the groups, then
+//     exact bzip2 code lengths per table: lane 0 of the table's warp runs the heap with (weight, node) packed in one
+//     64-bit shared-memory word -- one load per heap level -- and the 32 lanes walk the parent links (huffman.c:63-148)
+//   * canonical codes by a warp counting pass                                     (huffman.c:152-166)
+//   * the bit stream: every field's length is known before anything is written, so offsets come from scans and all
+//     threads OR their bits into the zeroed output (selectors, delta-coded lengths, symbols)  (compress.c:482-600)
 // =====================================================================================================
 constexpr int HP_NT = 256;
 constexpr int HP_SYMS = 8;     // symbols per thread per packing tile
+constexpr uint16_t HP_NOPARENT = 0xFFFFu;
 
-// exact restatement of BZ2_hbMakeCodeLengths (huffman.c:63-148): same heap, same tie rules, same rescale loop
-__device__ void make_code_lengths(uint8_t* len, const uint32_t* freq, int alpha, int max_len,
-                                  int32_t* heap, int32_t* weight, int32_t* parent)
+__device__ __forceinline__ uint32_t hp_hi(uint64_t e) { return (uint32_t)(e >> 32); }
+
+// exact restatement of BZ2_hbMakeCodeLengths: same heap discipline (strict '<' everywhere), same weight arithmetic,
+// same rescale loop.  Warp-cooperative: call with all 32 lanes.
+__device__ void make_code_lengths_warp(uint8_t* len, const uint32_t* freq, int alpha, int max_len,
+                                       uint64_t* heap, uint16_t* parent, uint32_t* lw, uint32_t lane)
 {
-	for (int i = 0; i < alpha; i++) weight[i + 1] = (int32_t)((freq[i] == 0 ? 1u : freq[i]) << 8);
+	for (int i = (int)lane; i < alpha; i += 32) lw[i + 1] = (freq[i] == 0 ? 1u : freq[i]) << 8;
+	__syncwarp();
 	for (;;) {
-		int n_nodes = alpha, n_heap = 0;
-		heap[0] = 0; weight[0] = 0; parent[0] = -2;
-		for (int i = 1; i <= alpha; i++) {
-			parent[i] = -1;
-			int z = ++n_heap, t = i;
-			int32_t wt = weight[t];
-			while (wt < weight[heap[z >> 1]]) { heap[z] = heap[z >> 1]; z >>= 1; }
-			heap[z] = t;
-		}
-		while (n_heap > 1) {
-			int pick[2];
-			#pragma unroll
-			for (int q = 0; q < 2; q++) {
-				pick[q] = heap[1]; heap[1] = heap[n_heap--];
-				int z = 1, t = heap[1];
-				int32_t wt = weight[t];
-				for (;;) {
-					int y = z << 1;
-					if (y > n_heap) break;
-					if (y < n_heap && weight[heap[y + 1]] < weight[heap[y]]) y++;
-					if (wt < weight[heap[y]]) break;
-					heap[z] = heap[y]; z = y;
-				}
-				heap[z] = t;
+		if (lane == 0) {
+			int n_nodes = alpha, n_heap = 0;
+			heap[0] = 0;                                   // weight 0 sentinel: every up-heap stops here
+			for (int i = 1; i <= alpha; i++) {
+				parent[i] = HP_NOPARENT;
+				const uint32_t wt = lw[i];
+				int z = ++n_heap;
+				for (;;) { const uint64_t up = heap[z >> 1]; if (!(wt < hp_hi(up))) break; heap[z] = up; z >>= 1; }
+				heap[z] = ((uint64_t)wt << 32) | (uint32_t)i;
 			}
-			n_nodes++;
-			parent[pick[0]] = parent[pick[1]] = n_nodes;
-			uint32_t w1 = (uint32_t)weight[pick[0]], w2 = (uint32_t)weight[pick[1]];
-			uint32_t d1 = w1 & 0xffu, d2 = w2 & 0xffu;
-			int32_t nw = (int32_t)(((w1 & 0xffffff00u) + (w2 & 0xffffff00u)) | (1u + (d1 > d2 ? d1 : d2)));
-			weight[n_nodes] = nw;
-			parent[n_nodes] = -1;
-			int z = ++n_heap;
-			while (nw < weight[heap[z >> 1]]) { heap[z] = heap[z >> 1]; z >>= 1; }
-			heap[z] = n_nodes;
+			while (n_heap > 1) {
+				uint64_t pick[2];
+				#pragma unroll
+				for (int q = 0; q < 2; q++) {
+					pick[q] = heap[1];
+					const uint64_t tmp = heap[n_heap--];
+					const uint32_t tw = hp_hi(tmp);
+					int z = 1;
+					for (;;) {
+						int y = z << 1;
+						if (y > n_heap) break;
+						uint64_t c = heap[y];
+						if (y < n_heap) { const uint64_t c1 = heap[y + 1]; if (hp_hi(c1) < hp_hi(c)) { c = c1; y++; } }
+						if (tw < hp_hi(c)) break;
+						heap[z] = c; z = y;
+					}
+					heap[z] = tmp;
+				}
+				n_nodes++;
+				parent[(uint32_t)pick[0]] = (uint16_t)n_nodes; parent[(uint32_t)pick[1]] = (uint16_t)n_nodes;
+				const uint32_t w1 = hp_hi(pick[0]), w2 = hp_hi(pick[1]);
+				const uint32_t d1 = w1 & 0xffu, d2 = w2 & 0xffu;
+				const uint32_t nwt = ((w1 & 0xffffff00u) + (w2 & 0xffffff00u)) | (1u + (d1 > d2 ? d1 : d2));
+				parent[n_nodes] = HP_NOPARENT;
+				int z = ++n_heap;
+				for (;;) { const uint64_t up = heap[z >> 1]; if (!(nwt < hp_hi(up))) break; heap[z] = up; z >>= 1; }
+				heap[z] = ((uint64_t)nwt << 32) | (uint32_t)n_nodes;
+			}
 		}
+		__syncwarp();
 		bool too_long = false;
-		for (int i = 1; i <= alpha; i++) {
+		for (int i = (int)lane + 1; i <= alpha; i += 32) {
 			int j = 0, k = i;
-			while (parent[k] >= 0) { k = parent[k]; j++; }
+			while (parent[k] != HP_NOPARENT) { k = parent[k]; j++; }
 			len[i - 1] = (uint8_t)j;
 			if (j > max_len) too_long = true;
 		}
-		if (!too_long) break;
-		for (int i = 1; i <= alpha; i++) { int j = weight[i] >> 8; j = 1 + (j / 2); weight[i] = j << 8; }
+		if (!__any_sync(0xffffffffu, too_long)) break;
+		for (int i = (int)lane + 1; i <= alpha; i += 32) { uint32_t j = lw[i] >> 8; j = 1 + (j / 2); lw[i] = j << 8; }
+		__syncwarp();
 	}
+	__syncwarp();
 }
 
-// sequential MSB-first bit writer used by thread 0 for the block header (whole 32-bit words, big-endian)
+// sequential MSB-first bit writer used by thread 0 for the fixed part of the block header (whole big-endian words)
 struct HdrWriter {
 	uint32_t* out; uint64_t acc; uint32_t live; uint32_t words;
 	__device__ void put(uint32_t nbits, uint32_t v) {
@@ -459,22 +477,24 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 	__shared__ uint32_t rfreq[kGroups][kMaxAlpha + 2];
 	__shared__ uint8_t  len[kGroups][kMaxAlpha + 2];
 	__shared__ uint32_t code[kGroups][kMaxAlpha + 2];
-	__shared__ int32_t  hheap[kGroups][kMaxAlpha + 2];
-	__shared__ int32_t  hweight[kGroups][kMaxAlpha * 2];
-	__shared__ int32_t  hparent[kGroups][kMaxAlpha * 2];
+	__shared__ __align__(16) uint64_t hheap[kGroups][kMaxAlpha + 6];
+	__shared__ uint16_t hparent[kGroups][kMaxAlpha * 2 + 4];
+	__shared__ uint32_t hlw[kGroups][kMaxAlpha + 2];
 	__shared__ uint32_t red[64];
-	uint32_t* win = reinterpret_cast<uint32_t*>(&hweight[0][0]);   // packing window; reused once the tables are final
-	static_assert(sizeof(hweight) >= (HP_NT * HP_SYMS * 20 / 32 + 4) * 4, "window must fit");
-	__shared__ uint32_t s_hdr_bits, s_ngroups;
+	__shared__ uint32_t s_tbits[kGroups + 2];
+	__shared__ uint32_t s_ngroups;
+	uint32_t* win = reinterpret_cast<uint32_t*>(&hheap[0][0]);     // packing window; reused once the tables are final
+	static_assert(sizeof(hheap) >= (HP_NT * HP_SYMS * 20 / 32 + 4) * 4, "window must fit");
 
-	const uint32_t tid = threadIdx.x;
+	const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
 	const uint32_t job = blockIdx.x;
 	if (job >= njobs) return;
 	EncJob& J = jobs[job];
 	const uint32_t n_mtf = J.n_mtf, n_in_use = J.n_in_use;
 	const int alpha = (int)n_in_use + 2;
 	const uint16_t* mtfv = mtfv_all + (size_t)job * mcap;
-	uint8_t* selector = sel_all + (size_t)job * selcap;
+	uint8_t* selector = sel_all + (size_t)job * selcap * 2;          // [selcap] table ids, then [selcap] their MTF codes
+	uint8_t* selmtf = selector + selcap;
 	uint32_t* out = reinterpret_cast<uint32_t*>(out_all + (size_t)job * ocap);
 
 	if (J.n == 0) {     // empty input: stream header + trailer only (compress.c:603-676 with nblock == 0)
@@ -504,12 +524,18 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 			int target = rem / n_part, ge = gs - 1, acc = 0;
 			while (acc < target && ge < alpha - 1) { ge++; acc += (int)freq[ge]; }
 			if (ge > gs && n_part != ng && n_part != 1 && ((ng - n_part) % 2 == 1)) { acc -= (int)freq[ge]; ge--; }
-			for (int v = 0; v < alpha; v++) len[n_part - 1][v] = (v >= gs && v <= ge) ? 0 : 15;
+			// table n_part-1 is cheap (0) inside [gs, ge], expensive (15) outside; written below by all threads
+			hlw[0][2 * (n_part - 1)] = (uint32_t)gs; hlw[0][2 * (n_part - 1) + 1] = (uint32_t)(ge + 1);
 			n_part--; gs = ge + 1; rem -= acc;
 		}
 	}
 	__syncthreads();
 	const int ng = (int)s_ngroups;
+	for (uint32_t i = tid; i < (uint32_t)ng * (uint32_t)alpha; i += HP_NT) {
+		uint32_t t = i / (uint32_t)alpha, v = i - t * (uint32_t)alpha;
+		len[t][v] = (v >= hlw[0][2 * t] && v < hlw[0][2 * t + 1]) ? 0 : 15;
+	}
+	__syncthreads();
 	const uint32_t n_sel = (n_mtf + kGSize - 1) / kGSize;
 
 	// ---- 4 refinement passes (compress.c:321-453)
@@ -520,9 +546,9 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 			uint32_t gs = gi * kGSize, ge = min(gs + kGSize, n_mtf);
 			uint32_t cost[kGroups] = { 0, 0, 0, 0, 0, 0 };
 			for (uint32_t i = gs; i < ge; i++) {
-				uint32_t s = mtfv[i];
+				uint32_t sy = mtfv[i];
 				#pragma unroll
-				for (int t = 0; t < kGroups; t++) if (t < ng) cost[t] += len[t][s];
+				for (int t = 0; t < kGroups; t++) if (t < ng) cost[t] += len[t][sy];
 			}
 			int bt = 0; uint32_t bc = cost[0];
 			#pragma unroll
@@ -531,43 +557,89 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 			for (uint32_t i = gs; i < ge; i++) atomicAdd(&rfreq[bt][mtfv[i]], 1u);
 		}
 		__syncthreads();
-		if ((tid & 31) == 0 && (int)(tid >> 5) < ng) {
-			int t = tid >> 5;
-			make_code_lengths(len[t], rfreq[t], alpha, 17, hheap[t], hweight[t], hparent[t]);
-		}
+		if ((int)wid < ng) make_code_lengths_warp(len[wid], rfreq[wid], alpha, 17, hheap[wid], hparent[wid], hlw[wid], lane);
 		__syncthreads();
 	}
 
-	// ---- canonical codes (huffman.c:152-166), one table per warp leader
-	if ((tid & 31) == 0 && (int)(tid >> 5) < ng) {
-		int t = tid >> 5, mn = 32, mx = 0;
-		for (int i = 0; i < alpha; i++) { int l = len[t][i]; mx = l > mx ? l : mx; mn = l < mn ? l : mn; }
-		uint32_t vec = 0;
-		for (int l = mn; l <= mx; l++) {
-			for (int i = 0; i < alpha; i++) if (len[t][i] == l) code[t][i] = vec++;
-			vec <<= 1;
+	// ---- canonical codes (huffman.c:152-166): code = first code of the length + rank among equal lengths
+	if ((int)wid < ng) {
+		const int t = (int)wid;
+		uint32_t* cnt = hlw[t];                              // [0..20] per-length counters, then first codes
+		if (lane < 24) cnt[lane] = 0;
+		__syncwarp();
+		for (int base = 0; base < alpha; base += 32) {       // rank inside the length class, in symbol order
+			const int i = base + (int)lane;
+			const bool act = i < alpha;
+			const uint32_t am = __ballot_sync(0xffffffffu, act);
+			if (act) {
+				const uint32_t l = len[t][i];
+				const uint32_t peers = __match_any_sync(am, l);
+				const uint32_t before = cnt[l];
+				code[t][i] = before + __popc(peers & ((1u << lane) - 1u));      // rank for now
+				__syncwarp(am);
+				if (lane == (uint32_t)(__ffs(peers) - 1)) cnt[l] = before + __popc(peers);
+			}
+			__syncwarp();
 		}
+		if (lane == 0) {                                     // first code of each length
+			uint32_t vec = 0;
+			for (int l = 1; l <= 20; l++) { uint32_t c = cnt[l]; cnt[l] = vec; vec = (vec + c) << 1; }
+		}
+		__syncwarp();
+		for (int i = (int)lane; i < alpha; i += 32) code[t][i] += cnt[len[t][i]];
 	}
 	__syncthreads();
 
-	// ---- total size: header bits (computed by thread 0 while writing) + sum of code lengths
+	// ---- sizes: symbol bits from the last pass' usage counts, header from the field lengths
 	uint32_t sym_bits_local = 0;
 	for (uint32_t i = tid; i < (uint32_t)ng * (uint32_t)alpha; i += HP_NT) {
 		uint32_t t = i / (uint32_t)alpha, v = i % (uint32_t)alpha;
 		sym_bits_local += rfreq[t][v] * len[t][v];      // rfreq of the last pass == usage with the final selectors
 	}
 	uint32_t sym_bits; block_scan_add<HP_NT>(sym_bits_local, red, &sym_bits);
-
-	// upper bound of the header so the output words can be cleared before anybody writes
-	// (32 stream + 48+32+1+24 + 16+256 + 3+15 + n_sel*6 + ng*(5+alpha*(1+2*20)))
+	// selectors: move-to-front codes (compress.c:462-479), sequential but register-only
+	if (tid == 0) {
+		uint32_t pos = 0x543210u;
+		for (uint32_t i = 0; i < n_sel; i++) {
+			const uint32_t sv = selector[i];
+			uint32_t j = 0;
+			while (((pos >> (4 * j)) & 15u) != sv) j++;
+			const uint32_t lowmask = (1u << (4 * j)) - 1u;
+			pos = (pos & ~((lowmask << 4) | 15u)) | ((pos & lowmask) << 4) | sv;
+			selmtf[i] = (uint8_t)j;
+		}
+	}
+	// delta-coded lengths: bits per table
+	if ((int)wid < ng) {
+		uint32_t b = 0;
+		for (int i = (int)lane; i < alpha; i += 32) {
+			int d = i ? (int)len[wid][i] - (int)len[wid][i - 1] : 0;
+			b += 2u * (uint32_t)abs(d) + 1u;
+		}
+		#pragma unroll
+		for (int o = 16; o; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+		if (lane == 0) s_tbits[wid] = b + 5;
+	}
+	__syncthreads();
+	uint32_t sel_bits_local = 0;
+	const uint32_t sel_per = (n_sel + HP_NT - 1) / HP_NT;
+	const uint32_t sb0 = min(n_sel, tid * sel_per), sb1 = min(n_sel, sb0 + sel_per);
+	for (uint32_t i = sb0; i < sb1; i++) sel_bits_local += selmtf[i] + 1u;
+	uint32_t sel_bits; const uint32_t sel_inc = block_scan_add<HP_NT>(sel_bits_local, red, &sel_bits);
+	uint32_t used16n = 0;
+	for (int i = 0; i < 16; i++) if ((J.in_use[i >> 1] >> ((i & 1) * 16)) & 0xffffu) used16n++;
+	const uint32_t fixed_bits = 32 + 48 + 32 + 1 + 24 + 16 + 16 * used16n + 3 + 15;
+	uint32_t len_bits = 0;
+	for (int t = 0; t < ng; t++) len_bits += s_tbits[t];
+	const uint32_t hdr_bits = fixed_bits + sel_bits + len_bits;
 	{
-		uint32_t hdr_max = 32 + 105 + 272 + 18 + n_sel * 6 + (uint32_t)ng * (5 + (uint32_t)alpha * 41);
-		uint32_t words = (hdr_max + sym_bits + 80 + 31) / 32 + 2;
+		uint32_t words = (hdr_bits + sym_bits + 80 + 31) / 32 + 2;
 		if ((size_t)words * 4 > ocap) { if (tid == 0) { J.status = 2; J.out_bytes = 0; } return; }
 		for (uint32_t i = tid; i < words; i += HP_NT) out[i] = 0;
 	}
 	__syncthreads();
 
+	// ---- header: fixed part by thread 0, selectors by everybody, one table of lengths per warp
 	if (tid == 0) {
 		HdrWriter hw{ out, 0, 0, 0 };
 		hw.put(8, 'B'); hw.put(8, 'Z'); hw.put(8, 'h'); hw.put(8, (uint32_t)('0' + level));
@@ -585,32 +657,43 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 		}
 		hw.put(3, (uint32_t)ng);
 		hw.put(15, n_sel);
-		{   // selectors, move-to-front coded, unary (compress.c:462-479, :530-535)
-			uint8_t pos[kGroups];
-			for (int i = 0; i < ng; i++) pos[i] = (uint8_t)i;
-			for (uint32_t i = 0; i < n_sel; i++) {
-				uint8_t s = selector[i];
-				int j = 0; uint8_t tmp = pos[0];
-				while (tmp != s) { j++; uint8_t t2 = pos[j]; pos[j] = tmp; tmp = t2; }
-				pos[0] = tmp;
-				hw.put((uint32_t)j + 1, ((1u << j) - 1u) << 1);
-			}
-		}
-		for (int t = 0; t < ng; t++) {   // delta coded lengths (compress.c:537-548)
-			int curr = len[t][0];
-			hw.put(5, (uint32_t)curr);
-			for (int i = 0; i < alpha; i++) {
-				int l = len[t][i];
-				while (curr < l) { hw.put(2, 2); curr++; }
-				while (curr > l) { hw.put(2, 3); curr--; }
-				hw.put(1, 0);
-			}
-		}
-		s_hdr_bits = hw.bits();
 		hw.finish();
 	}
+	{
+		uint32_t bp = fixed_bits + sel_inc - sel_bits_local;
+		for (uint32_t i = sb0; i < sb1; i++) {                // j ones then a zero
+			const uint32_t j = selmtf[i];
+			or_bits(out, bp, j + 1, ((1u << j) - 1u) << 1);
+			bp += j + 1;
+		}
+	}
+	if ((int)wid < ng) {
+		const int t = (int)wid;
+		uint32_t tb = fixed_bits + sel_bits;
+		for (int q = 0; q < t; q++) tb += s_tbits[q];
+		if (lane == 0) or_bits(out, tb, 5, len[t][0]);
+		tb += 5;
+		// lane owns a contiguous run of symbols; warp scan of the bit counts
+		const int per = (alpha + 31) / 32;
+		const int i0 = min(alpha, (int)lane * per), i1 = min(alpha, i0 + per);
+		uint32_t mybits = 0;
+		for (int i = i0; i < i1; i++) { int d = i ? (int)len[t][i] - (int)len[t][i - 1] : 0; mybits += 2u * (uint32_t)abs(d) + 1u; }
+		uint32_t incl = mybits;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+		uint32_t bp = tb + incl - mybits;
+		for (int i = i0; i < i1; i++) {
+			int d = i ? (int)len[t][i] - (int)len[t][i - 1] : 0;
+			uint32_t ad = (uint32_t)abs(d);
+			const uint32_t pair = d > 0 ? 2u : 3u;            // "10" = +1, "11" = -1
+			while (ad >= 16) { uint32_t v = 0; for (int r = 0; r < 16; r++) v = (v << 2) | pair; or_bits(out, bp, 32, v); bp += 32; ad -= 16; }
+			uint32_t v = 0;
+			for (uint32_t r = 0; r < ad; r++) v = (v << 2) | pair;
+			or_bits(out, bp, 2 * ad + 1, v << 1);             // ... then the terminating 0
+			bp += 2 * ad + 1;
+		}
+	}
 	__syncthreads();
-	const uint32_t hdr_bits = s_hdr_bits;
 
 	// ---- symbols: tiles of HP_NT*HP_SYMS, bit offsets by block scan, assembled in a shared window
 	uint32_t bitpos = hdr_bits;
@@ -624,7 +707,7 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 		for (int k = 0; k < HP_SYMS; k++) {
 			uint32_t i = i0 + k;
 			l[k] = 0; c[k] = 0;
-			if (i < n_mtf) { uint32_t t = selector[i / kGSize], s = mtfv[i]; l[k] = len[t][s]; c[k] = code[t][s]; }
+			if (i < n_mtf) { uint32_t t = selector[i / kGSize], sy = mtfv[i]; l[k] = len[t][sy]; c[k] = code[t][sy]; }
 			sum += l[k];
 		}
 		uint32_t tot; uint32_t inc = block_scan_add<HP_NT>(sum, red, &tot);   // includes the barrier after zeroing win

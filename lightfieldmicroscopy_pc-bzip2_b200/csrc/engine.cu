@@ -244,7 +244,7 @@ int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t 
 	if ((rc = reserve(bwt_, B * z.cap))) return rc;
 	if ((rc = reserve(rank_, B * z.cap))) return rc;
 	if ((rc = reserve(mtfv_, B * (size_t)z.mcap * 2))) return rc;
-	if ((rc = reserve(sel_, B * z.selcap))) return rc;
+	if ((rc = reserve(sel_, B * (size_t)z.selcap * 2))) return rc;
 	if ((rc = reserve(out_, B * (size_t)z.ocap + 16))) return rc;
 	if ((rc = reserve(scratch_, (size_t)grid * bwt_scratch_elems_per_cta(z.cap) * 4))) return rc;
 	if ((rc = reserve(payload_, pcap + 16))) return rc;
@@ -348,10 +348,8 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 	for (uint64_t b0 = 0; b0 < count; b0 += B) {
 		const uint32_t nj = (uint32_t)std::min<uint64_t>(B, count - b0);
 		mark();
-		uint64_t max_stream = 0;
-		for (uint64_t i = b0; i < b0 + nj; i++) max_stream = std::max(max_stream, end[i] - begin[i]);
 		if (launch_decode(d_payload, (uint64_t*)dbegin_.p + b0, (uint64_t*)dend_.p + b0, nj, (DecJob*)djobs_.p, (uint16_t*)mtfv_.p, z.mcap,
-		                  (uint8_t*)txt_.p, (uint8_t*)bwt_.p, z.cap, z.selcap, max_stream, st)) { err_ = "compressed block larger than the decoder staging area"; return LFM_ERR_UNSUPPORTED; }
+		                  (uint8_t*)txt_.p, (uint8_t*)bwt_.p, z.cap, z.selcap, st)) { err_ = "decoder launch failed"; return LFM_ERR_UNSUPPORTED; }
 		mark();
 		launch_inv_bwt((uint8_t*)bwt_.p, z.cap, (DecJob*)djobs_.p, nj, (uint32_t*)tt_.p, (uint8_t*)txt_.p,
 		               (int)std::min<uint32_t>(nj, (uint32_t)grid), st);
