@@ -205,3 +205,19 @@ def test_large_frame_round_trip_properties(L):
     for i in (0, 1, 200, nb - 1):
         s = pay[int(offs[i - 1]) if i else 0:int(offs[i])]
         assert len(bz2.decompress(s)) in (96 * 96 * 2, 96 * 32 * 2, 32 * 96 * 2, 32 * 32 * 2)
+
+
+def test_two_gpus_in_process_sharding(L, tmp_path):
+    """lfmSetDevices(0, 2): z-slabs split over two GPUs, host prefix sum -> same bytes as one GPU"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    a = lf_synth((24, 100, 120), 13, seed=2)
+    one = L.compress_to_bytes(a, header_version=0x80 | 13, nnum=13, block_size=(48, 48, 4, 1, 1), way=0)
+    try:
+        assert L.set_devices(0, 2) == 2
+        two = L.compress_to_bytes(a, header_version=0x80 | 13, nnum=13, block_size=(48, 48, 4, 1, 1), way=0)
+        assert one == two
+        assert np.array_equal(L.decompress_from_bytes(two, a.shape, way=0), a)
+    finally:
+        L.set_devices(0, 1)
