@@ -117,6 +117,17 @@ int Engine::reserve(Buf& b, size_t bytes)
 	return LFM_OK;
 }
 
+void* Engine::pinned(size_t bytes)
+{
+	if (pin_cap_ >= bytes) return pin_;
+	if (pin_) cudaFreeHost(pin_);
+	pin_ = nullptr; pin_cap_ = 0;
+	size_t want = bytes + bytes / 4 + 4096;
+	if (cudaHostAlloc(&pin_, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); pin_ = nullptr; return nullptr; }
+	pin_cap_ = want;
+	return pin_;
+}
+
 static inline uint32_t round16(uint64_t v) { return (uint32_t)((v + 15) & ~(uint64_t)15); }
 
 static Geom make_geom(const StackDesc& s)
@@ -215,7 +226,7 @@ int Engine::unpredict(const uint16_t* d_sym, uint16_t* d_out, const StackDesc& s
 		bad |= launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 1, first_even, 2, n_even, sm_count_, st);
 		bad |= launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 1, first_odd, 2, n_odd, sm_count_, st);
 	}
-	if (bad) { cudaGetLastError(); err_ = "cooperative launch of k_unpredict failed"; return LFM_ERR_CUDA; }
+	if (bad) { cudaGetLastError(); err_ = "cluster launch of k_unpredict failed"; return LFM_ERR_CUDA; }
 	return check("unpredict");
 }
 

@@ -74,6 +74,10 @@ public:
 	// growable device scratch, kept across calls
 	struct Buf { void* p = nullptr; size_t cap = 0; };
 	int reserve(Buf& b, size_t bytes);
+	// buffers the orchestrator (klb_imageIO.cpp) keeps on this GPU between calls: image, symbol image, payload, frame 0
+	Buf user[4];
+	// growable pinned host staging buffer (one per engine)
+	void* pinned(size_t bytes);
 
 	// debugging / stage-parity hook: copies of the intermediate arrays of the LAST compress_blocks batch
 	struct EncodeTrace {
@@ -96,6 +100,7 @@ private:
 	Buf djobs_, dbegin_, dend_, dids_, tt_;
 	Buf sel_sorted_, sel_hist_, sel_e_, sel_cand_;
 	uint32_t last_cap_ = 0, last_mcap_ = 0, last_njobs_ = 0;
+	void* pin_ = nullptr; size_t pin_cap_ = 0;
 	void* ev_[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 };
 

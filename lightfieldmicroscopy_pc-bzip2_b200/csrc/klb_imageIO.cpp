@@ -112,8 +112,13 @@ struct DevMem {                   // RAII device allocation
 };
 
 // ------------------------------------------------------------------------------------------------ compress core
-struct ShardOut { std::vector<uint8_t> payload; std::vector<uint32_t> sizes; int rc = 0; CompressStats st; double ms_h2d = 0, ms_d2h = 0; };
+struct ShardOut {
+	std::vector<uint32_t> sizes; int rc = 0; CompressStats st; double ms_h2d = 0, ms_d2h = 0;
+	const uint8_t* d_payload = nullptr; uint64_t payload_bytes = 0; int device = 0;      // streams stay on the GPU until fetched
+};
+enum { UB_IMG = 0, UB_SYM = 1, UB_PAY = 2, UB_F0 = 3 };
 
+// Phase 1: everything up to the compacted streams in device memory + header.blockOffset[].
 int compress_core(const FrameSource& src, klb_image_header& h, std::vector<ShardOut>& shards, std::vector<uint64_t>& shardFirstBlock)
 {
 	memset(&g_stats, 0, sizeof(g_stats));
@@ -134,13 +139,12 @@ int compress_core(const FrameSource& src, klb_image_header& h, std::vector<Shard
 		// auto-select on frame 0 (branches A and B of writeImage, src/klb_imageIO.cpp:2273-2377)
 		Engine& e = Engine::for_device(g_set.first_device);
 		cudaSetDevice(e.device());
-		DevMem f0;
-		if (f0.alloc(L.fpx * 2)) return LFM_ERR_CUDA;
+		if (e.reserve(e.user[UB_F0], L.fpx * 2)) return LFM_ERR_CUDA;
 		// stream-ordered copy: a default-stream cudaMemcpy from pageable memory may return before the DMA has landed,
 		// and the engine's non-blocking stream does not wait for the default stream
-		cudaMemcpyAsync(f0.p, src.frame(0, L.fpx), L.fpx * 2, cudaMemcpyHostToDevice, (cudaStream_t)e.stream());
+		cudaMemcpyAsync(e.user[UB_F0].p, src.frame(0, L.fpx), L.fpx * 2, cudaMemcpyHostToDevice, (cudaStream_t)e.stream());
 		double t0 = now_ms();
-		rc = e.select_mode((const uint16_t*)f0.p, desc, g_stats.entropy, &k);
+		rc = e.select_mode((const uint16_t*)e.user[UB_F0].p, desc, g_stats.entropy, &k);
 		if (rc) { g_err = e.last_error(); return rc; }
 		g_stats.ms_select = now_ms() - t0;
 		g_stats.selected = 1; g_stats.gpu_launches += 7 + 3;
@@ -165,39 +169,28 @@ int compress_core(const FrameSource& src, klb_image_header& h, std::vector<Shard
 		if (k != 0 && video && (f0 & 1)) f0--;              // an odd first frame is predicted from the even one before it
 		const uint64_t nf = f1 - f0 + 1;
 		Engine& e = Engine::for_device(g_set.first_device + d);
+		out.device = e.device();
 		cudaSetDevice(e.device());
 		cudaStream_t st = (cudaStream_t)e.stream();
-		DevMem dimg, dsym;
-		if (dimg.alloc(nf * L.fpx * 2) || (k != 0 && dsym.alloc(nf * L.fpx * 2))) { out.rc = LFM_ERR_CUDA; return; }
+		if (e.reserve(e.user[UB_IMG], nf * L.fpx * 2) || (k != 0 && e.reserve(e.user[UB_SYM], nf * L.fpx * 2))) { out.rc = LFM_ERR_CUDA; return; }
+		uint16_t* dimg = (uint16_t*)e.user[UB_IMG].p; uint16_t* dsym = (uint16_t*)e.user[UB_SYM].p;
 		double t0 = now_ms();
-		if (src.base) cudaMemcpyAsync(dimg.p, src.frame(f0, L.fpx), nf * L.fpx * 2, cudaMemcpyHostToDevice, st);
-		else for (uint64_t f = 0; f < nf; f++) cudaMemcpyAsync((uint16_t*)dimg.p + f * L.fpx, src.frame(f0 + f, L.fpx), L.fpx * 2, cudaMemcpyHostToDevice, st);
-		cudaStreamSynchronize(st);
-		out.ms_h2d = now_ms() - t0;
-		const uint16_t* img_base = (const uint16_t*)dimg.p - f0 * L.fpx;       // virtual base: absolute frame indexing
+		if (src.base) cudaMemcpyAsync(dimg, src.frame(f0, L.fpx), nf * L.fpx * 2, cudaMemcpyHostToDevice, st);
+		else for (uint64_t f = 0; f < nf; f++) cudaMemcpyAsync(dimg + f * L.fpx, src.frame(f0 + f, L.fpx), L.fpx * 2, cudaMemcpyHostToDevice, st);
+		const uint16_t* img_base = dimg - f0 * L.fpx;       // virtual base: absolute frame indexing
 		const uint16_t* sym_base = img_base;
 		if (k != 0) {
-			cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-			cudaEventRecord(a, st);
-			out.rc = e.predict(img_base, (uint16_t*)dsym.p - f0 * L.fpx, desc, k, video, (uint32_t)f0, (uint32_t)nf);
-			cudaEventRecord(b, st); cudaEventSynchronize(b);
-			float ms = 0; cudaEventElapsedTime(&ms, a, b); out.st.ms_predict = ms; out.st.launches++;
-			cudaEventDestroy(a); cudaEventDestroy(b);
+			out.rc = e.predict(img_base, dsym - f0 * L.fpx, desc, k, video, (uint32_t)f0, (uint32_t)nf);
+			out.st.launches++;
 			if (out.rc) return;
-			sym_base = (const uint16_t*)dsym.p - f0 * L.fpx;
+			sym_base = dsym - f0 * L.fpx;
 		}
 		const uint64_t first = s0 * L.blocksPerSlab, count = (s1 - s0) * L.blocksPerSlab;
 		shardFirstBlock[d] = first;
 		out.sizes.resize(count);
-		const uint8_t* dpay = nullptr; uint64_t pbytes = 0;
-		out.rc = e.compress_blocks(sym_base, desc, first, count, out.sizes.data(), &dpay, &pbytes, &out.st);
+		out.rc = e.compress_blocks(sym_base, desc, first, count, out.sizes.data(), &out.d_payload, &out.payload_bytes, &out.st);
+		out.ms_h2d = now_ms() - t0;                         // H2D + kernels (the copy is asynchronous and overlaps nothing yet)
 		if (out.rc) { g_err = e.last_error(); return; }
-		t0 = now_ms();
-		out.payload.resize(pbytes);
-		if (pbytes) cudaMemcpyAsync(out.payload.data(), dpay, pbytes, cudaMemcpyDeviceToHost, st);
-		cudaStreamSynchronize(st);
-		out.ms_d2h = now_ms() - t0;
-		if (cudaGetLastError() != cudaSuccess) out.rc = LFM_ERR_CUDA;
 	};
 	if (D == 1) work(0);
 	else {
@@ -214,12 +207,33 @@ int compress_core(const FrameSource& src, klb_image_header& h, std::vector<Shard
 		g_stats.ms_predict = std::max(g_stats.ms_predict, s.st.ms_predict);
 		g_stats.ms_rle = std::max(g_stats.ms_rle, s.st.ms_rle); g_stats.ms_bwt = std::max(g_stats.ms_bwt, s.st.ms_bwt);
 		g_stats.ms_mtf = std::max(g_stats.ms_mtf, s.st.ms_mtf); g_stats.ms_huff = std::max(g_stats.ms_huff, s.st.ms_huff);
-		g_stats.ms_h2d = std::max(g_stats.ms_h2d, s.ms_h2d); g_stats.ms_d2h = std::max(g_stats.ms_d2h, s.ms_d2h);
+		g_stats.ms_h2d = std::max(g_stats.ms_h2d, s.ms_h2d);
 		g_stats.gpu_launches += s.st.launches; g_stats.periodic_blocks += s.st.periodic_blocks;
 	}
 	g_stats.payload_bytes = acc;
 	g_stats.ms_total = now_ms() - t_start;
 	return LFM_OK;
+}
+
+// Phase 2: bring the shards' streams to the host, in block order, at dst (payload_bytes total)
+int fetch_payload(std::vector<ShardOut>& shards, uint8_t* dst)
+{
+	const double t0 = now_ms();
+	uint64_t off = 0;
+	for (auto& s : shards) {
+		cudaSetDevice(s.device);
+		Engine& e = Engine::for_device(s.device);
+		if (s.payload_bytes) cudaMemcpyAsync(dst + off, s.d_payload, s.payload_bytes, cudaMemcpyDeviceToHost, (cudaStream_t)e.stream());
+		off += s.payload_bytes;
+	}
+	int rc = LFM_OK;
+	for (auto& s : shards) {
+		cudaSetDevice(s.device);
+		if (cudaStreamSynchronize((cudaStream_t)Engine::for_device(s.device).stream()) != cudaSuccess) { cudaGetLastError(); rc = LFM_ERR_CUDA; }
+	}
+	g_stats.ms_d2h = now_ms() - t0;
+	g_stats.ms_total += g_stats.ms_d2h;
+	return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ decompress core
@@ -297,12 +311,11 @@ int decompress_core(const klb_image_header& h, const uint8_t* payload, uint64_t 
 		Engine& e = Engine::for_device(g_set.first_device + d);
 		cudaSetDevice(e.device());
 		cudaStream_t st = (cudaStream_t)e.stream();
-		DevMem dpay, dsym, dimg, droi;
-		if (dpay.alloc(p1 - p0 + 16) || dsym.alloc(nf * L.fpx * 2) || (k != 0 && dimg.alloc(nf * L.fpx * 2))) { rcs[d] = LFM_ERR_CUDA; return; }
+		if (e.reserve(e.user[UB_PAY], p1 - p0 + 16) || e.reserve(e.user[UB_SYM], nf * L.fpx * 2) || (k != 0 && e.reserve(e.user[UB_IMG], nf * L.fpx * 2))) { rcs[d] = LFM_ERR_CUDA; return; }
+		struct { void* p; } dpay{ e.user[UB_PAY].p }, dsym{ e.user[UB_SYM].p }, dimg{ e.user[UB_IMG].p };
 		double t0 = now_ms();
 		cudaMemcpyAsync(dpay.p, payload + p0, p1 - p0, cudaMemcpyHostToDevice, st);
 		if (k == 0 && !full) cudaMemsetAsync(dsym.p, 0, nf * L.fpx * 2, st);
-		cudaStreamSynchronize(st);
 		h2d[d] = now_ms() - t0;
 		for (size_t i = 0; i < beg.size(); i++) { beg[i] -= p0; end[i] -= p0; }
 		uint16_t* sym_base = (uint16_t*)dsym.p - f0 * L.fpx;
@@ -310,12 +323,8 @@ int decompress_core(const klb_image_header& h, const uint8_t* payload, uint64_t 
 		if (rcs[d]) { g_err = e.last_error(); return; }
 		const uint16_t* res_base = sym_base;
 		if (k != 0) {
-			cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-			cudaEventRecord(a, st);
 			rcs[d] = e.unpredict(sym_base, (uint16_t*)dimg.p - f0 * L.fpx, desc, k, video, (uint32_t)f0, (uint32_t)nf);
-			cudaEventRecord(b, st); cudaEventSynchronize(b);
-			float ms = 0; cudaEventElapsedTime(&ms, a, b); sts[d].ms_unpredict = ms; sts[d].launches += video ? 2 : 1;
-			cudaEventDestroy(a); cudaEventDestroy(b);
+			sts[d].launches += video ? 2 : 1;
 			if (rcs[d]) return;
 			res_base = (const uint16_t*)dimg.p - f0 * L.fpx;
 		}
@@ -362,11 +371,18 @@ int decompress_core(const klb_image_header& h, const uint8_t* payload, uint64_t 
 klb_imageIO::klb_imageIO() { numThreads = (int)std::thread::hardware_concurrency(); }
 klb_imageIO::klb_imageIO(const std::string& filename_) : filename(filename_) { numThreads = (int)std::thread::hardware_concurrency(); }
 
-static int write_file(FILE* fout, klb_image_header& h, const std::vector<ShardOut>& shards)
+static int write_file(FILE* fout, klb_image_header& h, std::vector<ShardOut>& shards)
 {
 	h.writeHeader(fout);
-	for (const auto& s : shards) if (!s.payload.empty() && fwrite(s.payload.data(), 1, s.payload.size(), fout) != s.payload.size()) return LFM_ERR_CREATE;
-	return LFM_OK;
+	uint64_t total = 0;
+	for (const auto& s : shards) total += s.payload_bytes;
+	if (total == 0) return LFM_OK;
+	// D2H into the first engine's pinned staging buffer, then one fwrite
+	uint8_t* stage = (uint8_t*)Engine::for_device(shards[0].device).pinned(total);
+	if (!stage) return LFM_ERR_CUDA;
+	int rc = fetch_payload(shards, stage);
+	if (rc) return rc;
+	return fwrite(stage, 1, total, fout) == total ? LFM_OK : LFM_ERR_CREATE;
 }
 
 int klb_imageIO::writeImage(const char* img, int /*numThreads*/)
@@ -404,10 +420,12 @@ int klb_imageIO::writeImageToMemory(const char* img, std::string& fileBytes)
 	int rc = compress_core(src, header, shards, first);
 	if (rc) return rc;
 	uint8_t fixed[320]; header.packFixed(fixed);
-	fileBytes.assign((const char*)fixed, 320);
-	fileBytes.append((const char*)header.blockOffset, header.Nb * 8);
-	for (const auto& s : shards) fileBytes.append((const char*)s.payload.data(), s.payload.size());
-	return LFM_OK;
+	uint64_t total = 0;
+	for (const auto& s : shards) total += s.payload_bytes;
+	fileBytes.resize(320 + header.Nb * 8 + total);
+	memcpy(&fileBytes[0], fixed, 320);
+	memcpy(&fileBytes[320], header.blockOffset, header.Nb * 8);
+	return fetch_payload(shards, (uint8_t*)&fileBytes[320 + header.Nb * 8]);
 }
 
 int klb_imageIO::readImageFromMemory(const char* fileBytes, size_t fileSize, char* imgOut, const klb_ROI* ROI)
@@ -495,13 +513,20 @@ int lfmCompressToMemory(const void* im, const uint32_t xyzct[5], const uint32_t 
 {
 	klb_imageIO io;
 	io.header.setHeader(xyzct, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize, KLB_COMPRESSION_TYPE::BZIP2, NULL, headerVersion, Nnum);
-	std::string bytes;
-	int rc = io.writeImageToMemory((const char*)im, bytes);
+	FrameSource src; src.base = (const uint16_t*)im;
+	std::vector<ShardOut> shards; std::vector<uint64_t> first;
+	int rc = compress_core(src, io.header, shards, first);
 	if (rc) return rc;
-	void* p = malloc(bytes.size() ? bytes.size() : 1);
+	uint64_t total = 0;
+	for (const auto& s : shards) total += s.payload_bytes;
+	const size_t hdr = 320 + io.header.Nb * 8;
+	uint8_t* p = (uint8_t*)malloc(hdr + total);
 	if (!p) return LFM_ERR_CREATE;
-	memcpy(p, bytes.data(), bytes.size());
-	*file_bytes = p; *file_size = bytes.size();
+	io.header.packFixed(p);
+	memcpy(p + 320, io.header.blockOffset, io.header.Nb * 8);
+	rc = fetch_payload(shards, p + hdr);
+	if (rc) { free(p); return rc; }
+	*file_bytes = p; *file_size = hdr + total;
 	return 0;
 }
 
