@@ -23,8 +23,8 @@ __global__ void __launch_bounds__(BWT_NT, 1)
 k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jobs, uint32_t njobs,
       uint8_t* __restrict__ bwt_all, uint32_t* __restrict__ scratch_all, int text_in_smem)
 {
-	uint32_t (*wcnt)[256] = reinterpret_cast<uint32_t (*)[256]>(bwt_smem);
-	uint32_t* base = reinterpret_cast<uint32_t*>(bwt_smem + BWT_NW * 256 * 4);
+	uint32_t* wcnt = reinterpret_cast<uint32_t*>(bwt_smem);
+	uint32_t* base = reinterpret_cast<uint32_t*>(bwt_smem + BWT_NW * BWT_WS * 4);
 	uint32_t* run  = base + 256;
 	uint32_t* red  = run + 256;          // 64
 	uint32_t* misc = red + 64;           // 16
@@ -160,7 +160,7 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 
 size_t bwt_smem_bytes(uint32_t cap, int text_in_smem)
 {
-	size_t fixed = (size_t)BWT_NW * 256 * 4 + (256 + 256 + 64 + 16) * 4;
+	size_t fixed = (size_t)BWT_NW * BWT_WS * 4 + (256 + 256 + 64 + 16) * 4;
 	return fixed + (text_in_smem ? (size_t)cap + 16 : 0);
 }
 size_t bwt_scratch_elems_per_cta(uint32_t cap) { return (size_t)S_COUNT * cap; }

@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(BWT_NT, 1)
 k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict__ jobs, uint32_t njobs,
           uint32_t* __restrict__ tt_all, uint8_t* __restrict__ txt_all)
 {
-	__shared__ uint32_t wcnt[BWT_NW][256];
+	__shared__ uint32_t wcnt[BWT_NW * BWT_WS];
 	__shared__ uint32_t run[256];
 	__shared__ uint32_t red[64];
 	__shared__ uint32_t s_next[IB_MAXS + 2];

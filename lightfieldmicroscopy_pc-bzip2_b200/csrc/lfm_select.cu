@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(BWT_NT, 1)
 k_select_sort(CandPtrs cands, uint64_t fpx, uint32_t chunk_px, uint32_t nchunks, uint8_t* __restrict__ sorted_all,
               uint32_t sstride)
 {
-	__shared__ uint32_t wcnt[BWT_NW][256];
+	__shared__ uint32_t wcnt[BWT_NW * BWT_WS];
 	__shared__ uint32_t run[256];
 	__shared__ uint32_t red[64];
 	const uint32_t chunk = blockIdx.x, cand = blockIdx.y;
