@@ -61,7 +61,7 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 			if (tid < 256) run[tid] = base[tid];
 			__syncthreads();
 			const uint32_t* s = src; uint32_t* d = dst;
-			radix_scatter<uint32_t>(n, run, wcnt,
+			radix_scatter<BWT_R, uint32_t>(n, run, wcnt,
 				[&](uint32_t e) { return s ? s[e] : e; },
 				[&](uint32_t idx) { return (uint32_t)text[idx + p]; },
 				[&](uint32_t pos, uint32_t idx) { d[pos] = idx; });
@@ -77,12 +77,11 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 		uint32_t* V[2] = { scr + (size_t)S_V0 * cap, scr + (size_t)S_V1 * cap };
 		uint32_t* U[2] = { scr + (size_t)S_U0 * cap, scr + (size_t)S_U1 * cap };
 		uint32_t m = split_groups(n, red,
-			[&](uint32_t j) -> bool {                     // does rotation sa[j] differ from sa[j-1] within 8 bytes?
-				if (j == 0 || j >= n) return true;
-				uint32_t a = sa[j - 1], b = sa[j];
-				#pragma unroll
-				for (int k = 0; k < 8; k++) if (text[a + k] != text[b + k]) return true;
-				return false;
+			[&](uint32_t j) -> uint64_t {                 // the 8-byte prefix of rotation sa[j]: three aligned words, shifted
+				const uint32_t idx = sa[j], sh = (idx & 3u) * 8u;
+				const uint32_t* tw = reinterpret_cast<const uint32_t*>(text + (idx & ~3u));
+				const uint32_t w0 = tw[0], w1 = tw[1], w2 = tw[2];
+				return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
 			},
 			[&](uint32_t j) { return j; },
 			[&](uint32_t j, uint32_t head, bool un, uint32_t slot) {
@@ -109,7 +108,7 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 					uint32_t* og = G[cur ^ 1]; uint32_t* orr = Rk[cur ^ 1]; uint32_t* ov = V[cur ^ 1];
 					const int sh = ps * 8;
 					digit_starts(m, run, wcnt, red, [&](uint32_t e) { return ((key ? kg[e] : kr[e]) >> sh) & 255u; });
-					radix_scatter<Trip>(m, run, wcnt,
+					radix_scatter<4, Trip>(m, run, wcnt,
 						[&](uint32_t e) { Trip t; t.g = kg[e]; t.r = kr[e]; t.v = kv[e]; return t; },
 						[&](const Trip& t) { return ((key ? t.g : t.r) >> sh) & 255u; },
 						[&](uint32_t pos, const Trip& t) { og[pos] = t.g; orr[pos] = t.r; ov[pos] = t.v; });
@@ -124,7 +123,7 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 				uint32_t* ng = G[cur ^ 1]; uint32_t* nv = V[cur ^ 1]; uint32_t* nu = U[ucur ^ 1];
 				const uint32_t mm = m;
 				m = split_groups(mm, red,
-					[&](uint32_t s) -> bool { return s == 0 || s >= mm || kg[s] != kg[s - 1] || kr[s] != kr[s - 1]; },
+					[&](uint32_t s) -> uint64_t { return ((uint64_t)kg[s] << 32) | kr[s]; },
 					[&](uint32_t s) { return up[s]; },
 					[&](uint32_t s, uint32_t head, bool un, uint32_t slot) {
 						uint32_t sfx = kv[s], pos = up[s];
@@ -139,10 +138,17 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 		}
 
 		// ---- phase 4: last column, origPtr (ties left <=> exactly periodic block: rotation 0 goes last in its group)
-		for (uint32_t j = tid; j < n; j += BWT_NT) {
-			uint32_t s = sa[j];
-			bwt[j] = text[s ? s - 1 : n - 1];
-			if (s == 0 && m == 0) jobs[job].orig_ptr = j;
+		for (uint32_t j = tid * 4; j < n; j += BWT_NT * 4) {       // four rotations per thread: one 16-byte load, one word store
+			const uint4 q = *reinterpret_cast<const uint4*>(sa + j);   // slots are 16-byte aligned; entries past n are never used
+			const uint32_t sv[4] = { q.x, q.y, q.z, q.w };
+			uint32_t wv = 0;
+			#pragma unroll
+			for (int k = 0; k < 4; k++) if (j + k < n) {
+				const uint32_t s = sv[k];
+				wv |= (uint32_t)text[s ? s - 1 : n - 1] << (8 * k);
+				if (s == 0 && m == 0) jobs[job].orig_ptr = j + k;
+			}
+			*reinterpret_cast<uint32_t*>(bwt + j) = wv;
 		}
 		if (m > 0) {
 			if (tid == 0) misc[1] = 0;

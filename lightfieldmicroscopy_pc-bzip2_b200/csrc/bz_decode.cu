@@ -413,7 +413,7 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 
 		// ---- LF mapping: T[pos] = i for the i-th occurrence ... stable counting sort of positions by byte
 		digit_starts(n, run, wcnt, red, [&](uint32_t e) { return (uint32_t)L[e]; });     // cftab (decompress.c:494-510)
-		radix_scatter<uint32_t>(n, run, wcnt,
+		radix_scatter<BWT_R, uint32_t>(n, run, wcnt,
 			[&](uint32_t e) { return (e << 8) | (uint32_t)L[e]; },
 			[&](uint32_t p) { return p & 255u; },
 			[&](uint32_t pos, uint32_t p) { tt[pos] = p >> 8; });

@@ -6,52 +6,58 @@
 namespace lfm {
 
 constexpr int BWT_NT = 1024;
-constexpr int BWT_R  = 8;                 // elements per thread per radix tile
+constexpr int BWT_R  = 8;                 // elements per thread per radix tile (4-byte payloads)
 constexpr int BWT_NW = BWT_NT / 32;
-constexpr int BWT_WS = 257;               // row stride (words) of the per-warp digit counters: conflict-free rows AND columns
+constexpr int BWT_WS = 257;               // row stride (words) of the per-warp digit counters: conflict-free rows AND columns;
+                                          // column 256 is the dummy digit of the lanes past the end of the data
 constexpr int SPLIT_R = 4;                // elements per thread per tile in split_groups
 #define LFM_WC(w, d) wcnt[(w) * BWT_WS + (d)]
 
 struct Trip { uint32_t g, r, v; };
 
-// One stable 8-bit counting-sort pass over m elements, tile by tile (tile = BWT_NT * BWT_R elements).
+// One stable 8-bit counting-sort pass over m elements, tile by tile (tile = BWT_NT * R elements).
 // run[256] (shared) must hold the exclusive bucket starts on entry; it is advanced as tiles are placed.
-// wcnt: BWT_NW x BWT_WS shared words.
+// wcnt: BWT_NW x BWT_WS shared words; every warp owns (and zeroes) its own row.
 //   1. all loads of the tile are issued first (independent global loads in flight together);
-//   2. per warp, BWT_R rounds of match.any multisplit give each element its rank among equal digits of the warp;
+//   2. ranking inside the warp: R match.any instructions back to back, then R shared-memory atomics by the group
+//      leaders (issued back to back: the counter update is ordered by the memory pipe, not by a register dependency),
+//      then R shuffles that hand the old counter value to the group -- three software-pipelined sweeps instead of
+//      R serialised load/modify/store rounds;
 //   3. the per-warp digit counts are scanned ACROSS warps by warp shuffles (warp w owns digits 8w..8w+7);
-//   4. scatter.
-template <class P, class LoadFn, class DigitFn, class StoreFn>
+//   4. scatter; the warp clears its own counter row for the next tile (two CTA barriers per tile in all).
+template <int R, class P, class LoadFn, class DigitFn, class StoreFn>
 __device__ __forceinline__ void radix_scatter(uint32_t m, uint32_t* run, uint32_t* wcnt,
                                               LoadFn load, DigitFn digit, StoreFn store)
 {
 	const uint32_t lane = lane_id(), w = warp_id();
-	constexpr uint32_t TILE = BWT_NT * BWT_R;
+	const uint32_t lt = (1u << lane) - 1u;
+	constexpr uint32_t TILE = BWT_NT * R;
+	uint32_t* myc = wcnt + w * BWT_WS;
+	__syncthreads();                                      // earlier users of wcnt / run are done
+	for (uint32_t i = lane; i < BWT_WS; i += 32) myc[i] = 0;
+	__syncwarp();
 	for (uint32_t t0 = 0; t0 < m; t0 += TILE) {
-		for (uint32_t i = threadIdx.x; i < BWT_NW * BWT_WS; i += BWT_NT) wcnt[i] = 0;
-		P pay[BWT_R]; uint32_t dl[BWT_R];                 // digit << 16 | rank inside the warp
+		P pay[R]; uint32_t dl[R];                         // digit << 16 | rank inside the warp
+		const uint32_t eb = t0 + w * (32 * R) + lane;
 		#pragma unroll
-		for (int r = 0; r < BWT_R; r++) {
-			uint32_t e = t0 + w * (32 * BWT_R) + r * 32 + lane;
-			if (e < m) pay[r] = load(e);
-		}
-		__syncthreads();
-		#pragma unroll
-		for (int r = 0; r < BWT_R; r++) {
-			uint32_t e = t0 + w * (32 * BWT_R) + r * 32 + lane;
-			bool act = e < m;
-			uint32_t amask = __ballot_sync(0xffffffffu, act);
-			dl[r] = 0;
-			if (act) {
-				uint32_t d = digit(pay[r]);
-				uint32_t peers = __match_any_sync(amask, d);
-				uint32_t leader = __ffs(peers) - 1;
-				uint32_t old = 0;
-				if (lane == leader) { old = LFM_WC(w, d); LFM_WC(w, d) = old + __popc(peers); }
-				old = __shfl_sync(peers, old, leader);
-				dl[r] = (d << 16) | (old + __popc(peers & ((1u << lane) - 1u)));
+		for (int r = 0; r < R; r++) if (eb + r * 32 < m) pay[r] = load(eb + r * 32);
+		{
+			uint32_t peers[R], old[R];
+			#pragma unroll
+			for (int r = 0; r < R; r++) dl[r] = (eb + r * 32 < m) ? digit(pay[r]) : 256u;
+			#pragma unroll
+			for (int r = 0; r < R; r++) peers[r] = __match_any_sync(0xffffffffu, dl[r]);
+			#pragma unroll
+			for (int r = 0; r < R; r++) {
+				old[r] = 0;
+				if ((peers[r] & lt) == 0) old[r] = atomicAdd(&myc[dl[r]], (uint32_t)__popc(peers[r]));
+				__syncwarp();
 			}
-			__syncwarp();
+			#pragma unroll
+			for (int r = 0; r < R; r++) {
+				const uint32_t o = __shfl_sync(0xffffffffu, old[r], __ffs(peers[r]) - 1);
+				dl[r] = (dl[r] << 16) | (o + __popc(peers[r] & lt));
+			}
 		}
 		__syncthreads();
 		#pragma unroll
@@ -67,32 +73,34 @@ __device__ __forceinline__ void radix_scatter(uint32_t m, uint32_t* run, uint32_
 		}
 		__syncthreads();
 		#pragma unroll
-		for (int r = 0; r < BWT_R; r++) {
-			uint32_t e = t0 + w * (32 * BWT_R) + r * 32 + lane;
-			if (e < m) store(LFM_WC(w, dl[r] >> 16) + (dl[r] & 0xffffu), pay[r]);
-		}
-		__syncthreads();
+		for (int r = 0; r < R; r++) if (eb + r * 32 < m) store(myc[dl[r] >> 16] + (dl[r] & 0xffffu), pay[r]);
+		__syncwarp();
+		for (uint32_t i = lane; i < BWT_WS; i += 32) myc[i] = 0;
+		__syncwarp();
 	}
+	__syncthreads();
 }
 
-// per-warp private histograms (match.any aggregated, no atomics) of an 8-bit digit over m elements,
+// per-warp private histograms (match.any aggregated) of an 8-bit digit over m elements,
 // reduced and exclusive-scanned into run[256]
 template <class DigitOfIndex>
 __device__ __forceinline__ void digit_starts(uint32_t m, uint32_t* run, uint32_t* wcnt, uint32_t* red, DigitOfIndex dig)
 {
 	const uint32_t lane = lane_id(), w = warp_id();
-	for (uint32_t i = threadIdx.x; i < BWT_NW * BWT_WS; i += BWT_NT) wcnt[i] = 0;
+	const uint32_t lt = (1u << lane) - 1u;
+	uint32_t* myc = wcnt + w * BWT_WS;
+	constexpr int U = 4;
 	__syncthreads();
-	for (uint32_t e0 = 0; e0 < m; e0 += BWT_NT) {
-		uint32_t e = e0 + threadIdx.x;
-		bool act = e < m;
-		uint32_t amask = __ballot_sync(0xffffffffu, act);
-		if (act) {
-			uint32_t d = dig(e);
-			uint32_t peers = __match_any_sync(amask, d);
-			if (lane == (uint32_t)(__ffs(peers) - 1)) LFM_WC(w, d) += __popc(peers);
-		}
-		__syncwarp();
+	for (uint32_t i = lane; i < BWT_WS; i += 32) myc[i] = 0;
+	__syncwarp();
+	for (uint32_t e0 = w * (32 * U); e0 < m; e0 += BWT_NT * U) {        // warp-uniform trip count
+		uint32_t d[U], peers[U];
+		#pragma unroll
+		for (int u = 0; u < U; u++) { const uint32_t e = e0 + u * 32 + lane; d[u] = e < m ? dig(e) : 256u; }
+		#pragma unroll
+		for (int u = 0; u < U; u++) peers[u] = __match_any_sync(0xffffffffu, d[u]);
+		#pragma unroll
+		for (int u = 0; u < U; u++) if ((peers[u] & lt) == 0) atomicAdd(&myc[d[u]], (uint32_t)__popc(peers[u]));
 	}
 	__syncthreads();
 	if (threadIdx.x < 256) {
@@ -105,20 +113,24 @@ __device__ __forceinline__ void digit_starts(uint32_t m, uint32_t* run, uint32_t
 	scan256_excl<BWT_NT>(run, red);
 }
 
-// Split a sorted list of `cnt` entries into groups of equal keys.
-//   is_head(i)   : entry i starts a new group (must return true for i == 0 and i >= cnt)
-//   pos_of(i)    : position of entry i in the suffix array (ascending in i)
-//   emit(i, head_pos, unresolved, slot) : called once per entry; slot = index among the unresolved entries
-// returns the number of unresolved entries (members of groups larger than 1). Uniform across the CTA.
-template <class HeadFn, class PosFn, class EmitFn>
-__device__ __forceinline__ uint32_t split_groups(uint32_t cnt, uint32_t* red, HeadFn is_head, PosFn pos_of, EmitFn emit)
+// Walk cnt sorted entries; entry j is a group head when its 64-bit key differs from the key of entry j-1.
+// group head value pos_of(j) is propagated to the members (max-scan, heads ascend), singleton groups are resolved,
+// the others are appended (compacted, order kept) to the next unresolved set.
+// emit(j, head, unresolved, slot) is called once per entry. Returns the number of unresolved entries.
+template <class KeyFn, class PosFn, class EmitFn>
+__device__ __forceinline__ uint32_t split_groups(uint32_t cnt, uint32_t* red, KeyFn key_of, PosFn pos_of, EmitFn emit)
 {
 	uint32_t carry_head = 0, carry_cnt = 0;
 	for (uint32_t t0 = 0; t0 < cnt; t0 += BWT_NT * SPLIT_R) {
 		uint32_t i0 = t0 + threadIdx.x * SPLIT_R;
 		bool hd[SPLIT_R + 1]; uint32_t gh[SPLIT_R];
-		#pragma unroll
-		for (int r = 0; r <= SPLIT_R; r++) hd[r] = is_head(i0 + r);
+		{
+			uint64_t ky[SPLIT_R + 2];
+			#pragma unroll
+			for (int r = 0; r < SPLIT_R + 2; r++) { const uint32_t j = i0 + r; ky[r] = (j >= 1 && j <= cnt) ? key_of(j - 1) : 0; }
+			#pragma unroll
+			for (int r = 0; r <= SPLIT_R; r++) { const uint32_t j = i0 + r; hd[r] = (j == 0 || j >= cnt) ? true : (ky[r] != ky[r + 1]); }
+		}
 		uint32_t local = 0;
 		#pragma unroll
 		for (int r = 0; r < SPLIT_R; r++) { if (i0 + r < cnt && hd[r]) local = pos_of(i0 + r); gh[r] = local; }

@@ -32,7 +32,7 @@ k_select_sort(CandPtrs cands, uint64_t fpx, uint32_t chunk_px, uint32_t nchunks,
 		return (uint32_t)b[n - 1];                      // key 0
 	};
 	digit_starts(m, run, wcnt, red, [&](uint32_t e) { return e < n ? (uint32_t)b[e] : 0u; });
-	radix_scatter<uint32_t>(m, run, wcnt, pair_of,
+	radix_scatter<BWT_R, uint32_t>(m, run, wcnt, pair_of,
 		[&](uint32_t p) { return p >> 8; },
 		[&](uint32_t pos, uint32_t p) { dst[pos] = (uint8_t)p; });
 }

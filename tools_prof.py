@@ -6,7 +6,7 @@ from conftest import lf_synth
 L = importlib.import_module("lightfieldmicroscopy_pc-bzip2_b200")
 wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-nfr, H, W, nnum, way, hv = {"c2": (1, 2048, 2048, 15, 2, 12), "c3s": (16, 2048, 2048, 13, 1, 0)}[wl]
+nfr, H, W, nnum, way, hv = {"c2": (1, 2048, 2048, 15, 2, 12), "c3s": (16, 2048, 2048, 13, 1, 0), "c3f": (16, 2048, 2048, 13, 1, 12), "c4s": (32, 1024, 1024, 13, 0, 0x80 | 12)}[wl]
 L.set_devices(0, 1); L.set_way(way)
 a = lf_synth((nfr, H, W), nnum)
 d = torch.from_numpy(a.view(np.int16)).cuda(); out = torch.empty_like(d)
