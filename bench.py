@@ -197,7 +197,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    acc = dict(tc=0.0, td=0.0, bwt=0.0, rle=0.0, mtf=0.0, huff=0.0, dec=0.0, ibwt=0.0, unrle=0.0, launches=0, payload=0)
+    acc = dict(tc=0.0, td=0.0, pred=0.0, sel=0.0, bwt=0.0, rle=0.0, mtf=0.0, huff=0.0, dec=0.0, ibwt=0.0, unrle=0.0, unpred=0.0, launches=0, payload=0)
 
     def step_device(i, timed):
         d = dpool[i % POOL]
@@ -213,7 +213,7 @@ def main():
         sd = L.stats()
         if timed:
             acc["tc"] += t1 - t0; acc["td"] += t2 - t1
-            acc["bwt"] += sc.ms_bwt; acc["rle"] += sc.ms_rle; acc["mtf"] += sc.ms_mtf; acc["huff"] += sc.ms_huff
+            acc["pred"] += sc.ms_predict; acc["sel"] += sc.ms_select; acc["unpred"] += sd.ms_unpredict; acc["bwt"] += sc.ms_bwt; acc["rle"] += sc.ms_rle; acc["mtf"] += sc.ms_mtf; acc["huff"] += sc.ms_huff
             acc["dec"] += sd.ms_decode; acc["ibwt"] += sd.ms_ibwt; acc["unrle"] += sd.ms_unrle
             acc["launches"] += sc.gpu_launches + sd.gpu_launches; acc["payload"] += pb.value
         return d
@@ -231,20 +231,27 @@ def main():
     ev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
 
-    # ---- e2e through the C ABI with host buffers
+    # ---- e2e through the C ABI with HOST buffers (pinned, as the contract allows): every step copies the raw stack
+    # host->device, compresses, copies the .lfm image device->host, then copies it back in, decodes and copies the
+    # decoded stack device->host.  Buffers are caller-owned (lfmCompressToBuffer / lfmDecompressFromMemory).
+    EP = min(POOL, 4)
+    hin = [torch.from_numpy(pool[i].view(np.int16)).pin_memory() for i in range(EP)]
+    hin_np = [t.numpy().view(np.uint16) for t in hin]
+    hblob = torch.empty(raw + raw // 2 + (1 << 20), dtype=torch.uint8).pin_memory(); hblob_np = hblob.numpy()
+    hout = torch.empty_like(hin[0]).pin_memory(); hout_np = hout.numpy().view(np.uint16)
     e2e = dict(tc=0.0, td=0.0, h2d=0, d2h=0)
     for i in range(2 + args.steps):
-        a = pool[i % POOL]
+        a = hin_np[i % EP]
         t0 = time.perf_counter()
-        blob = L.compress_to_bytes(a, header_version=hv, nnum=nnum, way=way)
+        nblob = L.compress_into(a, hblob_np, header_version=hv, nnum=nnum, way=way)
         t1 = time.perf_counter()
-        back = L.decompress_from_bytes(blob, a.shape, way=way)
+        L.decompress_into(hblob_np, nblob, hout_np, way=way)
         t2 = time.perf_counter()
-        if i == 0:
-            assert np.array_equal(back, a), "e2e round trip mismatch"
-        if i >= 2:
+        if i < 2:
+            assert np.array_equal(hout_np, a), "e2e round trip mismatch"
+        else:
             e2e["tc"] += t1 - t0; e2e["td"] += t2 - t1
-            e2e["h2d"] += a.nbytes + len(blob); e2e["d2h"] += len(blob) + a.nbytes
+            e2e["h2d"] += a.nbytes + nblob; e2e["d2h"] += nblob + a.nbytes
     barrier()
 
     t_step = torch.tensor([t_all, e2e["tc"] + e2e["td"]], dtype=torch.float64, device="cuda")
@@ -266,7 +273,7 @@ def main():
         n_post_rle = raw                        # LF-synth frames have no long runs: post-RLE1 length == raw length within 0.1 %
         bwt_ms = acc["bwt"] / args.steps
         achieved = 2.0 * n_post_rle / (bwt_ms * 1e-3) / 1e9 if bwt_ms > 0 else 0.0
-        stage_ms = {k: acc[k] / args.steps for k in ("rle", "bwt", "mtf", "huff", "dec", "ibwt", "unrle")}
+        stage_ms = {k: acc[k] / args.steps for k in ("sel", "pred", "rle", "bwt", "mtf", "huff", "dec", "ibwt", "unrle", "unpred")}
         try:
             rb = reference_round_trip(pool[:4], nnum, way, hv, 3, 1)
             cpu = {"value": rb["raw"] / (rb["tc"] + rb["td"]) / 1e9, "unit": "GB/s", "cores": rb["cores"], "kind": rb["kind"], "sample": rb["sample"],

@@ -39,6 +39,10 @@ int readLFMheaderEx(const char* filename, uint8_t* headerVersion, uint8_t* Nnum)
    buffer the caller free()s. Same arguments as writeLFMstackEx. */
 int lfmCompressToMemory(const void* im, const uint32_t xyzct[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS],
                         uint8_t headerVersion, uint8_t Nnum, void** file_bytes, uint64_t* file_size);
+/* same, into a caller-owned HOST buffer of `capacity` bytes (pinned memory makes the D2H copy a straight DMA);
+   *file_size receives the size needed; returns 5 when the buffer is too small (nothing is written then) */
+int lfmCompressToBuffer(const void* im, const uint32_t xyzct[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS],
+                        uint8_t headerVersion, uint8_t Nnum, void* file_bytes, uint64_t capacity, uint64_t* file_size);
 /* inverse: decode a complete .lfm file image held in HOST memory into im (host, full stack) */
 int lfmDecompressFromMemory(const void* file_bytes, uint64_t file_size, void* im);
 

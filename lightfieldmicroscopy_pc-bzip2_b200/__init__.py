@@ -67,6 +67,8 @@ lib.readLFMheaderEx.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.POINTER(C.c_
 lib.readLFMheaderEx.restype = C.c_int
 lib.lfmCompressToMemory.argtypes = [C.c_void_p, _u32x5, C.c_void_p, C.c_uint8, C.c_uint8, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
 lib.lfmCompressToMemory.restype = C.c_int
+lib.lfmCompressToBuffer.argtypes = [C.c_void_p, _u32x5, C.c_void_p, C.c_uint8, C.c_uint8, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+lib.lfmCompressToBuffer.restype = C.c_int
 lib.lfmDecompressFromMemory.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
 lib.lfmDecompressFromMemory.restype = C.c_int
 lib.lfmCompressDevice.argtypes = [C.c_void_p, _u32x5, C.c_void_p, C.c_uint8, C.c_uint8, C.POINTER(C.c_uint8), C.c_void_p, C.c_uint64,
@@ -85,7 +87,7 @@ _libc.free.argtypes = [C.c_void_p]
 
 EXPORTS = ["writeKLBstack", "writeKLBstackSlices", "readKLBheader", "readKLBstack", "readKLBstackInPlace", "readKLBroiInPlace",
            "lfmSetPredictorWay", "lfmGetPredictorWay", "lfmSetDevices", "writeLFMstackEx", "readLFMheaderEx",
-           "lfmCompressToMemory", "lfmDecompressFromMemory", "lfmCompressDevice", "lfmDecompressDevice", "lfmNumBlocks",
+           "lfmCompressToMemory", "lfmCompressToBuffer", "lfmDecompressFromMemory", "lfmCompressDevice", "lfmDecompressDevice", "lfmNumBlocks",
            "lfmGetLastStats", "lfmLastError", "lfmDebugEncodeBlock"]
 
 
@@ -188,6 +190,32 @@ def compress_to_bytes(img, header_version=0, nnum=13, block_size=None, way=None)
         return C.string_at(p.value, n.value)
     finally:
         _libc.free(p)
+
+
+def compress_into(img, out, header_version=0, nnum=13, block_size=None, way=None):
+    """compress a host stack into the caller's uint8 buffer `out` (numpy array, e.g. a view of pinned memory);
+    returns the number of bytes written"""
+    assert img.dtype == np.uint16 and img.flags.c_contiguous and out.dtype == np.uint8 and out.flags.c_contiguous
+    if way is not None:
+        set_way(way)
+    n = C.c_uint64()
+    bs = _bs(block_size)
+    rc = lib.lfmCompressToBuffer(img.ctypes.data, _xyzct(img.shape), C.cast(bs, C.c_void_p) if bs is not None else None,
+                                 header_version, nnum, out.ctypes.data, out.nbytes, C.byref(n))
+    if rc:
+        raise LfmError(rc, "lfmCompressToBuffer")
+    return n.value
+
+
+def decompress_into(data, nbytes, out, way=None):
+    """decode the .lfm image held in the uint8 array `data[:nbytes]` into the caller's uint16 array `out`"""
+    assert out.dtype == np.uint16 and out.flags.c_contiguous
+    if way is not None:
+        set_way(way)
+    rc = lib.lfmDecompressFromMemory(data.ctypes.data, nbytes, out.ctypes.data)
+    if rc:
+        raise LfmError(rc, "lfmDecompressFromMemory")
+    return out
 
 
 def decompress_from_bytes(data, shape, way=None):

@@ -27,7 +27,7 @@ constexpr int DEC_LB = 10;                       // lookup bits
 constexpr int DEC_LUT = 1 << DEC_LB;
 
 struct DecWarpSmem {
-	uint16_t lut[kGroups][DEC_LUT];              // sym | len << 9   (0: longer than DEC_LB bits)
+	uint16_t lut[kGroups][DEC_LUT];              // len | sym << 5   (0: longer than DEC_LB bits)
 	int32_t  limit[kGroups][24];
 	int32_t  base[kGroups][24];
 	uint16_t perm[kGroups][kMaxAlpha + 2];
@@ -36,6 +36,7 @@ struct DecWarpSmem {
 };
 
 constexpr uint32_t DEC_RING = 256;               // staged stream words per warp (power of two)
+constexpr uint32_t DEC_OUT = 128;                // staged output symbols per warp (power of two)
 
 extern __shared__ __align__(16) uint8_t dec_smem[];
 
@@ -47,10 +48,11 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	const uint32_t lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
 	const uint32_t job = blockIdx.x * nw + w;
 	if (job >= njobs) return;
-	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)DEC_RING * 4;
+	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)DEC_RING * 4 + (size_t)DEC_OUT * 2;
 	DecWarpSmem& S = *reinterpret_cast<DecWarpSmem*>(dec_smem + (size_t)w * per_warp);
 	uint8_t* selector = dec_smem + (size_t)w * per_warp + sizeof(DecWarpSmem);
 	uint32_t* sw = reinterpret_cast<uint32_t*>(selector + selcap);
+	uint16_t* so = reinterpret_cast<uint16_t*>(sw + DEC_RING);           // decoded symbols, flushed 32 at a time
 	DecJob& J = jobs[job];
 	uint16_t* mtfv = mtfv_all + (size_t)job * mcap;
 	const uint8_t* src = payload + begin[job];
@@ -82,13 +84,16 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	};
 	top_up();
 
-	// ---- uniform bit reader: bb holds bc >= 32 valid bits, left aligned; wi = next word to pull from the ring
+	// ---- uniform bit reader: bb holds bc >= 32 valid bits, left aligned (zeros below them); nxt = ring word wi, already
+	// in a register, so a refill is two shifts and an OR on the critical path and the shared load of the following word
+	// overlaps the next symbols
 	uint64_t bb = ((uint64_t)sw[0] << 32) | sw[1];
 	uint32_t bc = 64; wi = 2;
+	uint32_t nxt = sw[2];
 	const uint32_t wi_limit = nwords + 4;                  // a well-formed stream never needs words beyond this
 	auto drop = [&](uint32_t nb) {                         // nb <= 32
 		bb <<= nb; bc -= nb;
-		if (bc < 32) { bb |= (uint64_t)sw[wi & (DEC_RING - 1)] << (32 - bc); bc += 32; wi++; }
+		if (bc < 32) { bb |= (uint64_t)nxt << (32 - bc); bc += 32; wi++; nxt = sw[wi & (DEC_RING - 1)]; }
 	};
 	auto peek = [&](uint32_t nb) -> uint32_t { return (uint32_t)(bb >> (64 - nb)); };
 	auto get = [&](uint32_t nb) -> uint32_t { uint32_t v = peek(nb); drop(nb); return v; };
@@ -169,7 +174,7 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 				int sym = S.perm[t][p], l = S.len[t][sym];
 				if (l > DEC_LB) break;
 				uint32_t span = 1u << (DEC_LB - l);
-				uint16_t e = (uint16_t)(sym | (l << 9));
+				uint16_t e = (uint16_t)(l | (sym << 5));
 				for (uint32_t q = 0; q < span && fill + q < (uint32_t)DEC_LUT; q++) S.lut[t][fill + q] = e;
 				fill += span;
 			}
@@ -185,18 +190,49 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 
 	// ---- symbols (decompress.c:349-487 without the MTF): append until EOB. One lookup per symbol; the rare events
 	// (code longer than DEC_LB bits, 32-symbol flush + ring top-up, next selector) stay off the common path.
+	// One group of 50 symbols per outer iteration.  The inner loop has ONE branch: it leaves on a long code, on EOB or at
+	// the end of the group.  Consuming a LUT entry is pure register arithmetic that is a no-op for the "long code" entry
+	// 0, so it is done before the exit test and stays off the branch's shadow; the refill is predicated; the symbol goes
+	// to a shared staging ring (lane 0), which is flushed with coalesced stores at the group boundaries.
 	const uint32_t EOB = n_in_use + 1;
-	uint32_t nsym = 0, obuf = 0;
+	uint32_t nsym = 0, flushed = 0;
 	bool done = false;
+	uint32_t hi = (uint32_t)(bb >> 32), lo = (uint32_t)bb;
 	for (int grp = 0; !done; grp++) {
 		if (grp >= n_sel) FAIL(2);
 		const int t = selector[grp];
 		if (t >= n_groups) FAIL(2);
 		const uint16_t* lut = S.lut[t];
-		#pragma unroll 1
-		for (int k = 0; k < kGSize; k++) {
-			uint32_t e = lut[(uint32_t)(bb >> (64 - DEC_LB))];
-			if (e == 0) {
+		uint32_t k = 0;
+		bool stop = false;
+		while (!stop && k < (uint32_t)kGSize) {
+			uint32_t e;
+			#pragma unroll 1
+			for (;;) {
+				// lazy refill, decided on the bit count left by the PREVIOUS symbol: off the lookup -> shift -> lookup chain.
+				// At least 13 valid bits are always present, so the DEC_LB-bit index does not depend on the inserted word.
+				const uint32_t idx = hi >> (32 - DEC_LB);
+				const bool fill = bc <= 32u;
+				const uint64_t add = (uint64_t)nxt << ((32u - bc) & 31u);
+				hi |= fill ? (uint32_t)(add >> 32) : 0u;
+				lo |= fill ? (uint32_t)add : 0u;
+				bc += fill ? 32u : 0u;
+				wi += fill ? 1u : 0u;
+				nxt = sw[wi & (DEC_RING - 1)];
+				e = lut[idx];                                                      // len | sym << 5   (0: longer than DEC_LB bits)
+				if ((e == 0u) | stop | (k >= (uint32_t)kGSize)) break;
+				const uint32_t nhi = __funnelshift_l(lo, hi, e);                   // funnel shifts take their count modulo 32
+				lo = __funnelshift_l(0u, lo, e);
+				hi = nhi;
+				bc -= e & 31u;
+				const uint32_t sym = e >> 5;
+				if (lane == 0) so[nsym & (DEC_OUT - 1)] = (uint16_t)sym;
+				nsym++; k++;
+				stop = (sym == EOB);
+			}
+			if (stop || k >= (uint32_t)kGSize) break;
+			{   // code longer than DEC_LB bits: bzip2's limit/base/perm walk (decompress.c GET_MTF_VAL)
+				bb = ((uint64_t)hi << 32) | lo;
 				const uint32_t window = peek(20);
 				const int32_t* limit = S.limit[t]; const int32_t* base = S.base[t];
 				int zn = S.minlen[t]; int32_t zvec = (int32_t)(window >> (20 - zn));
@@ -208,21 +244,24 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 				}
 				int32_t idx = zvec - base[zn];
 				if (idx < 0 || idx >= kMaxAlpha) FAIL(2);
-				e = (uint32_t)S.perm[t][idx] | ((uint32_t)zn << 9);
+				const uint32_t sym = S.perm[t][idx];
+				drop((uint32_t)zn);
+				hi = (uint32_t)(bb >> 32); lo = (uint32_t)bb;
+				if (lane == 0) so[nsym & (DEC_OUT - 1)] = (uint16_t)sym;
+				nsym++; k++;
+				stop = (sym == EOB);
 			}
-			const uint32_t sym = e & 511u;
-			drop(e >> 9);
-			if (lane == (nsym & 31u)) obuf = sym;
-			nsym++;
-			if ((nsym & 31u) == 0) {
-				mtfv[nsym - 32 + lane] = (uint16_t)obuf;
-				if (nsym + 32 >= mcap || wi > wi_limit) FAIL(2);
-				top_up();
-			}
-			if (sym == EOB) { done = true; break; }
 		}
+		done = stop;
+		if (nsym > mcap || wi > wi_limit) FAIL(2);               // more symbols than any block of this geometry can hold
+		__syncwarp();
+		while (flushed + 32 <= nsym) { mtfv[flushed + lane] = so[(flushed + lane) & (DEC_OUT - 1)]; flushed += 32; }
+		__syncwarp();
+		top_up();
 	}
-	if (nsym & 31u) { if (lane < (nsym & 31u)) mtfv[(nsym & ~31u) + lane] = (uint16_t)obuf; }
+	if (flushed + lane < nsym) mtfv[flushed + lane] = so[(flushed + lane) & (DEC_OUT - 1)];
+	bb = ((uint64_t)hi << 32) | lo;
+	if (bc <= 32u) { bb |= (uint64_t)nxt << (32u - bc); bc += 32u; wi++; nxt = sw[wi & (DEC_RING - 1)]; }      // back to the header reader's invariant
 	// the stream must end here: end-of-stream magic + combined CRC (single block: == block CRC)
 	uint32_t e1 = get(24), e2 = get(24);
 	if (e1 == 0x314159 && e2 == 0x265359) FAIL(4);            // multi-block stream: not supported in this version
@@ -601,7 +640,7 @@ k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* 
 int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t* end, uint32_t njobs, DecJob* jobs,
                   uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap, cudaStream_t st)
 {
-	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)DEC_RING * 4;
+	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)DEC_RING * 4 + (size_t)DEC_OUT * 2;
 	int nw = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
 	if (nw < 1) return 1;
 	const size_t smem = per_warp * nw;

@@ -379,68 +379,62 @@ constexpr int HP_NT = 256;
 constexpr int HP_SYMS = 8;     // symbols per thread per packing tile
 constexpr uint16_t HP_NOPARENT = 0xFFFFu;
 
-__device__ __forceinline__ uint32_t hp_hi(uint64_t e) { return (uint32_t)(e >> 32); }
+constexpr int HP_HEAP = 2 * kMaxAlpha + 8;          // heap slots per table: every child index of a live node exists
+constexpr uint32_t HP_INF = 0xFFFFFFFFu;             // weight of an empty heap slot (real weights stay below 2^29)
 
-// exact restatement of BZ2_hbMakeCodeLengths: same heap discipline (strict '<' everywhere), same weight arithmetic,
-// same rescale loop.  Warp-cooperative: call with all 32 lanes.
-__device__ void make_code_lengths_warp(uint8_t* len, const uint32_t* freq, int alpha, int max_len,
-                                       uint64_t* heap, uint16_t* parent, uint32_t* lw, uint32_t lane)
+// Exact restatement of the tree construction of BZ2_hbMakeCodeLengths (huffman.c:63-148) for ONE table, run by ONE
+// lane: same heap discipline (strict '<' everywhere), same weight arithmetic.  The lanes of a warp build the tables
+// of a block side by side (one lane per table), so the sequential part costs the issue slots of one warp.
+//   heap entry = weight << 32 | node, ordered by weight only; slot 0 holds weight 0 (every up-heap stops there);
+//   slots past the heap hold HP_INF, and both children of a slot sit in one 16-byte word: a down-heap level is one
+//   shared-memory load, two compares and one store, with no bounds test.
+// Leaves are nodes 1..alpha with weights lw[1..alpha]; parent[] receives the links (HP_NOPARENT at the root).
+__device__ __forceinline__ void hp_build_tree(uint64_t* heap, uint16_t* parent, const uint32_t* lw, int alpha)
 {
-	for (int i = (int)lane; i < alpha; i += 32) lw[i + 1] = (freq[i] == 0 ? 1u : freq[i]) << 8;
-	__syncwarp();
-	for (;;) {
-		if (lane == 0) {
-			int n_nodes = alpha, n_heap = 0;
-			heap[0] = 0;                                   // weight 0 sentinel: every up-heap stops here
-			for (int i = 1; i <= alpha; i++) {
-				parent[i] = HP_NOPARENT;
-				const uint32_t wt = lw[i];
-				int z = ++n_heap;
-				for (;;) { const uint64_t up = heap[z >> 1]; if (!(wt < hp_hi(up))) break; heap[z] = up; z >>= 1; }
-				heap[z] = ((uint64_t)wt << 32) | (uint32_t)i;
-			}
-			while (n_heap > 1) {
-				uint64_t pick[2];
-				#pragma unroll
-				for (int q = 0; q < 2; q++) {
-					pick[q] = heap[1];
-					const uint64_t tmp = heap[n_heap--];
-					const uint32_t tw = hp_hi(tmp);
-					int z = 1;
-					for (;;) {
-						int y = z << 1;
-						if (y > n_heap) break;
-						uint64_t c = heap[y];
-						if (y < n_heap) { const uint64_t c1 = heap[y + 1]; if (hp_hi(c1) < hp_hi(c)) { c = c1; y++; } }
-						if (tw < hp_hi(c)) break;
-						heap[z] = c; z = y;
-					}
-					heap[z] = tmp;
-				}
-				n_nodes++;
-				parent[(uint32_t)pick[0]] = (uint16_t)n_nodes; parent[(uint32_t)pick[1]] = (uint16_t)n_nodes;
-				const uint32_t w1 = hp_hi(pick[0]), w2 = hp_hi(pick[1]);
-				const uint32_t d1 = w1 & 0xffu, d2 = w2 & 0xffu;
-				const uint32_t nwt = ((w1 & 0xffffff00u) + (w2 & 0xffffff00u)) | (1u + (d1 > d2 ? d1 : d2));
-				parent[n_nodes] = HP_NOPARENT;
-				int z = ++n_heap;
-				for (;;) { const uint64_t up = heap[z >> 1]; if (!(nwt < hp_hi(up))) break; heap[z] = up; z >>= 1; }
-				heap[z] = ((uint64_t)nwt << 32) | (uint32_t)n_nodes;
-			}
-		}
-		__syncwarp();
-		bool too_long = false;
-		for (int i = (int)lane + 1; i <= alpha; i += 32) {
-			int j = 0, k = i;
-			while (parent[k] != HP_NOPARENT) { k = parent[k]; j++; }
-			len[i - 1] = (uint8_t)j;
-			if (j > max_len) too_long = true;
-		}
-		if (!__any_sync(0xffffffffu, too_long)) break;
-		for (int i = (int)lane + 1; i <= alpha; i += 32) { uint32_t j = lw[i] >> 8; j = 1 + (j / 2); lw[i] = j << 8; }
-		__syncwarp();
+	for (int i = 0; i < 2 * alpha + 6; i++) heap[i] = (uint64_t)HP_INF << 32;
+	heap[0] = 0;
+	int n_heap = 0;
+	for (int i = 1; i <= alpha; i++) {
+		parent[i] = HP_NOPARENT;
+		const uint32_t wt = lw[i];
+		int z = ++n_heap;
+		for (;;) { const uint64_t up = heap[z >> 1]; if (!(wt < (uint32_t)(up >> 32))) break; heap[z] = up; z >>= 1; }
+		heap[z] = ((uint64_t)wt << 32) | (uint32_t)i;
 	}
-	__syncwarp();
+	int n_nodes = alpha;
+	while (n_heap > 1) {
+		uint64_t pick[2];
+		#pragma unroll
+		for (int q = 0; q < 2; q++) {
+			pick[q] = heap[1];
+			const uint64_t tmp = heap[n_heap];
+			heap[n_heap] = (uint64_t)HP_INF << 32;
+			n_heap--;
+			const uint32_t tw = (uint32_t)(tmp >> 32);
+			int z = 1;
+			if (n_heap >= 1) {
+				for (;;) {
+					const int y = z << 1;
+					const ulonglong2 ch = *reinterpret_cast<const ulonglong2*>(heap + y);     // children y, y+1
+					const uint32_t w0 = (uint32_t)(ch.x >> 32), w1 = (uint32_t)(ch.y >> 32);
+					const bool right = w1 < w0;
+					const uint64_t c = right ? ch.y : ch.x;
+					if (tw < (right ? w1 : w0)) break;                                         // HP_INF below the heap: always stops
+					heap[z] = c; z = y + (right ? 1 : 0);
+				}
+				heap[z] = tmp;
+			}
+		}
+		n_nodes++;
+		parent[(uint32_t)pick[0]] = (uint16_t)n_nodes; parent[(uint32_t)pick[1]] = (uint16_t)n_nodes;
+		const uint32_t w1 = (uint32_t)(pick[0] >> 32), w2 = (uint32_t)(pick[1] >> 32);
+		const uint32_t d1 = w1 & 0xffu, d2 = w2 & 0xffu;
+		const uint32_t nwt = ((w1 & 0xffffff00u) + (w2 & 0xffffff00u)) | (1u + (d1 > d2 ? d1 : d2));
+		parent[n_nodes] = HP_NOPARENT;
+		int z = ++n_heap;
+		for (;;) { const uint64_t up = heap[z >> 1]; if (!(nwt < (uint32_t)(up >> 32))) break; heap[z] = up; z >>= 1; }
+		heap[z] = ((uint64_t)nwt << 32) | (uint32_t)n_nodes;
+	}
 }
 
 // sequential MSB-first bit writer used by thread 0 for the fixed part of the block header (whole big-endian words)
@@ -477,14 +471,18 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 	__shared__ uint32_t rfreq[kGroups][kMaxAlpha + 2];
 	__shared__ uint8_t  len[kGroups][kMaxAlpha + 2];
 	__shared__ uint32_t code[kGroups][kMaxAlpha + 2];
-	__shared__ __align__(16) uint64_t hheap[kGroups][kMaxAlpha + 6];
+	extern __shared__ __align__(16) uint8_t hp_smem[];
+	uint64_t (*hheap)[HP_HEAP] = reinterpret_cast<uint64_t (*)[HP_HEAP]>(hp_smem);     // [kGroups][HP_HEAP], 16-byte aligned rows
 	__shared__ uint16_t hparent[kGroups][kMaxAlpha * 2 + 4];
 	__shared__ uint32_t hlw[kGroups][kMaxAlpha + 2];
+	__shared__ __align__(16) uint4 lenpack[kMaxAlpha + 2];            // code lengths of tables (0,1) (2,3) (4,5), 16 bits each
 	__shared__ uint32_t red[64];
 	__shared__ uint32_t s_tbits[kGroups + 2];
 	__shared__ uint32_t s_ngroups;
-	uint32_t* win = reinterpret_cast<uint32_t*>(&hheap[0][0]);     // packing window; reused once the tables are final
-	static_assert(sizeof(hheap) >= (HP_NT * HP_SYMS * 20 / 32 + 4) * 4, "window must fit");
+	__shared__ uint32_t s_redo;
+	uint32_t* win = reinterpret_cast<uint32_t*>(hp_smem);          // packing window; reused once the tables are final
+	static_assert(sizeof(uint64_t) * kGroups * HP_HEAP >= (HP_NT * HP_SYMS * 20 / 32 + 4) * 4, "window must fit");
+	static_assert((HP_HEAP * 8) % 16 == 0, "heap rows must stay 16-byte aligned");
 
 	const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
 	const uint32_t job = blockIdx.x;
@@ -539,26 +537,77 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 	const uint32_t n_sel = (n_mtf + kGSize - 1) / kGSize;
 
 	// ---- 4 refinement passes (compress.c:321-453)
+	const uint32_t* mtfv32 = reinterpret_cast<const uint32_t*>(mtfv);          // slots are 16-byte aligned, groups start on even indices
 	for (int iter = 0; iter < 4; iter++) {
 		for (uint32_t i = tid; i < kGroups * (kMaxAlpha + 2); i += HP_NT) (&rfreq[0][0])[i] = 0;
-		__syncthreads();
-		for (uint32_t gi = tid; gi < n_sel; gi += HP_NT) {
-			uint32_t gs = gi * kGSize, ge = min(gs + kGSize, n_mtf);
-			uint32_t cost[kGroups] = { 0, 0, 0, 0, 0, 0 };
-			for (uint32_t i = gs; i < ge; i++) {
-				uint32_t sy = mtfv[i];
-				#pragma unroll
-				for (int t = 0; t < kGroups; t++) if (t < ng) cost[t] += len[t][sy];
-			}
-			int bt = 0; uint32_t bc = cost[0];
-			#pragma unroll
-			for (int t = 1; t < kGroups; t++) if (t < ng && cost[t] < bc) { bc = cost[t]; bt = t; }
-			selector[gi] = (uint8_t)bt;
-			for (uint32_t i = gs; i < ge; i++) atomicAdd(&rfreq[bt][mtfv[i]], 1u);
+		for (uint32_t i = tid; i < (uint32_t)alpha; i += HP_NT) {             // the cost of a symbol under all tables in one 16-byte word
+			uint4 q;
+			q.x = (uint32_t)len[0][i] | ((uint32_t)len[1][i] << 16);
+			q.y = ng > 2 ? ((uint32_t)len[2][i] | ((ng > 3 ? (uint32_t)len[3][i] : 255u) << 16)) : 0x00ff00ffu;
+			q.z = ng > 4 ? ((uint32_t)len[4][i] | ((ng > 5 ? (uint32_t)len[5][i] : 255u) << 16)) : 0x00ff00ffu;
+			q.w = 0;
+			lenpack[i] = q;
 		}
 		__syncthreads();
-		if ((int)wid < ng) make_code_lengths_warp(len[wid], rfreq[wid], alpha, 17, hheap[wid], hparent[wid], hlw[wid], lane);
+		for (uint32_t gi = tid; gi < n_sel; gi += HP_NT) {
+			const uint32_t gs = gi * kGSize, ge = min(gs + kGSize, n_mtf);
+			uint32_t c01 = 0, c23 = 0, c45 = 0;
+			const uint32_t full = (ge - gs) >> 1;
+			#pragma unroll 5
+			for (uint32_t j = 0; j < full; j++) {
+				const uint32_t two = __ldg(mtfv32 + (gs >> 1) + j);
+				const uint4 a = lenpack[two & 0xffffu], b = lenpack[two >> 16];
+				c01 += a.x + b.x; c23 += a.y + b.y; c45 += a.z + b.z;
+			}
+			if ((ge - gs) & 1u) { const uint4 a = lenpack[mtfv[ge - 1]]; c01 += a.x; c23 += a.y; c45 += a.z; }
+			// tables that do not exist cost 255 per symbol: never chosen (a real table costs at most 20 per symbol);
+			// ties go to the lowest table, as in compress.c:383-386
+			uint32_t bc = c01 & 0xffffu; int bt = 0;
+			if ((c01 >> 16) < bc) { bc = c01 >> 16; bt = 1; }
+			if ((c23 & 0xffffu) < bc) { bc = c23 & 0xffffu; bt = 2; }
+			if ((c23 >> 16) < bc) { bc = c23 >> 16; bt = 3; }
+			if ((c45 & 0xffffu) < bc) { bc = c45 & 0xffffu; bt = 4; }
+			if ((c45 >> 16) < bc) { bc = c45 >> 16; bt = 5; }
+			selector[gi] = (uint8_t)bt;
+			uint32_t* rf = rfreq[bt];
+			for (uint32_t j = 0; j < full; j++) {
+				const uint32_t two = __ldg(mtfv32 + (gs >> 1) + j);
+				atomicAdd(&rf[two & 0xffffu], 1u); atomicAdd(&rf[two >> 16], 1u);
+			}
+			if ((ge - gs) & 1u) atomicAdd(&rf[mtfv[ge - 1]], 1u);
+		}
 		__syncthreads();
+		// exact bzip2 code lengths (huffman.c:63-148): leaf weights, then [tree by one lane per table -> depths by one warp
+		// per table -> halve the weights of a table whose depth exceeds 17 and rebuild it], usually a single round
+		for (uint32_t i = tid; i < (uint32_t)ng * (uint32_t)alpha; i += HP_NT) {
+			const uint32_t t = i / (uint32_t)alpha, v2 = i - t * (uint32_t)alpha;
+			const uint32_t fq = rfreq[t][v2];
+			hlw[t][v2 + 1] = (fq == 0 ? 1u : fq) << 8;
+		}
+		uint32_t redo = (1u << ng) - 1u;
+		for (;;) {
+			__syncthreads();
+			if (tid == 0) s_redo = 0;
+			if (wid == 0 && (int)lane < ng && ((redo >> lane) & 1u)) hp_build_tree(hheap[lane], hparent[lane], hlw[lane], alpha);
+			__syncthreads();
+			if ((int)wid < ng && ((redo >> wid) & 1u)) {
+				const uint16_t* parent = hparent[wid];
+				bool too_long = false;
+				for (int i = (int)lane + 1; i <= alpha; i += 32) {
+					int j = 0, k2 = i;
+					while (parent[k2] != HP_NOPARENT) { k2 = parent[k2]; j++; }
+					len[wid][i - 1] = (uint8_t)j;
+					if (j > 17) too_long = true;
+				}
+				if (__any_sync(0xffffffffu, too_long)) {
+					for (int i = (int)lane + 1; i <= alpha; i += 32) { uint32_t j = hlw[wid][i] >> 8; j = 1 + (j / 2); hlw[wid][i] = j << 8; }
+					if (lane == 0) atomicOr(&s_redo, 1u << wid);
+				}
+			}
+			__syncthreads();
+			redo = s_redo;
+			if (redo == 0) break;
+		}
 	}
 
 	// ---- canonical codes (huffman.c:152-166): code = first code of the length + rank among equal lengths
@@ -597,10 +646,50 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 		sym_bits_local += rfreq[t][v] * len[t][v];      // rfreq of the last pass == usage with the final selectors
 	}
 	uint32_t sym_bits; block_scan_add<HP_NT>(sym_bits_local, red, &sym_bits);
-	// selectors: move-to-front codes (compress.c:462-479), sequential but register-only
-	if (tid == 0) {
-		uint32_t pos = 0x543210u;
-		for (uint32_t i = 0; i < n_sel; i++) {
+	// selectors: move-to-front codes (compress.c:462-479).  The list after a chunk of selectors is
+	//   recency(chunk) ++ (list before \ recency(chunk)),   an associative operation on (<= 6 entry) recency lists:
+	// every thread reduces its chunk to a recency list (nibble-packed, most recent first), a CTA-wide scan composes
+	// them, and each thread replays its chunk from its now known start list.
+	{
+		const uint32_t per = (n_sel + HP_NT - 1) / HP_NT;
+		const uint32_t s0 = min(n_sel, tid * per), s1 = min(n_sel, s0 + per);
+		auto push_front = [](uint32_t& list, uint32_t& mask, uint32_t sv) {           // move sv to the front of a recency list
+			if ((mask >> sv) & 1u) {
+				uint32_t j = 0;
+				while (((list >> (4 * j)) & 15u) != sv) j++;
+				const uint32_t lowmask = (1u << (4 * j)) - 1u;
+				list = (list & ~((lowmask << 4) | 15u)) | ((list & lowmask) << 4) | sv;
+			} else { list = (list << 4) | sv; mask |= 1u << sv; }
+		};
+		auto then = [](uint32_t la, uint32_t ma, uint32_t lb, uint32_t mb, uint32_t& lo, uint32_t& mo) {   // a first, then b
+			uint32_t nb = (uint32_t)__popc(mb), l = lb;
+			const uint32_t na = (uint32_t)__popc(ma);
+			for (uint32_t j = 0; j < na; j++) {
+				const uint32_t vv = (la >> (4 * j)) & 15u;
+				if (!((mb >> vv) & 1u)) { l |= vv << (4 * nb); nb++; }
+			}
+			lo = l; mo = ma | mb;
+		};
+		uint32_t rl = 0, rm = 0;
+		for (uint32_t i = s0; i < s1; i++) push_front(rl, rm, selector[i]);
+		__syncthreads();                                                          // red[] is still being read by the scan above
+		// inclusive scan inside the warp, then across the 8 warps
+		uint32_t il = rl, im = rm;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t pl = __shfl_up_sync(0xffffffffu, il, o), pm = __shfl_up_sync(0xffffffffu, im, o);
+			if (lane >= (uint32_t)o) then(pl, pm, il, im, il, im);
+		}
+		if (lane == 31) { red[wid] = il; red[16 + wid] = im; }
+		__syncthreads();
+		uint32_t bl = 0, bm = 0;                                                  // everything before my warp
+		for (uint32_t ww = 0; ww < wid; ww++) then(bl, bm, red[ww], red[16 + ww], bl, bm);
+		uint32_t el = __shfl_up_sync(0xffffffffu, il, 1), em = __shfl_up_sync(0xffffffffu, im, 1);
+		if (lane == 0) { el = 0; em = 0; }
+		then(bl, bm, el, em, el, em);                                             // exclusive prefix of this thread
+		uint32_t pos, pm2;
+		then(0x543210u, 0x3fu, el, em, pos, pm2);                                 // start list: prefix recency ++ rest of 0..5
+		for (uint32_t i = s0; i < s1; i++) {
 			const uint32_t sv = selector[i];
 			uint32_t j = 0;
 			while (((pos >> (4 * j)) & 15u) != sv) j++;
@@ -608,6 +697,7 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 			pos = (pos & ~((lowmask << 4) | 15u)) | ((pos & lowmask) << 4) | sv;
 			selmtf[i] = (uint8_t)j;
 		}
+		__syncthreads();
 	}
 	// delta-coded lengths: bits per table
 	if ((int)wid < ng) {
@@ -762,7 +852,9 @@ void launch_mtf(const uint8_t* bwt, uint8_t* rank_scratch, uint32_t cap, EncJob*
 void launch_huff_pack(const uint16_t* mtfv, uint32_t mcap, EncJob* jobs, uint32_t njobs, uint8_t* sel, uint32_t selcap,
                       uint8_t* out, uint32_t ocap, int level, cudaStream_t st)
 {
-	k_huff_pack<<<njobs, HP_NT, 0, st>>>(mtfv, mcap, jobs, njobs, sel, selcap, out, ocap, level);
+	const size_t smem = sizeof(uint64_t) * kGroups * HP_HEAP;
+	cudaFuncSetAttribute(k_huff_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	k_huff_pack<<<njobs, HP_NT, smem, st>>>(mtfv, mcap, jobs, njobs, sel, selcap, out, ocap, level);
 }
 
 }  // namespace lfm

@@ -89,7 +89,17 @@ Engine::Engine(int device) : device_(device)
 	if (cudaGetDeviceProperties(&p, device_) == cudaSuccess) sm_count_ = p.multiProcessorCount;
 	cudaStream_t st; cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
 	stream_ = st;
+	for (int i = 0; i < 4; i++) { cudaEvent_t e; cudaEventCreate(&e); ev_[i] = e; }
 }
+
+static double elapsed_or_zero(void* a, void* b)
+{
+	float ms = 0.f;
+	if (cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess) { cudaGetLastError(); return 0.0; }
+	return ms;
+}
+double Engine::last_predict_ms() { return elapsed_or_zero(ev_[0], ev_[1]); }
+double Engine::last_unpredict_ms() { return elapsed_or_zero(ev_[2], ev_[3]); }
 
 int Engine::check(const char* what)
 {
@@ -202,7 +212,9 @@ int Engine::predict(const uint16_t* d_img, uint16_t* d_sym, const StackDesc& s, 
 	cudaSetDevice(device_);
 	if (predictor < 1 || predictor > 7 || s.way < 0 || s.way > 2) return LFM_ERR_UNSUPPORTED;
 	if (video && s.way != 0) return LFM_ERR_UNSUPPORTED;     // the reference's z!=0 angle/space kernels are not invertible
+	cudaEventRecord((cudaEvent_t)ev_[0], (cudaStream_t)stream_);
 	launch_predict_fwd(d_img, d_sym, (int)s.xyzct[0], (int)s.xyzct[1], s.Nnum, s.way, predictor, video, z0, nz, (cudaStream_t)stream_);
+	cudaEventRecord((cudaEvent_t)ev_[1], (cudaStream_t)stream_);
 	return check("predict");
 }
 
@@ -217,6 +229,7 @@ int Engine::unpredict(const uint16_t* d_sym, uint16_t* d_out, const StackDesc& s
 	static const bool poison = getenv("LFM_B200_DEBUG_POISON") != nullptr;
 	if (poison) cudaMemsetAsync(d_out + (size_t)z0 * W * H, 0xAB, (size_t)nz * W * H * 2, st);
 	int bad = 0;
+	cudaEventRecord((cudaEvent_t)ev_[2], st);
 	if (!video) bad |= launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 0, z0, 1, nz, sm_count_, st);
 	else {
 		// odd frames need the decoded even frame before them: evens first, then odds (z0 must be even)
@@ -226,6 +239,7 @@ int Engine::unpredict(const uint16_t* d_sym, uint16_t* d_out, const StackDesc& s
 		bad |= launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 1, first_even, 2, n_even, sm_count_, st);
 		bad |= launch_unpredict(d_sym, d_out, W, H, s.Nnum, s.way, predictor, 1, first_odd, 2, n_odd, sm_count_, st);
 	}
+	cudaEventRecord((cudaEvent_t)ev_[3], st);
 	if (bad) { cudaGetLastError(); err_ = "cluster launch of k_unpredict failed"; return LFM_ERR_CUDA; }
 	return check("unpredict");
 }

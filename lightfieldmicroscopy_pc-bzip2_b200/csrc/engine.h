@@ -66,6 +66,10 @@ public:
 	// Inverse predictor (unsymbolize fused) over frames [z0, z0+nz); in place is NOT allowed (d_sym != d_out).
 	int unpredict(const uint16_t* d_sym, uint16_t* d_out, const StackDesc& s, int predictor, int video, uint32_t z0, uint32_t nz);
 
+	// device time of the last predict() / unpredict() call (valid once the stream has been synchronised)
+	double last_predict_ms();
+	double last_unpredict_ms();
+
 	void* stream() const { return stream_; }
 	int   device() const { return device_; }
 	int   sm_count() const { return sm_count_; }

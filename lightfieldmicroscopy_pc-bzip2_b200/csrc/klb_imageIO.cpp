@@ -189,6 +189,7 @@ int compress_core(const FrameSource& src, klb_image_header& h, std::vector<Shard
 		shardFirstBlock[d] = first;
 		out.sizes.resize(count);
 		out.rc = e.compress_blocks(sym_base, desc, first, count, out.sizes.data(), &out.d_payload, &out.payload_bytes, &out.st);
+		if (k != 0 && out.rc == 0) out.st.ms_predict = e.last_predict_ms();
 		out.ms_h2d = now_ms() - t0;                         // H2D + kernels (the copy is asynchronous and overlaps nothing yet)
 		if (out.rc) { g_err = e.last_error(); return; }
 	};
@@ -346,6 +347,7 @@ int decompress_core(const klb_image_header& h, const uint8_t* payload, uint64_t 
 		}
 		cudaStreamSynchronize(st);
 		d2h[d] = now_ms() - t0;
+		if (k != 0) sts[d].ms_unpredict = e.last_unpredict_ms();
 		if (cudaGetLastError() != cudaSuccess) rcs[d] = LFM_ERR_CUDA;
 	};
 	if (D == 1) work(0);
@@ -530,6 +532,26 @@ int lfmCompressToMemory(const void* im, const uint32_t xyzct[5], const uint32_t 
 	return 0;
 }
 
+int lfmCompressToBuffer(const void* im, const uint32_t xyzct[5], const uint32_t blockSize[5], uint8_t headerVersion, uint8_t Nnum,
+                        void* file_bytes, uint64_t capacity, uint64_t* file_size)
+{
+	klb_imageIO io;
+	io.header.setHeader(xyzct, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize, KLB_COMPRESSION_TYPE::BZIP2, NULL, headerVersion, Nnum);
+	FrameSource src; src.base = (const uint16_t*)im;
+	std::vector<ShardOut> shards; std::vector<uint64_t> first;
+	int rc = compress_core(src, io.header, shards, first);
+	if (rc) return rc;
+	uint64_t total = 0;
+	for (const auto& s : shards) total += s.payload_bytes;
+	const size_t hdr = 320 + io.header.Nb * 8;
+	if (file_size) *file_size = hdr + total;
+	if (!file_bytes || capacity < hdr + total) return LFM_ERR_CREATE;
+	uint8_t* p = (uint8_t*)file_bytes;
+	io.header.packFixed(p);
+	memcpy(p + 320, io.header.blockOffset, io.header.Nb * 8);
+	return fetch_payload(shards, p + hdr);
+}
+
 int lfmDecompressFromMemory(const void* file_bytes, uint64_t file_size, void* im)
 {
 	klb_imageIO io;
@@ -563,8 +585,10 @@ int lfmCompressDevice(const void* d_im, const uint32_t xyzct[5], const uint32_t 
 	const int video = (headerVersion & 0x80) ? 1 : 0;
 	int k;
 	if ((headerVersion & 0x7F) < NUM_PREDICTORS) {
+		const double t0 = now_ms();
 		rc = e.select_mode((const uint16_t*)d_im, desc, g_stats.entropy, &k);
 		if (rc) return rc;
+		g_stats.ms_select = now_ms() - t0;
 		g_stats.selected = 1; g_stats.gpu_launches += 10;
 	} else { k = headerVersion & 0x77 & 0x7F; if (k > 7) return LFM_ERR_UNSUPPORTED; }
 	if (k != 0 && video && way != 0) return LFM_ERR_UNSUPPORTED;
@@ -589,6 +613,7 @@ int lfmCompressDevice(const void* d_im, const uint32_t xyzct[5], const uint32_t 
 	for (uint64_t i = 0; i < L.Nb; i++) { acc += sizes[i]; blockOffset[i] = acc; }
 	*d_payload = dpay; *payload_bytes = pb;
 	g_stats.ms_rle = st.ms_rle; g_stats.ms_bwt = st.ms_bwt; g_stats.ms_mtf = st.ms_mtf; g_stats.ms_huff = st.ms_huff;
+	if (k != 0) g_stats.ms_predict = e.last_predict_ms();
 	g_stats.gpu_launches += st.launches; g_stats.periodic_blocks = st.periodic_blocks; g_stats.payload_bytes = pb;
 	return 0;
 }
@@ -629,6 +654,7 @@ int lfmDecompressDevice(const void* d_payload, const uint64_t* blockOffset, uint
 		st.launches += video ? 2 : 1;
 		cudaStreamSynchronize((cudaStream_t)e.stream());
 		if (cudaGetLastError() != cudaSuccess) return LFM_ERR_CUDA;
+		g_stats.ms_unpredict = e.last_unpredict_ms();
 	}
 	g_stats.predictor = k;
 	g_stats.ms_decode = st.ms_decode; g_stats.ms_ibwt = st.ms_ibwt; g_stats.ms_unrle = st.ms_unrle;

@@ -20,26 +20,69 @@ namespace lfm {
 
 constexpr int PF_NT = 256;
 
+// Forward predictor, row-marching form.  A CTA owns 256 image columns and walks down a band of rows:
+//   * everything that depends on the column (tile index tx, in-tile u, first-tile-column tests) is a per-thread
+//     constant, everything that depends on the row (ty, v) is uniform over the CTA -> the rule function's border
+//     tests are either hoisted or warp-uniform branches;
+//   * the row above is carried in registers (up = previous cur, upleft = previous left), the far neighbours
+//     (distance T) are plain coalesced 2-byte loads that hit L1/L2: DRAM sees 2 B/px in and 2 B/px out;
+//   * WAY and K are template parameters: the rule function collapses to the few adds of the selected predictor.
+template <int WAY, int K>
 __global__ void __launch_bounds__(PF_NT)
-k_predict_fwd(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int W, int H, int T, int way, int k,
-              int video, uint32_t z0, uint32_t nz)
+k_predict_fwd(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int W, int H, int T, int video,
+              uint32_t z0, int band)
 {
+	const int x = blockIdx.x * PF_NT + threadIdx.x;
+	if (x >= W) return;
+	const int y0 = blockIdx.y * band, y1 = min(H, y0 + band);
+	const uint32_t z = z0 + blockIdx.z;
 	const uint64_t fpx = (uint64_t)W * H;
-	const uint64_t idx = (uint64_t)blockIdx.x * PF_NT + threadIdx.x;
-	if (idx >= fpx * nz) return;
-	const uint32_t zi = (uint32_t)(idx / fpx);
-	const uint32_t rem = (uint32_t)(idx - (uint64_t)zi * fpx);
-	const int y = (int)(rem / (uint32_t)W), x = (int)(rem - (uint32_t)y * (uint32_t)W);
-	const uint32_t z = z0 + zi;
 	const uint16_t* cur = img + (uint64_t)z * fpx;
-	const int tx = x / T, ty = y / T, u = x - tx * T, v = y - ty * T;
-	auto px = [&](int dx, int dy) { return (int)__ldg(cur + (size_t)(y + dy) * W + (x + dx)); };
-	int p = predict0(px, T, way, k, tx, ty, u, v);
-	if (video & (int)z & 1) {                       // `i_or_v & z`: only odd frames look back (klb_imageIO.cpp:1243)
-		int P = (int)__ldg(cur - fpx + (size_t)y * W + x);
-		p = (x == 0 && y == 0) ? P : ((p + P) >> 1);
+	uint16_t* out = sym + (uint64_t)z * fpx;
+	const int tx = x / T, u = x - tx * T;
+	int ty = y0 / T, v = y0 - ty * T;
+	const bool zf = (video & (int)z & 1) != 0;                  // `i_or_v & z`: only odd frames look back (klb_imageIO.cpp:1243)
+	int up = 0, upleft = 0;
+	if (y0 > 0) {
+		up = (int)__ldg(cur + (size_t)(y0 - 1) * W + x);
+		if (x > 0) upleft = (int)__ldg(cur + (size_t)(y0 - 1) * W + x - 1);
 	}
-	sym[(uint64_t)z * fpx + rem] = symbolize16(px(0, 0) - p);
+	const uint16_t* rp = cur + (size_t)y0 * W + x;
+	uint16_t* op = out + (size_t)y0 * W + x;
+	constexpr int RB = 8;                                        // rows whose DRAM loads are in flight together
+	for (int yb = y0; yb < y1; yb += RB) {
+		int cc[RB], ll[RB];
+		#pragma unroll
+		for (int r = 0; r < RB; r++) {
+			cc[r] = 0; ll[r] = 0;
+			if (yb + r < y1) {
+				cc[r] = (int)__ldg(rp + (size_t)r * W);
+				if (x > 0) ll[r] = (int)__ldg(rp + (size_t)r * W - 1);
+			}
+		}
+		#pragma unroll
+		for (int r = 0; r < RB; r++) {
+			if (yb + r < y1) {
+				const int y = yb + r, c = cc[r], left = ll[r];
+				const uint16_t* rq = rp + (size_t)r * W;
+				auto px = [&](int dx, int dy) -> int {
+					if (dy == 0 && dx == -1) return left;
+					if (dy == -1 && dx == 0) return up;
+					if (dy == -1 && dx == -1) return upleft;
+					return (int)__ldg(rq + (ptrdiff_t)dy * W + dx);
+				};
+				int p = predict0(px, T, WAY, K, tx, ty, u, v);
+				if (WAY == 0 && zf) {
+					const int P = (int)__ldg(rq - fpx);
+					p = (x == 0 && y == 0) ? P : ((p + P) >> 1);
+				}
+				op[(size_t)r * W] = symbolize16(c - p);
+				up = c; upleft = left;
+				if (++v == T) { v = 0; ty++; }
+			}
+		}
+		rp += (size_t)RB * W; op += (size_t)RB * W;
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -225,12 +268,185 @@ k_unpredict_angle(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H,
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory inverse for the two ways whose dependency graph factorises.
+//
+// k_unpredict_grid: a 2-D recurrence over the TILE grid -- out(tx,ty) = res + f(out(tx-1,ty), out(tx,ty-1), out(tx-1,ty-1)).
+//   way "space": one CTA per (frame, u, v): the sub-aperture image (pixel (u,v) of every microlens);
+//   way "angle": one CTA per frame, (u,v) = (0,0): the grid of tile DC pixels.
+//   The residuals of the sub-image are gathered into shared memory first (all loads in flight together), then
+//   thread tx walks down column tx of the grid along the anti-diagonal wavefront d = tx + ty: `up` is the thread's own
+//   previous output, `upleft` the value it read from its left neighbour one step earlier, `left` comes through a
+//   double-buffered shared line -- one CTA barrier per wavefront step, no global-memory round trip on the chain.
+// k_unpredict_tiles_angle: way "angle", predictor != 2: with the DCs in place every tile is an independent DPCM.
+//   A CTA stages one tile row (T image rows x 128 tiles) in shared memory with coalesced loads, ONE THREAD decodes ONE
+//   tile in place (raster order; its left / up / up-left neighbours are shared-memory reads of its own earlier
+//   writes -- no synchronisation at all), then the strip is written back coalesced.
+constexpr int UG_MAX_SMEM = 200 * 1024;
+
+__global__ void __launch_bounds__(1024)
+k_unpredict_grid(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T, int way, int k,
+                 uint32_t z_start, uint32_t z_step, uint32_t uv_per_frame)
+{
+	extern __shared__ __align__(16) uint8_t ug_smem[];
+	const uint32_t tid = threadIdx.x;
+	const uint32_t f = blockIdx.x / uv_per_frame, uv = blockIdx.x - f * uv_per_frame;
+	const int v = (int)(uv / (uint32_t)T), u = (int)(uv - (uint32_t)v * (uint32_t)T);      // (0,0) for the DC grid
+	const int nx = (W - u + T - 1) / T, ny = (H - v + T - 1) / T;                         // grid points of this sub-image
+	if (nx <= 0 || ny <= 0) return;
+	const uint64_t fpx = (uint64_t)W * H;
+	const uint32_t z = z_start + f * z_step;
+	const uint16_t* s = sym + (uint64_t)z * fpx + (size_t)v * W + u;
+	uint16_t* o = out + (uint64_t)z * fpx + (size_t)v * W + u;
+	int16_t* res = reinterpret_cast<int16_t*>(ug_smem);                                    // [ny][nx] residuals
+	uint16_t* line = reinterpret_cast<uint16_t*>(ug_smem) + (((size_t)nx * ny + 7) & ~(size_t)7);   // [2][nx + 1]
+	const size_t rowstep = (size_t)T * W;
+
+	// ---- gather (unsymbolize on the way in)
+	const uint32_t total = (uint32_t)nx * (uint32_t)ny;
+	for (uint32_t i0 = tid; i0 < total; i0 += blockDim.x * 8) {
+		uint16_t q[8];
+		#pragma unroll
+		for (int r = 0; r < 8; r++) {
+			const uint32_t i = i0 + r * blockDim.x;
+			if (i < total) { const uint32_t gy = i / (uint32_t)nx, gx = i - gy * (uint32_t)nx; q[r] = __ldg(s + gy * rowstep + (size_t)gx * T); }
+		}
+		#pragma unroll
+		for (int r = 0; r < 8; r++) { const uint32_t i = i0 + r * blockDim.x; if (i < total) res[i] = (int16_t)unsymbolize16(q[r]); }
+	}
+	// way space: tile (0,0) is an ordinary intra-tile DPCM decoded beforehand (k_unpredict_seed); DC grid: predictor 0
+	int first = 0;
+	if (tid == 0 && way == 2) first = (int)__ldcg(o);
+	__syncthreads();
+
+	// ---- wavefront
+	const int tx = (int)tid;
+	int up = 0, upleft = 0;
+	const int nsteps = nx + ny - 1;
+	for (int d = 0; d < nsteps; d++) {
+		const int ty = d - tx;
+		const uint16_t* rd = line + ((d + 1) & 1) * (nx + 1);           // written at step d-1
+		uint16_t* wr = line + (d & 1) * (nx + 1);
+		if (tx < nx && ty >= 0 && ty < ny) {
+			const int left = tx > 0 ? (int)rd[tx - 1] : 0;
+			int val;
+			if (d == 0) val = (way == 2) ? first : (int)(uint16_t)res[0];
+			else {
+				auto px = [&](int dx, int dy) -> int { return dx == 0 ? up : (dy == 0 ? left : upleft); };
+				const int p = predict0(px, T, way, k, tx, ty, u, v);
+				val = (int)(uint16_t)((int)res[(size_t)ty * nx + tx] + p);
+			}
+			wr[tx] = (uint16_t)val;
+			o[(size_t)ty * rowstep + (size_t)tx * T] = (uint16_t)val;
+			upleft = left; up = val;
+		}
+		__syncthreads();
+	}
+}
+
+constexpr int UT_NT = 128;       // tiles (= threads) per CTA
+
+template <int K>
+__global__ void __launch_bounds__(UT_NT)
+k_unpredict_tiles_angle(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T,
+                        uint32_t z_start, uint32_t z_step, int tilesX, int tilesY, int chunks)
+{
+	extern __shared__ __align__(16) uint8_t ut_smem[];
+	uint16_t* sm = reinterpret_cast<uint16_t*>(ut_smem);
+	const uint32_t tid = threadIdx.x;
+	uint32_t b = blockIdx.x;
+	const int chunk = (int)(b % (uint32_t)chunks); b /= (uint32_t)chunks;
+	const int ty = (int)(b % (uint32_t)tilesY);
+	const uint32_t f = b / (uint32_t)tilesY;
+	const uint64_t fpx = (uint64_t)W * H;
+	const uint32_t z = z_start + f * z_step;
+	const int x0 = chunk * UT_NT * T, y0 = ty * T;
+	const int sw = min(W - x0, UT_NT * T), th = min(T, H - y0);           // strip width / height in pixels
+	const uint16_t* s = sym + (uint64_t)z * fpx + (size_t)y0 * W + x0;
+	uint16_t* o = out + (uint64_t)z * fpx + (size_t)y0 * W + x0;
+	const bool vec = ((W & 7) == 0) && ((sw & 7) == 0) && ((((uintptr_t)sym | (uintptr_t)out) & 15) == 0);   // x0 is a multiple of 128
+	const int pitch = sw;
+
+	// ---- stage the strip (residual symbols)
+	if (vec) {
+		const int wv = sw >> 3;
+		for (int i = (int)tid; i < wv * th; i += UT_NT) {
+			const int r = i / wv, cx = i - r * wv;
+			reinterpret_cast<uint4*>(sm + (size_t)r * pitch)[cx] = __ldg(reinterpret_cast<const uint4*>(s + (size_t)r * W) + cx);
+		}
+	} else {
+		for (int i = (int)tid; i < sw * th; i += UT_NT) { const int r = i / sw, cx = i - r * sw; sm[(size_t)r * pitch + cx] = __ldg(s + (size_t)r * W + cx); }
+	}
+	__syncthreads();
+
+	// ---- one thread, one tile
+	const int tx = chunk * UT_NT + (int)tid;
+	if (tx < tilesX) {
+		const int tw = min(T, W - tx * T);
+		uint16_t* t0 = sm + (size_t)tid * T;
+		t0[0] = __ldcg(o + (size_t)tid * T);                              // the DC, decoded by k_unpredict_grid
+		for (int v = 0; v < th; v++) {
+			uint16_t* row = t0 + (size_t)v * pitch;
+			for (int u = (v == 0) ? 1 : 0; u < tw; u++) {
+				auto px = [&](int dx, int dy) -> int { return (int)row[u + dx + dy * pitch]; };
+				const int p = predict0(px, T, 1, K, tx, ty, u, v);
+				row[u] = (uint16_t)(unsymbolize16(row[u]) + p);
+			}
+		}
+	}
+	__syncthreads();
+
+	// ---- write the decoded strip back
+	if (vec) {
+		const int wv = sw >> 3;
+		for (int i = (int)tid; i < wv * th; i += UT_NT) {
+			const int r = i / wv, cx = i - r * wv;
+			reinterpret_cast<uint4*>(o + (size_t)r * W)[cx] = reinterpret_cast<const uint4*>(sm + (size_t)r * pitch)[cx];
+		}
+	} else {
+		for (int i = (int)tid; i < sw * th; i += UT_NT) { const int r = i / sw, cx = i - r * sw; o[(size_t)r * W + cx] = sm[(size_t)r * pitch + cx]; }
+	}
+}
+
+template <int K>
+static void launch_tiles_angle(const uint16_t* sym, uint16_t* out, int W, int H, int T, uint32_t z_start, uint32_t z_step,
+                               uint32_t count, int tilesX, int tilesY, int chunks, size_t smem, cudaStream_t st)
+{
+	cudaFuncSetAttribute(k_unpredict_tiles_angle<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	k_unpredict_tiles_angle<K><<<(unsigned)((uint64_t)count * tilesY * chunks), UT_NT, smem, st>>>(sym, out, W, H, T, z_start, z_step, tilesX, tilesY, chunks);
+}
+
+template <int WAY>
+static void launch_predict_fwd_way(const uint16_t* img, uint16_t* sym, int W, int H, int T, int k, int video,
+                                   uint32_t z0, uint32_t nz, int band, dim3 grid, cudaStream_t st)
+{
+	switch (k) {
+	case 1: k_predict_fwd<WAY, 1><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
+	case 2: k_predict_fwd<WAY, 2><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
+	case 3: k_predict_fwd<WAY, 3><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
+	case 4: k_predict_fwd<WAY, 4><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
+	case 5: k_predict_fwd<WAY, 5><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
+	case 6: k_predict_fwd<WAY, 6><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
+	default: k_predict_fwd<WAY, 7><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
+	}
+	(void)nz;
+}
+
 void launch_predict_fwd(const uint16_t* img, uint16_t* sym, int W, int H, int T, int way, int k, int video,
                         uint32_t z0, uint32_t nz, cudaStream_t st)
 {
-	uint64_t total = (uint64_t)W * H * nz;
-	uint64_t blocks = (total + PF_NT - 1) / PF_NT;
-	k_predict_fwd<<<(unsigned)blocks, PF_NT, 0, st>>>(img, sym, W, H, T, way, k, video, z0, nz);
+	if (nz == 0) return;
+	// band height: enough CTAs to fill the GPU for a single frame, long bands (less halo re-reading) for stacks
+	const int colchunks = (W + PF_NT - 1) / PF_NT;
+	int band = 64;
+	while (band > 16 && (uint64_t)colchunks * ((H + band - 1) / band) * nz < 1184) band >>= 1;
+	for (uint32_t zb = 0; zb < nz; zb += 65535) {            // gridDim.z limit
+		const uint32_t cz = std::min<uint32_t>(65535, nz - zb);
+		dim3 grid((unsigned)colchunks, (unsigned)((H + band - 1) / band), cz);
+		if (way == 0) launch_predict_fwd_way<0>(img, sym, W, H, T, k, video, z0 + zb, cz, band, grid, st);
+		else if (way == 1) launch_predict_fwd_way<1>(img, sym, W, H, T, k, video, z0 + zb, cz, band, grid, st);
+		else launch_predict_fwd_way<2>(img, sym, W, H, T, k, video, z0 + zb, cz, band, grid, st);
+	}
 }
 
 // frames z_start, z_start+z_step, ... (count of them); video stacks: even frames first, then odd frames.
@@ -242,13 +458,37 @@ int launch_unpredict(const uint16_t* sym, uint16_t* out, int W, int H, int T, in
 	if (count == 0) return 0;
 	const int tilesX = (W + T - 1) / T, tilesY = (H + T - 1) / T;
 	const unsigned wpb = UF_NT / 32;
-	if (!video && way == 2) {                               // barrier-free: first tile, then T*T recurrences per frame
+	const size_t grid_smem = ((((size_t)tilesX * tilesY + 7) & ~(size_t)7) + 2 * ((size_t)tilesX + 1)) * 2 + 16;
+	const bool grid_ok = tilesX <= 1024 && grid_smem <= (size_t)UG_MAX_SMEM;
+	const unsigned grid_nt = (unsigned)std::max(32, (tilesX + 31) & ~31);
+	if (!video && way == 2 && grid_ok) {                    // tile (0,0), then T*T sub-aperture recurrences per frame
+		k_unpredict_seed<<<(count + wpb - 1) / wpb, UF_NT, 0, st>>>(sym, out, W, H, T, way, k, z_start, z_step, count, 0);
+		cudaFuncSetAttribute(k_unpredict_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_smem);
+		k_unpredict_grid<<<(unsigned)((uint64_t)count * T * T), grid_nt, grid_smem, st>>>(sym, out, W, H, T, 2, k, z_start, z_step, (uint32_t)(T * T));
+		return cudaGetLastError() == cudaSuccess ? 0 : 1;
+	}
+	const size_t strip_smem = (size_t)T * T * UT_NT * 2 + 16;
+	if (!video && way == 1 && k != 2 && grid_ok && strip_smem <= (size_t)UG_MAX_SMEM) {   // DC grid, then every tile on its own
+		cudaFuncSetAttribute(k_unpredict_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_smem);
+		k_unpredict_grid<<<count, grid_nt, grid_smem, st>>>(sym, out, W, H, T, 1, k, z_start, z_step, 1u);
+		const int chunks = (tilesX + UT_NT - 1) / UT_NT;
+		switch (k) {
+		case 1: launch_tiles_angle<1>(sym, out, W, H, T, z_start, z_step, count, tilesX, tilesY, chunks, strip_smem, st); break;
+		case 3: launch_tiles_angle<3>(sym, out, W, H, T, z_start, z_step, count, tilesX, tilesY, chunks, strip_smem, st); break;
+		case 4: launch_tiles_angle<4>(sym, out, W, H, T, z_start, z_step, count, tilesX, tilesY, chunks, strip_smem, st); break;
+		case 5: launch_tiles_angle<5>(sym, out, W, H, T, z_start, z_step, count, tilesX, tilesY, chunks, strip_smem, st); break;
+		case 6: launch_tiles_angle<6>(sym, out, W, H, T, z_start, z_step, count, tilesX, tilesY, chunks, strip_smem, st); break;
+		default: launch_tiles_angle<7>(sym, out, W, H, T, z_start, z_step, count, tilesX, tilesY, chunks, strip_smem, st); break;
+		}
+		return cudaGetLastError() == cudaSuccess ? 0 : 1;
+	}
+	if (!video && way == 2) {                               // (fallback for tile grids that do not fit shared memory)
 		k_unpredict_seed<<<(count + wpb - 1) / wpb, UF_NT, 0, st>>>(sym, out, W, H, T, way, k, z_start, z_step, count, 0);
 		const uint64_t warps = (uint64_t)count * T * T;
 		k_unpredict_space<<<(unsigned)((warps + wpb - 1) / wpb), UF_NT, 0, st>>>(sym, out, W, H, T, k, z_start, z_step, count);
 		return cudaGetLastError() == cudaSuccess ? 0 : 1;
 	}
-	if (!video && way == 1 && k != 2) {                     // barrier-free: DC grid, then every tile on its own
+	if (!video && way == 1 && k != 2) {
 		k_unpredict_seed<<<(count + wpb - 1) / wpb, UF_NT, 0, st>>>(sym, out, W, H, T, way, k, z_start, z_step, count, 1);
 		const uint64_t warps = (uint64_t)count * tilesX * tilesY;
 		k_unpredict_angle<<<(unsigned)((warps + wpb - 1) / wpb), UF_NT, 0, st>>>(sym, out, W, H, T, k, z_start, z_step, count);

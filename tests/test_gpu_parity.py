@@ -176,6 +176,12 @@ def test_memory_and_device_entry_points(L):
     a = lf_synth((3, 200, 210), 15, seed=6)
     blob = L.compress_to_bytes(a, header_version=0, nnum=15, way=2)
     assert np.array_equal(L.decompress_from_bytes(blob, a.shape, way=2), a)
+    buf = np.empty(len(blob) + 10, np.uint8); back = np.empty_like(a)
+    assert L.compress_into(a, buf, header_version=0, nnum=15, way=2) == len(blob) and bytes(buf[:len(blob)]) == blob
+    assert np.array_equal(L.decompress_into(buf, len(blob), back, way=2), a)
+    with pytest.raises(L.LfmError) as ei:
+        L.compress_into(a, buf[:100], header_version=0, nnum=15, way=2)
+    assert ei.value.code == 5
     t = torch.from_numpy(a.astype(np.int16)).cuda()
     xyzct = L._u32x5(210, 200, 3, 1, 1)
     nb = L.lib.lfmNumBlocks(xyzct, None)
