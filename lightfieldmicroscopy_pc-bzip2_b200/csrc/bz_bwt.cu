@@ -54,6 +54,11 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 		}
 		__syncthreads();
 		digit_starts(n, base, wcnt, red, [&](uint32_t e) { return (uint32_t)text[e]; });
+		if (tid < 256) {                                  // inUse map = byte values that occur (bzlib.c:226, :243-258)
+			const uint32_t c = (tid == 255 ? n : base[tid + 1]) - base[tid];
+			const uint32_t bal = __ballot_sync(0xffffffffu, c != 0);
+			if ((tid & 31) == 0) jobs[job].in_use[tid >> 5] = bal;
+		}
 
 		// ---- phase 1: 8 LSD passes over the 8-byte prefix (byte 7 first)
 		uint32_t* src = nullptr; uint32_t* dst = scr + (size_t)S_SA0 * cap;

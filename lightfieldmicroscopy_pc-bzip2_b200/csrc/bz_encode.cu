@@ -63,12 +63,10 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 	__shared__ uint32_t crc_tab[256];
 	__shared__ uint32_t red[64];
 	__shared__ uint32_t s_a[RLE_NT], s_b[RLE_NT];
-	__shared__ uint32_t s_inuse[8];
 	const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
 	const uint32_t job = blockIdx.x;
 	if (job >= njobs) return;
 	crc_tab[tid] = crc_table_entry(tid);
-	if (tid < 8) s_inuse[tid] = 0;
 
 	uint32_t c0[5], ext[5];
 	block_box(g, first_block + job, c0, ext);
@@ -130,11 +128,6 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 	uint32_t crc = 0;
 	{
 		uint32_t o = incs - outc, i = e0, rs = open_start;
-		uint32_t iu[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-		auto mark = [&](uint32_t v) {
-			#pragma unroll
-			for (int k = 0; k < 8; k++) if ((v >> 5) == (uint32_t)k) iu[k] |= 1u << (v & 31);
-		};
 		while (i < e1) {
 			if (i == 0 || b[i] != b[i - 1]) rs = i;
 			const uint32_t ch = b[i];
@@ -142,20 +135,17 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 			while (e < e1 && b[e] == b[e - 1]) e++;
 			const uint32_t run_end = (e < e1) ? e : next_head;       // where the whole run stops
 			const uint32_t run_len = run_end - rs;
-			mark(ch);
 			uint32_t p = i;
 			while (p < e) {
 				const uint32_t r = p - rs, q = r % 255u;
 				if (q < 4) {
 					out[o++] = (uint8_t)ch;
-					if (q == 3) { uint32_t reclen = min(255u, run_len - (r - 3)); out[o++] = (uint8_t)(reclen - 4); mark(reclen - 4); }
+					if (q == 3) { uint32_t reclen = min(255u, run_len - (r - 3)); out[o++] = (uint8_t)(reclen - 4); }
 					p++;
 				} else p += 255u - q;                                   // the rest of this 255-record emits nothing
 			}
 			i = e;
 		}
-		#pragma unroll
-		for (int k = 0; k < 8; k++) if (iu[k]) atomicOr(&s_inuse[k], iu[k]);
 		// ---- D. chunk CRC (the first non-empty chunk carries the 0xFFFFFFFF start value)
 		if (e1 > e0) {
 			crc = (e0 == 0) ? 0xFFFFFFFFu : 0u;
@@ -182,9 +172,10 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 	if (tid == 0) {
 		EncJob& J = jobs[job];
 		J.raw_bytes = gcount; J.n = n; J.crc = ~s_a[0]; J.status = 0; J.periodic = 0; J.orig_ptr = 0;
-		uint32_t niu = 0;
-		for (int k = 0; k < 8; k++) { J.in_use[k] = s_inuse[k]; niu += __popc(s_inuse[k]); }
-		J.n_in_use = niu;
+		// the inUse map (bzlib.c:226, :243-258) is exactly "byte values with a non-zero count in the block": k_bwt derives
+		// it from the byte histogram it needs anyway
+		for (int k = 0; k < 8; k++) J.in_use[k] = 0;
+		J.n_in_use = 0;
 	}
 }
 
@@ -243,17 +234,25 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 	}
 	__syncthreads();
 	const uint32_t EOB = n_in_use + 1;
-	const uint32_t CH = (n + MTF_NT - 1) / MTF_NT;
+	const uint32_t CH = ((n + MTF_NT - 1) / MTF_NT + 3) & ~3u;      // whole words: chunks are read and written 4 bytes at a time
 	const uint32_t c0 = min(n, tid * CH), c1 = min(n, c0 + CH);
+	const uint32_t* bwt32 = reinterpret_cast<const uint32_t*>(bwt);    // slots are 16-byte aligned and padded past n
+	uint32_t* rk32 = reinterpret_cast<uint32_t*>(rk);
 
 	// ---- 1. recency list of the chunk
 	#pragma unroll
 	for (int k = 0; k < 8; k++) seen[k * MTF_NT + tid] = 0;
 	uint32_t my_cnt = 0;
-	for (uint32_t i = c1; i > c0; i--) {
-		uint32_t c = seqmap[bwt[i - 1]];
-		uint32_t wv = seen[(c >> 5) * MTF_NT + tid], bit = 1u << (c & 31);
-		if (!(wv & bit)) { seen[(c >> 5) * MTF_NT + tid] = wv | bit; rl[my_cnt * MTF_RLS + tid] = (uint8_t)c; my_cnt++; }
+	for (uint32_t i4 = (c0 < c1) ? ((c1 + 3) & ~3u) : c0; i4 > c0; i4 -= 4) {   // a non-empty chunk starts on a multiple of 4
+		const uint32_t word = bwt32[(i4 - 4) >> 2];
+		#pragma unroll
+		for (int k = 3; k >= 0; k--) {
+			if (i4 - 4 + k < c1) {
+				const uint32_t c = seqmap[(word >> (8 * k)) & 255u];
+				const uint32_t wv = seen[(c >> 5) * MTF_NT + tid], bit = 1u << (c & 31);
+				if (!(wv & bit)) { seen[(c >> 5) * MTF_NT + tid] = wv | bit; rl[my_cnt * MTF_RLS + tid] = (uint8_t)c; my_cnt++; }
+			}
+		}
 	}
 	cnt[tid] = my_cnt;
 	__syncthreads();
@@ -286,59 +285,89 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 	{
 		uint32_t* my = st + tid;                               // word w of my list: my[w * STS]
 		uint32_t front = my[0] & 255u;
-		for (uint32_t i = c0; i < c1; i++) {
-			const uint32_t c = seqmap[bwt[i]];
-			uint32_t r = 0;
-			if (c != front) {
-				const uint32_t pat = c * 0x01010101u;
-				uint32_t carry = c;
-				for (uint32_t w = 0; ; w++) {
-					const uint32_t word = my[w * MTF_STS];
-					const uint32_t m = __vcmpeq4(word, pat);
-					if (m) {
-						const uint32_t j = (uint32_t)(__ffs(m) - 1) >> 3;                  // byte holding c
-						const uint32_t low = j ? (word & (0xFFFFFFFFu >> (32 - 8 * j))) : 0u;   // bytes below it
-						const uint32_t keep = (j == 3) ? 0u : (word & (0xFFFFFFFFu << (8 * (j + 1))));
-						my[w * MTF_STS] = keep | (low << 8) | carry;
-						r = 4 * w + j;
-						break;
+		for (uint32_t i4 = c0; i4 < c1; i4 += 4) {
+			const uint32_t inw = bwt32[i4 >> 2];
+			uint32_t outw = 0;
+			#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				if (i4 + k < c1) {
+					const uint32_t c = seqmap[(inw >> (8 * k)) & 255u];
+					uint32_t r = 0;
+					if (c != front) {
+						const uint32_t pat = c * 0x01010101u;
+						uint32_t carry = c;
+						for (uint32_t w = 0; ; w++) {
+							const uint32_t word = my[w * MTF_STS];
+							const uint32_t x = word ^ pat;
+							const uint32_t m = (x - 0x01010101u) & ~x & 0x80808080u;               // 0x80 in (at least) the lowest byte equal to c
+							if (m) {
+								const uint32_t j = (uint32_t)(__ffs(m) - 1) >> 3;                  // lowest matching byte: borrows only spoil higher ones
+								const uint32_t low = j ? (word & (0xFFFFFFFFu >> (32 - 8 * j))) : 0u;   // bytes below it
+								const uint32_t keep = (j == 3) ? 0u : (word & (0xFFFFFFFFu << (8 * (j + 1))));
+								my[w * MTF_STS] = keep | (low << 8) | carry;
+								r = 4 * w + j;
+								break;
+							}
+							my[w * MTF_STS] = (word << 8) | carry;
+							carry = word >> 24;
+						}
+						front = c;
 					}
-					my[w * MTF_STS] = (word << 8) | carry;
-					carry = word >> 24;
+					outw |= r << (8 * k);
 				}
-				front = c;
 			}
-			rk[i] = (uint8_t)r;
+			rk32[i4 >> 2] = outw;
 		}
 	}
 	#undef ST_BYTE
 	// ---- 4. zero-run coding. A run is emitted by the chunk in which it ends.
+	__syncthreads();
 	uint32_t lead = 0, trail = 0;                            // leading / trailing zero ranks of my chunk
 	{
-		uint32_t i = c0;
-		while (i < c1 && rk[i] == 0) { lead++; i++; }
-		if (lead < c1 - c0) { uint32_t j = c1; while (j > c0 && rk[j - 1] == 0) { trail++; j--; } }
-	}
-	cnt[tid] = (lead == c1 - c0) ? 0xFFFFFFFFu : trail;     // all zero: passes the incoming run on
-	__syncthreads();
-	if (tid == 0) {
-		uint32_t z = 0;
-		for (uint32_t t = 0; t < MTF_NT; t++) {
-			zin[t] = z;
-			uint32_t a0 = min(n, t * CH), a1 = min(n, a0 + CH);
-			if (cnt[t] == 0xFFFFFFFFu) z += a1 - a0; else z = cnt[t];
+		bool open = true;
+		for (uint32_t i4 = c0; i4 < c1; i4 += 4) {
+			const uint32_t w = rk32[i4 >> 2];
+			#pragma unroll
+			for (int k = 0; k < 4; k++) if (i4 + k < c1) {
+				const bool z0 = ((w >> (8 * k)) & 255u) == 0;
+				if (open) { if (z0) lead++; else open = false; }
+				trail = z0 ? trail + 1 : 0;
+			}
 		}
-		red[40] = z;                                        // run still pending at the end of the block
 	}
-	__syncthreads();
-	const uint32_t zpend_end = red[40];
+	// run carried INTO each chunk: scan of (all zero?, value) with  a . b = b.allzero ? (a.allzero, a.v + b.v) : (false, b.v)
+	uint32_t zin_mine, zpend_end;
+	{
+		const bool my_az = (lead == c1 - c0);
+		uint32_t az = my_az ? 1u : 0u, vv = my_az ? (c1 - c0) : trail;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t paz = __shfl_up_sync(0xffffffffu, az, o), pv = __shfl_up_sync(0xffffffffu, vv, o);
+			if (lane >= (uint32_t)o) { if (az) { vv += pv; az = paz; } }
+		}
+		if (lane == 31) { cnt[wid] = az; cnt[8 + wid] = vv; }
+		__syncthreads();
+		uint32_t bv = 0;                                       // run pending after all the warps before mine
+		for (uint32_t ww = 0; ww < wid; ww++) { const uint32_t a2 = cnt[ww], v2 = cnt[8 + ww]; bv = a2 ? bv + v2 : v2; }
+		uint32_t eaz = __shfl_up_sync(0xffffffffu, az, 1), ev = __shfl_up_sync(0xffffffffu, vv, 1);
+		if (lane == 0) { eaz = 1u; ev = 0; }
+		zin_mine = eaz ? bv + ev : ev;                         // exclusive prefix = run pending at my chunk start
+		const uint32_t incl_v = az ? bv + vv : vv;
+		if (tid == MTF_NT - 1) red[40] = incl_v;               // run still pending at the end of the block
+		__syncthreads();
+		zpend_end = red[40];
+	}
 	auto ndigits = [](uint32_t r) { return r ? (uint32_t)(31 - __clz(r + 1)) : 0u; };
 	uint32_t outc = 0;
 	{
-		uint32_t z = zin[tid];
-		for (uint32_t i = c0; i < c1; i++) {
-			if (rk[i] == 0) z++;
-			else { outc += ndigits(z) + 1; z = 0; }
+		uint32_t z = zin_mine;
+		for (uint32_t i4 = c0; i4 < c1; i4 += 4) {
+			const uint32_t w = rk32[i4 >> 2];
+			#pragma unroll
+			for (int k = 0; k < 4; k++) if (i4 + k < c1) {
+				if (((w >> (8 * k)) & 255u) == 0) z++;
+				else { outc += ndigits(z) + 1; z = 0; }
+			}
 		}
 	}
 	// the thread that owns the last byte also flushes the final run and writes EOB
@@ -347,16 +376,20 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 	uint32_t total; uint32_t inc = block_scan_add<MTF_NT>(outc, red, &total);
 	uint32_t o = inc - outc;
 	{
-		uint32_t z = zin[tid];
+		uint32_t z = zin_mine;
 		auto put_run = [&](uint32_t zz) {
 			if (!zz) return;
 			uint32_t q = zz - 1;
 			for (;;) { mtfv[o++] = (uint16_t)(q & 1u); if (q < 2) break; q = (q - 2) >> 1; }
 		};
-		for (uint32_t i = c0; i < c1; i++) {
-			uint32_t r = rk[i];
-			if (r == 0) z++;
-			else { put_run(z); z = 0; mtfv[o++] = (uint16_t)(r + 1); }
+		for (uint32_t i4 = c0; i4 < c1; i4 += 4) {
+			const uint32_t w = rk32[i4 >> 2];
+			#pragma unroll
+			for (int k = 0; k < 4; k++) if (i4 + k < c1) {
+				const uint32_t r = (w >> (8 * k)) & 255u;
+				if (r == 0) z++;
+				else { put_run(z); z = 0; mtfv[o++] = (uint16_t)(r + 1); }
+			}
 		}
 		if (owner_of_end) { put_run(zpend_end); mtfv[o++] = (uint16_t)EOB; }
 	}

@@ -29,8 +29,8 @@ constexpr int PF_NT = 256;
 //   * WAY and K are template parameters: the rule function collapses to the few adds of the selected predictor.
 template <int WAY, int K>
 __global__ void __launch_bounds__(PF_NT)
-k_predict_fwd(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int W, int H, int T, int video,
-              uint32_t z0, int band)
+k_predict_fwd_rows(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int W, int H, int T, int video,
+                   uint32_t z0, int band)
 {
 	const int x = blockIdx.x * PF_NT + threadIdx.x;
 	if (x >= W) return;
@@ -82,6 +82,90 @@ k_predict_fwd(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int 
 			}
 		}
 		rp += (size_t)RB * W; op += (size_t)RB * W;
+	}
+}
+
+// Forward predictor, shared-memory tile form (the HBM-rate path).  A CTA stages a tile of 256 columns x (band + T + 1)
+// rows -- its output columns plus `hw` halo columns on the left (T+1 rounded to whole 16-byte vectors) and T+1 halo rows
+// above -- with coalesced 16-byte loads, four rows per thread in flight (many bytes in flight per thread is what
+// saturating HBM needs).  Then thread = tile column walks down the tile: every neighbour is a conflict-free 2-byte
+// shared-memory load (consecutive lanes, consecutive pixels, compile-time row pitch); results leave as 64-byte warp
+// stores.  DRAM sees 2 B/px in (+ the halo, mostly L2 hits) and 2 B/px out.
+constexpr int PF_PITCH = PF_NT;                  // shared-memory row pitch in pixels = tile width incl. halo
+
+template <int WAY, int K>
+__global__ void __launch_bounds__(PF_NT)
+k_predict_fwd(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int W, int H, int T, int video,
+              uint32_t z0, int band, int hw)
+{
+	extern __shared__ __align__(16) uint8_t pf_smem[];
+	uint16_t* sm = reinterpret_cast<uint16_t*>(pf_smem);
+	const int tid = (int)threadIdx.x;
+	const int cols = PF_NT - hw;                                 // output columns per CTA
+	const int x0 = blockIdx.x * cols, y0 = blockIdx.y * band, y1 = min(H, y0 + band);
+	const uint32_t z = z0 + blockIdx.z;
+	const uint64_t fpx = (uint64_t)W * H;
+	const uint16_t* cur = img + (uint64_t)z * fpx;
+	uint16_t* out = sym + (uint64_t)z * fpx;
+	const int ys = y0 - (T + 1), xs = x0 - hw;                   // image coordinates of smem element (0, 0); may be negative
+	const int yc = max(0, ys);                                   // staged rows [yc, y1): rows above the image stay unwritten
+	const int nrows = y1 - yc;
+	if (((W & 7) == 0) && ((((uintptr_t)img) & 15) == 0)) {
+		// thread (cv, rr): 16-byte column cv (of 32) of rows rr, rr+8, ...
+		const int cv = tid & 31, rr = tid >> 5;
+		const int xv = xs + cv * 8;
+		if (xv >= 0 && xv < W) {
+			const uint4* g = reinterpret_cast<const uint4*>(cur + (size_t)yc * W + xv);
+			uint16_t* d = sm + (yc - ys) * PF_PITCH + cv * 8;
+			const uint32_t gstep = (uint32_t)(W >> 3);
+			// asynchronous global -> shared copies (LDGSTS): every row of this thread is in flight at once, no staging registers
+			uint32_t dsm = (uint32_t)__cvta_generic_to_shared(d) + (uint32_t)rr * (PF_PITCH * 2);
+			const uint4* gp = g + (uint32_t)rr * gstep;
+			for (int r = rr; r < nrows; r += 8, dsm += 8 * PF_PITCH * 2, gp += 8 * gstep)
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dsm), "l"(gp) : "memory");
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+	} else {
+		const int xc = max(0, xs), nc = min(W, x0 + cols) - xc;
+		for (int i = tid; i < nc * nrows; i += PF_NT) {
+			const int r = i / nc, cx = i - r * nc;
+			sm[(yc - ys + r) * PF_PITCH + (xc - xs) + cx] = __ldg(cur + (size_t)(yc + r) * W + xc + cx);
+		}
+	}
+	__syncthreads();
+	const int x = xs + tid;
+	if (tid < hw || x >= W) return;
+	const int tx = x / T, u = x - tx * T;
+	int ty = y0 / T, v = y0 - ty * T;
+	const bool zf = (video & (int)z & 1) != 0;                  // `i_or_v & z`: only odd frames look back (klb_imageIO.cpp:1243)
+	const uint16_t* b = sm + (y0 - ys) * PF_PITCH + tid;
+	uint16_t* op = out + (size_t)y0 * W + x;
+	auto generic_row = [&](int y) {
+		auto px = [&](int dx, int dy) -> int { return (int)b[dy * PF_PITCH + dx]; };
+		int p = predict0(px, T, WAY, K, tx, ty, u, v);
+		if (WAY == 0 && zf) {
+			const int P = (int)__ldg(cur + (size_t)y * W + x - fpx);
+			p = (x == 0 && y == 0) ? P : ((p + P) >> 1);
+		}
+		*op = symbolize16((int)b[0] - p);
+	};
+	// walk the band tile row by tile row: inside a tile row ty is fixed and, after its first image row, v > 0 -- the
+	// straight-line interior rule then needs no per-row test at all (tx > 0 only splits the warp over the first tile column)
+	int y = y0;
+	while (y < y1) {
+		const int yend = min(y1, y + (T - v));                    // end of this tile row inside the band
+		if (WAY != 2 && v == 0) { generic_row(y); y++; v++; b += PF_PITCH; op += W; }
+		if (tx > 0 && ty > 0 && !(WAY == 0 && zf)) {
+			#pragma unroll 4
+			for (; y < yend; y++, v++, b += PF_PITCH, op += W) {
+				auto px = [&](int dx, int dy) -> int { return (int)b[dy * PF_PITCH + dx]; };
+				*op = symbolize16((int)b[0] - predict_interior<WAY, K>(px, T, u, v));
+			}
+		} else {
+			for (; y < yend; y++, v++, b += PF_PITCH, op += W) generic_row(y);
+		}
+		v = 0; ty++;
 	}
 }
 
@@ -416,37 +500,50 @@ static void launch_tiles_angle(const uint16_t* sym, uint16_t* out, int W, int H,
 	k_unpredict_tiles_angle<K><<<(unsigned)((uint64_t)count * tilesY * chunks), UT_NT, smem, st>>>(sym, out, W, H, T, z_start, z_step, tilesX, tilesY, chunks);
 }
 
+template <int WAY, int K>
+static void launch_predict_fwd_wk(const uint16_t* img, uint16_t* sym, int W, int H, int T, int video, uint32_t z0, uint32_t nz,
+                                  cudaStream_t st)
+{
+	const int hw = (T + 1 + 7) & ~7;
+	const bool tile = hw <= PF_NT / 2;                          // halo of at most half the tile (Nnum <= 127)
+	const int cols = tile ? PF_NT - hw : PF_NT;
+	const int colchunks = (W + cols - 1) / cols;
+	// band height: enough CTAs to fill the GPU for a single frame, tall tiles (less halo) for stacks; <= 48 KB of shared memory
+	int band = 64;
+	while (band > 16 && (uint64_t)colchunks * ((H + band - 1) / band) * nz < 1184) band >>= 1;
+	while (band > 8 && (size_t)(band + T + 1) * PF_PITCH * 2 > 48 * 1024) band >>= 1;
+	const size_t smem = (size_t)(band + T + 1) * PF_PITCH * 2;
+	if (tile) cudaFuncSetAttribute(k_predict_fwd<WAY, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	for (uint32_t zb = 0; zb < nz; zb += 65535) {            // gridDim.z limit
+		const uint32_t cz = std::min<uint32_t>(65535, nz - zb);
+		dim3 grid((unsigned)colchunks, (unsigned)((H + band - 1) / band), cz);
+		if (tile) k_predict_fwd<WAY, K><<<grid, PF_NT, smem, st>>>(img, sym, W, H, T, video, z0 + zb, band, hw);
+		else k_predict_fwd_rows<WAY, K><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0 + zb, band);   // huge Nnum
+	}
+}
+
 template <int WAY>
 static void launch_predict_fwd_way(const uint16_t* img, uint16_t* sym, int W, int H, int T, int k, int video,
-                                   uint32_t z0, uint32_t nz, int band, dim3 grid, cudaStream_t st)
+                                   uint32_t z0, uint32_t nz, cudaStream_t st)
 {
 	switch (k) {
-	case 1: k_predict_fwd<WAY, 1><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
-	case 2: k_predict_fwd<WAY, 2><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
-	case 3: k_predict_fwd<WAY, 3><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
-	case 4: k_predict_fwd<WAY, 4><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
-	case 5: k_predict_fwd<WAY, 5><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
-	case 6: k_predict_fwd<WAY, 6><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
-	default: k_predict_fwd<WAY, 7><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0, band); break;
+	case 1: launch_predict_fwd_wk<WAY, 1>(img, sym, W, H, T, video, z0, nz, st); break;
+	case 2: launch_predict_fwd_wk<WAY, 2>(img, sym, W, H, T, video, z0, nz, st); break;
+	case 3: launch_predict_fwd_wk<WAY, 3>(img, sym, W, H, T, video, z0, nz, st); break;
+	case 4: launch_predict_fwd_wk<WAY, 4>(img, sym, W, H, T, video, z0, nz, st); break;
+	case 5: launch_predict_fwd_wk<WAY, 5>(img, sym, W, H, T, video, z0, nz, st); break;
+	case 6: launch_predict_fwd_wk<WAY, 6>(img, sym, W, H, T, video, z0, nz, st); break;
+	default: launch_predict_fwd_wk<WAY, 7>(img, sym, W, H, T, video, z0, nz, st); break;
 	}
-	(void)nz;
 }
 
 void launch_predict_fwd(const uint16_t* img, uint16_t* sym, int W, int H, int T, int way, int k, int video,
                         uint32_t z0, uint32_t nz, cudaStream_t st)
 {
 	if (nz == 0) return;
-	// band height: enough CTAs to fill the GPU for a single frame, long bands (less halo re-reading) for stacks
-	const int colchunks = (W + PF_NT - 1) / PF_NT;
-	int band = 64;
-	while (band > 16 && (uint64_t)colchunks * ((H + band - 1) / band) * nz < 1184) band >>= 1;
-	for (uint32_t zb = 0; zb < nz; zb += 65535) {            // gridDim.z limit
-		const uint32_t cz = std::min<uint32_t>(65535, nz - zb);
-		dim3 grid((unsigned)colchunks, (unsigned)((H + band - 1) / band), cz);
-		if (way == 0) launch_predict_fwd_way<0>(img, sym, W, H, T, k, video, z0 + zb, cz, band, grid, st);
-		else if (way == 1) launch_predict_fwd_way<1>(img, sym, W, H, T, k, video, z0 + zb, cz, band, grid, st);
-		else launch_predict_fwd_way<2>(img, sym, W, H, T, k, video, z0 + zb, cz, band, grid, st);
-	}
+	if (way == 0) launch_predict_fwd_way<0>(img, sym, W, H, T, k, video, z0, nz, st);
+	else if (way == 1) launch_predict_fwd_way<1>(img, sym, W, H, T, k, video, z0, nz, st);
+	else launch_predict_fwd_way<2>(img, sym, W, H, T, k, video, z0, nz, st);
 }
 
 // frames z_start, z_start+z_step, ... (count of them); video stacks: even frames first, then odd frames.

@@ -6,7 +6,7 @@
 namespace lfm {
 
 constexpr int BWT_NT = 1024;
-constexpr int BWT_R  = 8;                 // elements per thread per radix tile (4-byte payloads)
+constexpr int BWT_R  = 12;                // elements per thread per radix tile (4-byte payloads)
 constexpr int BWT_NW = BWT_NT / 32;
 constexpr int BWT_WS = 257;               // row stride (words) of the per-warp digit counters: conflict-free rows AND columns;
                                           // column 256 is the dummy digit of the lanes past the end of the data
@@ -41,35 +41,44 @@ __device__ __forceinline__ void radix_scatter(uint32_t m, uint32_t* run, uint32_
 		const uint32_t eb = t0 + w * (32 * R) + lane;
 		#pragma unroll
 		for (int r = 0; r < R; r++) if (eb + r * 32 < m) pay[r] = load(eb + r * 32);
-		{
-			uint32_t peers[R], old[R];
+		#pragma unroll
+		for (int r = 0; r < R; r++) dl[r] = (eb + r * 32 < m) ? digit(pay[r]) : 256u;
+		constexpr int RH = R > 8 ? R / 2 : R;                // ranking sweeps over at most 8 elements at a time (register budget)
+		#pragma unroll
+		for (int r0 = 0; r0 < R; r0 += RH) {
+			uint32_t peers[RH], old[RH];
 			#pragma unroll
-			for (int r = 0; r < R; r++) dl[r] = (eb + r * 32 < m) ? digit(pay[r]) : 256u;
+			for (int r = 0; r < RH; r++) peers[r] = __match_any_sync(0xffffffffu, dl[r0 + r]);
 			#pragma unroll
-			for (int r = 0; r < R; r++) peers[r] = __match_any_sync(0xffffffffu, dl[r]);
-			#pragma unroll
-			for (int r = 0; r < R; r++) {
+			for (int r = 0; r < RH; r++) {
 				old[r] = 0;
-				if ((peers[r] & lt) == 0) old[r] = atomicAdd(&myc[dl[r]], (uint32_t)__popc(peers[r]));
+				if ((peers[r] & lt) == 0) old[r] = atomicAdd(&myc[dl[r0 + r]], (uint32_t)__popc(peers[r]));
 				__syncwarp();
 			}
 			#pragma unroll
-			for (int r = 0; r < R; r++) {
+			for (int r = 0; r < RH; r++) {
 				const uint32_t o = __shfl_sync(0xffffffffu, old[r], __ffs(peers[r]) - 1);
-				dl[r] = (dl[r] << 16) | (o + __popc(peers[r] & lt));
+				dl[r0 + r] = (dl[r0 + r] << 16) | (o + __popc(peers[r] & lt));
 			}
 		}
 		__syncthreads();
-		#pragma unroll
-		for (int q = 0; q < 256 / BWT_NW; q++) {          // exclusive scan over the warps, digit by digit
-			const uint32_t d = w * (256 / BWT_NW) + q;
-			const uint32_t v = LFM_WC(lane, d);
-			uint32_t incl = v;
+		{
+			// exclusive scan over the warps, digit by digit: thread (d, part) owns the counters of digit d in warps
+			// 8*part .. 8*part+7 (bank = (8*part + i + d) mod 32: conflict free), the 4 parts are adjacent lanes
+			static_assert(BWT_NT == 1024 && BWT_NW == 32, "scan layout assumes 1024 threads");
+			const uint32_t d = threadIdx.x >> 2, part = threadIdx.x & 3u;
+			uint32_t* col = wcnt + (part * 8) * BWT_WS + d;
+			uint32_t c[8], tot = 0;
 			#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
-			const uint32_t base = run[d];
-			LFM_WC(lane, d) = base + incl - v;
-			if (lane == 31) run[d] = base + incl;
+			for (int i = 0; i < 8; i++) { c[i] = col[i * BWT_WS]; tot += c[i]; }
+			uint32_t incl = tot;
+			uint32_t t1 = __shfl_up_sync(0xffffffffu, incl, 1); if (part >= 1) incl += t1;
+			uint32_t t2 = __shfl_up_sync(0xffffffffu, incl, 2); if (part >= 2) incl += t2;
+			uint32_t acc = run[d] + incl - tot;
+			#pragma unroll
+			for (int i = 0; i < 8; i++) { col[i * BWT_WS] = acc; acc += c[i]; }
+			__syncwarp();
+			if (part == 3) run[d] = acc;
 		}
 		__syncthreads();
 		#pragma unroll

@@ -39,7 +39,7 @@ w.write("\n")
 
 for name in seen:
     txt = run(["--page", "source", "--print-source", "cuda,sass", "--csv", "-k", "regex:^%s$" % name, "-c", "1"]) if False else \
-          run(["--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", "regex:%s" % name, "--launch-count", "1"])
+          run(["--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", "regex:%s" % name.replace("void ", "").split("<")[0], "--launch-count", "1"])
     rows = list(csv.reader(io.StringIO(txt)))
     hdr = None; cur_file = ""; lines = collections.OrderedDict()
     for r in rows:
