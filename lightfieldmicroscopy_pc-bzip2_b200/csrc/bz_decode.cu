@@ -424,10 +424,21 @@ k_imtf(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, DecJob* __restrict_
 size_t imtf_smem_bytes() { return (size_t)64 * IM_STS * 4 + (size_t)256 * IM_SLS + 64 * 4 + (IM_NT + 4) * 4 + 256 + 64; }
 
 // =====================================================================================================
-// k_inv_bwt : one CTA per block
+// k_inv_bwt : one persistent CTA per block.
+//   1. LF mapping = one stable counting-sort pass over the last column (decompress.c:494-510 cftab + tt);
+//   2. the n-step walk through tt (decompress.c:511-573 / bzlib.c unRLE) is a linked list.  It is cut at every K-th array
+//      position (+ the start): ~n/32 sublists.  Every thread measures four sublists at a time (four independent pointer
+//      chases in flight), the sublists are ranked by pointer jumping in shared memory (ceil(log2) rounds), and then
+//      written, again four at a time per thread.
+//   A block whose rotations are not all distinct (exactly periodic text) walks a shorter cycle several times; the
+//   ranking then does not cover the block and the sublists are chained sequentially from the start instead.
 // =====================================================================================================
-constexpr int IB_MAXS = 1500;     // max number of splitters
+constexpr int IB_MAXS = 6144;     // max number of regular splitters
 constexpr int IB_VIS  = 2 * (IB_MAXS + 2);   // max sublist visits (a periodic block laps its cycle)
+constexpr int IB_ILP  = 4;        // sublists walked concurrently by one thread
+constexpr uint32_t IB_NIL = 0xFFFFu;
+
+extern __shared__ __align__(16) uint8_t ib_smem[];
 
 __global__ void __launch_bounds__(BWT_NT, 1)
 k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict__ jobs, uint32_t njobs,
@@ -436,9 +447,9 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 	__shared__ uint32_t wcnt[BWT_NW * BWT_WS];
 	__shared__ uint32_t run[256];
 	__shared__ uint32_t red[64];
-	__shared__ uint32_t s_next[IB_MAXS + 2];
-	__shared__ uint32_t s_len[IB_MAXS + 2];
 	__shared__ uint32_t s_nvis;
+	uint32_t* s_dist = reinterpret_cast<uint32_t*>(ib_smem);                         // [2][IB_MAXS + 2]
+	uint16_t* s_nxt = reinterpret_cast<uint16_t*>(s_dist + 2 * (IB_MAXS + 2));      // [2][IB_MAXS + 2]
 	const uint32_t tid = threadIdx.x;
 	uint32_t* tt = tt_all + (size_t)blockIdx.x * cap;          // per-CTA scratch
 	uint32_t* vis = tt_all + (size_t)gridDim.x * cap + (size_t)blockIdx.x * 2 * IB_VIS;   // visit list (id, offset)
@@ -461,36 +472,102 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 		__syncthreads();
 
 		// ---- splitters: every K-th position, plus the start of the walk
-		uint32_t K = 64;
-		while ((n + K - 1) / K > IB_MAXS) K <<= 1;
-		const uint32_t S = (n + K - 1) / K;
+		uint32_t kshift = 2;                               // sublists of ~4 .. 32 steps: as many as the ranking arrays hold
+		while (((n + (1u << kshift) - 1) >> kshift) > (uint32_t)IB_MAXS) kshift++;
+		const uint32_t K = 1u << kshift, S = (n + K - 1) >> kshift;
 		const uint32_t p0 = tt[J.orig_ptr] >> 8;
-		const bool p0_regular = (p0 % K) == 0;
+		const bool p0_regular = (p0 & (K - 1)) == 0;
 		const uint32_t nspl = S + (p0_regular ? 0 : 1);
-		auto splitter_id = [&](uint32_t p, uint32_t& id) -> bool {
-			if (p % K == 0) { id = p / K; return true; }
-			if (p == p0) { id = S; return true; }
-			return false;
+		const uint32_t start_id = p0_regular ? (p0 >> kshift) : S;
+		auto measure = [&](uint32_t* dist, uint16_t* nxt, bool cut) {
+			for (uint32_t q0 = tid; q0 < nspl; q0 += BWT_NT * IB_ILP) {
+				uint32_t p[IB_ILP], len[IB_ILP]; bool act[IB_ILP];
+				#pragma unroll
+				for (int j = 0; j < IB_ILP; j++) { const uint32_t q = q0 + j * BWT_NT; act[j] = q < nspl; p[j] = q < S ? (q << kshift) : p0; len[j] = 0; }
+				bool any = true;
+				while (any) {
+					any = false;
+					#pragma unroll
+					for (int j = 0; j < IB_ILP; j++) if (act[j]) p[j] = tt[p[j]] >> 8;
+					#pragma unroll
+					for (int j = 0; j < IB_ILP; j++) if (act[j]) {
+						len[j]++;
+						if ((p[j] & (K - 1)) == 0 || p[j] == p0 || len[j] >= n) act[j] = false; else any = true;
+					}
+				}
+				#pragma unroll
+				for (int j = 0; j < IB_ILP; j++) {
+					const uint32_t q = q0 + j * BWT_NT;
+					if (q < nspl) {
+						uint32_t id = (p[j] == p0) ? start_id : (p[j] >> kshift);
+						if (cut && id == start_id) id = IB_NIL;                 // open the cycle at the start: a path
+						dist[q] = len[j]; nxt[q] = (uint16_t)id;
+					}
+				}
+			}
 		};
-		for (uint32_t q = tid; q < nspl; q += BWT_NT) {
-			uint32_t p = q < S ? q * K : p0, len = 0, id = 0;
-			do { p = tt[p] >> 8; len++; } while (!splitter_id(p, id) && len < n);
-			s_next[q] = id; s_len[q] = len;
-		}
+		measure(s_dist, s_nxt, true);
 		__syncthreads();
-		// ---- chain the sublists from the start for exactly n steps (a periodic block laps its cycle several times)
-		if (tid == 0) {
-			uint32_t q = p0_regular ? p0 / K : S, off = 0, nv = 0;
-			while (off < n && nv < (uint32_t)IB_VIS) { vis[2 * nv] = q; vis[2 * nv + 1] = off; nv++; off += s_len[q]; q = s_next[q]; }
-			if (off < n) J.status = 2;
-			s_nvis = nv;
+		// ---- rank the sublists: distance to the end of the path by pointer jumping (double buffered)
+		uint32_t cur = 0;
+		for (uint32_t span = 1; span < nspl; span <<= 1) {
+			const uint32_t* di = s_dist + cur * (IB_MAXS + 2); const uint16_t* ni = s_nxt + cur * (IB_MAXS + 2);
+			uint32_t* dq = s_dist + (cur ^ 1) * (IB_MAXS + 2); uint16_t* nq = s_nxt + (cur ^ 1) * (IB_MAXS + 2);
+			for (uint32_t q = tid; q < nspl; q += BWT_NT) {
+				const uint32_t nx = ni[q];
+				uint32_t d = di[q], n2 = nx;
+				if (nx != IB_NIL) { d += di[nx]; n2 = ni[nx]; }
+				dq[q] = d; nq[q] = (uint16_t)n2;
+			}
+			cur ^= 1;
+			__syncthreads();
 		}
+		const uint32_t* dfin = s_dist + cur * (IB_MAXS + 2);
+		const uint16_t* nfin = s_nxt + cur * (IB_MAXS + 2);
+		const bool ranked = (dfin[start_id] == n) && (nfin[start_id] == IB_NIL);     // the path from the start covers the block
 		__syncthreads();
-		const uint32_t nvis = s_nvis;
-		for (uint32_t i = tid; i < nvis; i += BWT_NT) {
-			uint32_t q = vis[2 * i], off = vis[2 * i + 1];
-			uint32_t p = q < S ? q * K : p0, len = s_len[q];
-			for (uint32_t k = 0; k < len && off + k < n; k++) { uint32_t e = tt[p]; txt[off + k] = (uint8_t)e; p = e >> 8; }
+		if (ranked) {
+			// ---- write: sublist q starts at output offset n - dist_to_end(q)
+			for (uint32_t q0 = tid; q0 < nspl; q0 += BWT_NT * IB_ILP) {
+				uint32_t p[IB_ILP], off[IB_ILP], end[IB_ILP];
+				#pragma unroll
+				for (int j = 0; j < IB_ILP; j++) {
+					const uint32_t q = q0 + j * BWT_NT;
+					p[j] = q < S ? (q << kshift) : p0; off[j] = 0; end[j] = 0;
+					if (q < nspl) { off[j] = n - dfin[q]; end[j] = n; }     // end: upper bound, the walk stops at the next splitter
+				}
+				bool any = true;
+				while (any) {
+					any = false;
+					uint32_t e[IB_ILP];
+					#pragma unroll
+					for (int j = 0; j < IB_ILP; j++) if (off[j] < end[j]) e[j] = tt[p[j]];
+					#pragma unroll
+					for (int j = 0; j < IB_ILP; j++) if (off[j] < end[j]) {
+						txt[off[j]] = (uint8_t)e[j];
+						p[j] = e[j] >> 8; off[j]++;
+						if ((p[j] & (K - 1)) == 0 || p[j] == p0) end[j] = off[j]; else any = true;
+					}
+				}
+			}
+		} else {
+			// ---- exactly periodic block: chain the sublists from the start for exactly n steps (laps its cycle)
+			uint32_t* s_len = s_dist; uint16_t* s_next = s_nxt;
+			measure(s_len, s_next, false);
+			__syncthreads();
+			if (tid == 0) {
+				uint32_t q = start_id, off = 0, nv = 0;
+				while (off < n && nv < (uint32_t)IB_VIS) { vis[2 * nv] = q; vis[2 * nv + 1] = off; nv++; off += s_len[q]; q = s_next[q]; }
+				if (off < n) J.status = 2;
+				s_nvis = nv;
+			}
+			__syncthreads();
+			const uint32_t nvis = s_nvis;
+			for (uint32_t i = tid; i < nvis; i += BWT_NT) {
+				uint32_t q = vis[2 * i], off = vis[2 * i + 1];
+				uint32_t p = q < S ? (q << kshift) : p0, len = s_len[q];
+				for (uint32_t k = 0; k < len && off + k < n; k++) { uint32_t e = tt[p]; txt[off + k] = (uint8_t)e; p = e >> 8; }
+			}
 		}
 		__syncthreads();
 	}
@@ -655,7 +732,9 @@ size_t inv_bwt_scratch_elems(int grid, uint32_t cap) { return (size_t)grid * cap
 void launch_inv_bwt(const uint8_t* bwt, uint32_t cap, DecJob* jobs, uint32_t njobs, uint32_t* tt_scratch, uint8_t* txt,
                     int grid, cudaStream_t st)
 {
-	k_inv_bwt<<<grid, BWT_NT, 0, st>>>(bwt, cap, jobs, njobs, tt_scratch, txt);
+	const size_t smem = (size_t)2 * (IB_MAXS + 2) * (4 + 2);
+	cudaFuncSetAttribute(k_inv_bwt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	k_inv_bwt<<<grid, BWT_NT, smem, st>>>(bwt, cap, jobs, njobs, tt_scratch, txt);
 }
 void launch_unrle(const uint8_t* txt, uint8_t* stage_scratch, uint32_t cap, uint32_t max_raw_bytes, DecJob* jobs, uint32_t njobs,
                   uint16_t* sym, const Geom& g, const uint64_t* block_ids, cudaStream_t st)

@@ -160,7 +160,98 @@ k_predict_fwd(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int 
 			#pragma unroll 4
 			for (; y < yend; y++, v++, b += PF_PITCH, op += W) {
 				auto px = [&](int dx, int dy) -> int { return (int)b[dy * PF_PITCH + dx]; };
-				*op = symbolize16((int)b[0] - predict_interior<WAY, K>(px, T, u, v));
+				*op = symbolize16((int)b[0] - predict_interior<WAY, K>(px, px, T, u, v));
+			}
+		} else {
+			for (; y < yend; y++, v++, b += PF_PITCH, op += W) generic_row(y);
+		}
+		v = 0; ty++;
+	}
+}
+
+// Two pixels per thread (the form used whenever rows are whole 16-byte vectors): same tile, 128 threads, each owning
+// the adjacent tile columns 2t and 2t+1.  The pair is read with one 32-bit shared load and written with one 32-bit
+// store; in the interior rule the row above (up, up-left) is carried in registers and the left neighbour of the second
+// pixel is the first pixel itself, so the near-neighbour ways cost two shared loads per PAIR and the loop overhead is
+// halved -- this is what takes the kernel from issue-bound to HBM-bound.
+constexpr int PF2_NT = PF_NT / 2;
+
+template <int WAY, int K>
+__global__ void __launch_bounds__(PF2_NT)
+k_predict_fwd2(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int W, int H, int T, int video,
+               uint32_t z0, int band, int hw)
+{
+	extern __shared__ __align__(16) uint8_t pf_smem[];
+	uint16_t* sm = reinterpret_cast<uint16_t*>(pf_smem);
+	const int tid = (int)threadIdx.x;
+	const int cols = PF_NT - hw;                                 // output columns per CTA
+	const int x0 = blockIdx.x * cols, y0 = blockIdx.y * band, y1 = min(H, y0 + band);
+	const uint32_t z = z0 + blockIdx.z;
+	const uint64_t fpx = (uint64_t)W * H;
+	const uint16_t* cur = img + (uint64_t)z * fpx;
+	uint16_t* out = sym + (uint64_t)z * fpx;
+	const int ys = y0 - (T + 1), xs = x0 - hw;                   // image coordinates of smem element (0, 0); may be negative
+	const int yc = max(0, ys);
+	const int nrows = y1 - yc;
+	{
+		const int cv = tid & 31, rr = tid >> 5;                    // 16-byte column cv (of 32) of rows rr, rr+4, ...
+		const int xv = xs + cv * 8;
+		if (xv >= 0 && xv < W) {
+			const uint32_t gstep = (uint32_t)(W >> 3);
+			const uint4* gp = reinterpret_cast<const uint4*>(cur + (size_t)yc * W + xv) + (uint32_t)rr * gstep;
+			uint32_t dsm = (uint32_t)__cvta_generic_to_shared(sm + (yc - ys) * PF_PITCH + cv * 8) + (uint32_t)rr * (PF_PITCH * 2);
+			for (int r = rr; r < nrows; r += 4, dsm += 4 * PF_PITCH * 2, gp += 4 * gstep)
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dsm), "l"(gp) : "memory");
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+	}
+	__syncthreads();
+	const int sc = 2 * tid;                                      // my first tile column
+	const int x = xs + sc;
+	if (sc < hw || x >= W) return;                               // hw and W are even: a pair is inside or outside as a whole
+	const int txa = x / T, ua = x - txa * T;
+	const int txb = (ua + 1 == T) ? txa + 1 : txa, ub = (ua + 1 == T) ? 0 : ua + 1;
+	int ty = y0 / T, v = y0 - ty * T;
+	const bool zf = (video & (int)z & 1) != 0;
+	const uint16_t* b = sm + (y0 - ys) * PF_PITCH + sc;
+	uint16_t* op = out + (size_t)y0 * W + x;
+	auto generic_row = [&](int y) {
+		auto pxa = [&](int dx, int dy) -> int { return (int)b[dy * PF_PITCH + dx]; };
+		auto pxb = [&](int dx, int dy) -> int { return (int)b[1 + dy * PF_PITCH + dx]; };
+		int pa = predict0(pxa, T, WAY, K, txa, ty, ua, v), pb = predict0(pxb, T, WAY, K, txb, ty, ub, v);
+		if (WAY == 0 && zf) {
+			const uint32_t P2 = __ldg(reinterpret_cast<const uint32_t*>(cur + (size_t)y * W + x - fpx));
+			const int Pa = (int)(P2 & 0xffffu), Pb = (int)(P2 >> 16);
+			pa = (x == 0 && y == 0) ? Pa : ((pa + Pa) >> 1);
+			pb = (pb + Pb) >> 1;
+		}
+		const uint32_t c2 = *reinterpret_cast<const uint32_t*>(b);
+		*reinterpret_cast<uint32_t*>(op) = (uint32_t)symbolize16((int)(c2 & 0xffffu) - pa) | ((uint32_t)symbolize16((int)(c2 >> 16) - pb) << 16);
+	};
+	int y = y0;
+	while (y < y1) {
+		const int yend = min(y1, y + (T - v));                    // end of this tile row inside the band
+		if (WAY != 2 && v == 0) { generic_row(y); y++; v++; b += PF_PITCH; op += W; }
+		if (txa > 0 && ty > 0 && !(WAY == 0 && zf)) {
+			if (y < yend) {
+				// the row above, carried in registers from here on
+				const uint32_t u2 = *reinterpret_cast<const uint32_t*>(b - PF_PITCH);
+				int up0 = (int)(u2 & 0xffffu), up1 = (int)(u2 >> 16), ul0 = (int)b[-PF_PITCH - 1];
+				#pragma unroll 4
+				for (; y < yend; y++, v++, b += PF_PITCH, op += W) {
+					const uint32_t c2 = *reinterpret_cast<const uint32_t*>(b);
+					const int c0 = (int)(c2 & 0xffffu), c1 = (int)(c2 >> 16);
+					const int left0 = (int)b[-1];
+					auto neara = [&](int dx, int dy) -> int { return dy == 0 ? left0 : (dx == 0 ? up0 : ul0); };
+					auto nearb = [&](int dx, int dy) -> int { return dy == 0 ? c0 : (dx == 0 ? up1 : up0); };
+					auto fara = [&](int dx, int dy) -> int { return (int)b[dy * PF_PITCH + dx]; };
+					auto farb = [&](int dx, int dy) -> int { return (int)b[1 + dy * PF_PITCH + dx]; };
+					const int pa = predict_interior<WAY, K>(neara, fara, T, ua, v);
+					const int pb = predict_interior<WAY, K>(nearb, farb, T, ub, v);
+					*reinterpret_cast<uint32_t*>(op) = (uint32_t)symbolize16(c0 - pa) | ((uint32_t)symbolize16(c1 - pb) << 16);
+					ul0 = left0; up0 = c0; up1 = c1;
+				}
 			}
 		} else {
 			for (; y < yend; y++, v++, b += PF_PITCH, op += W) generic_row(y);
@@ -509,15 +600,18 @@ static void launch_predict_fwd_wk(const uint16_t* img, uint16_t* sym, int W, int
 	const int cols = tile ? PF_NT - hw : PF_NT;
 	const int colchunks = (W + cols - 1) / cols;
 	// band height: enough CTAs to fill the GPU for a single frame, tall tiles (less halo) for stacks; <= 48 KB of shared memory
-	int band = 64;
+	const bool pairs = tile && ((W & 7) == 0) && ((((uintptr_t)img | (uintptr_t)sym) & 15) == 0);   // rows are whole 16-byte vectors
+	int band = pairs ? 32 : 64;                                 // 128-thread CTAs: smaller tiles keep ~36 warps per SM resident
 	while (band > 16 && (uint64_t)colchunks * ((H + band - 1) / band) * nz < 1184) band >>= 1;
 	while (band > 8 && (size_t)(band + T + 1) * PF_PITCH * 2 > 48 * 1024) band >>= 1;
 	const size_t smem = (size_t)(band + T + 1) * PF_PITCH * 2;
-	if (tile) cudaFuncSetAttribute(k_predict_fwd<WAY, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (pairs) cudaFuncSetAttribute(k_predict_fwd2<WAY, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	else if (tile) cudaFuncSetAttribute(k_predict_fwd<WAY, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	for (uint32_t zb = 0; zb < nz; zb += 65535) {            // gridDim.z limit
 		const uint32_t cz = std::min<uint32_t>(65535, nz - zb);
 		dim3 grid((unsigned)colchunks, (unsigned)((H + band - 1) / band), cz);
-		if (tile) k_predict_fwd<WAY, K><<<grid, PF_NT, smem, st>>>(img, sym, W, H, T, video, z0 + zb, band, hw);
+		if (pairs) k_predict_fwd2<WAY, K><<<grid, PF2_NT, smem, st>>>(img, sym, W, H, T, video, z0 + zb, band, hw);
+		else if (tile) k_predict_fwd<WAY, K><<<grid, PF_NT, smem, st>>>(img, sym, W, H, T, video, z0 + zb, band, hw);
 		else k_predict_fwd_rows<WAY, K><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0 + zb, band);   // huge Nnum
 	}
 }

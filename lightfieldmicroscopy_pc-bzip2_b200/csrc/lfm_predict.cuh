@@ -122,29 +122,31 @@ __device__ __forceinline__ int predict0(Fetch px, int T, int way, int k, int tx,
 
 // Straight-line form of predict0 for the bulk of the image: INTERIOR tiles (tx > 0 and ty > 0) and, for the ways that use
 // near neighbours (tiles, angle), rows with v > 0.  WAY and K are compile-time, the only data-dependent choice left is
-// u == 0 (a select).  Must agree with predict0 on its domain -- the forward kernel uses predict0 everywhere else.
-template <int WAY, int K, class Fetch>
-__device__ __forceinline__ int predict_interior(Fetch px, int T, int u, int v)
+// u == 0 (a select).  near(dx,dy) is only called with the literal offsets (-1,0) (0,-1) (-1,-1), so a caller may serve
+// them from registers; far(dx,dy) gets the offsets that involve T.  Must agree with predict0 on its domain -- the
+// forward kernel uses predict0 everywhere else.
+template <int WAY, int K, class Near, class Far>
+__device__ __forceinline__ int predict_interior(Near near, Far far, int T, int u, int v)
 {
 	if (WAY == 2) {
-		const int fu = px(0, -T), fl = px(-T, 0);
+		const int fu = far(0, -T), fl = far(-T, 0);
 		if (K == 1) return fl;
 		if (K == 2) return fu;
-		const int ful = px(-T, -T);
+		const int ful = far(-T, -T);
 		if (K == 3) return ful;
 		if (K == 4) return fu + fl - ful;
 		if (K == 5) return fu + ((fl - ful) >> 1);
 		if (K == 6) return fl + ((fu - ful) >> 1);
 		return (u > 0 && v > 0) ? ((fu + fl) >> 1) : (fu + fl - ful);
 	}
-	const int up = px(0, -1);
+	const int up = near(0, -1);
 	if (WAY == 1) {                                   // v > 0: u == 0 -> up; else the near-neighbour rule (5 and 6 trade places)
-		const int left = px(-1, 0);
+		const int left = near(-1, 0);
 		int gen;
 		if (K == 1) gen = left;
 		else if (K == 2) gen = up;
 		else {
-			const int ul = px(-1, -1);
+			const int ul = near(-1, -1);
 			if (K == 3) gen = ul;
 			else if (K == 4) gen = left + up - ul;
 			else if (K == 5) gen = up + ((left - ul) >> 1);          // kk = 6
@@ -155,15 +157,15 @@ __device__ __forceinline__ int predict_interior(Fetch px, int T, int u, int v)
 	}
 	// WAY 0 (tiles), v > 0: a = (u == 0); b and c cannot occur
 	const bool a = (u == 0);
-	if (K == 1) { const int fl = px(-T, 0); return a ? fl : ((px(-1, 0) + fl) >> 1); }
-	if (K == 2) { const int fu = px(0, -T); return a ? fu : ((up + fu) >> 1); }
-	if (K == 3) { const int far = px(-T, -T); return ((a ? up : px(-1, -1)) + far) >> 1; }
-	const int left = px(-1, 0);
+	if (K == 1) { const int fl = far(-T, 0); return a ? fl : ((near(-1, 0) + fl) >> 1); }
+	if (K == 2) { const int fu = far(0, -T); return a ? fu : ((up + fu) >> 1); }
+	if (K == 3) { const int f3 = far(-T, -T); return ((a ? up : near(-1, -1)) + f3) >> 1; }
+	const int left = near(-1, 0);
 	if (K == 7) {
-		const int g = px(0, -T) + px(-T, 0) - px(-T, -T);
-		return a ? ((g + up) >> 1) : ((px(0, -T - 1) + px(-T - 1, 0) + up + left) >> 2);
+		const int g = far(0, -T) + far(-T, 0) - far(-T, -T);
+		return a ? ((g + up) >> 1) : ((far(0, -T - 1) + far(-T - 1, 0) + up + left) >> 2);
 	}
-	const int fu = px(0, -T), fl = px(-T, 0), ful = px(-T, -T), ul = px(-1, -1);
+	const int fu = far(0, -T), fl = far(-T, 0), ful = far(-T, -T), ul = near(-1, -1);
 	int g, full;
 	if (K == 4) { g = fu + fl - ful; full = (g + up + left - ul) >> 1; }
 	else if (K == 5) { g = fu + ((fl - ful) >> 1); full = (g + up + ((left - ul) >> 1)) >> 1; }

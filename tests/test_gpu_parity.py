@@ -116,6 +116,22 @@ def test_oracle_cross_check_on_fresh_data(L, oracle, tmp_path):
             assert np.array_equal(L.read_stack(fg, way=way), a)
 
 
+@pytest.mark.parametrize("way", [0, 1, 2])
+def test_vector_width_frames_all_predictors(L, oracle, tmp_path, way):
+    """row length a multiple of 8 pixels (the two-pixels-per-thread forward kernel and the vectorised inverse strips):
+    every predictor of every way, file bytes == oracle file bytes, exact round trip"""
+    rng = np.random.default_rng(5 + way)
+    a = (lf_synth((2, 120, 272), 13, seed=9).astype(np.int64) + rng.integers(0, 300, (2, 120, 272))).astype(np.uint16)
+    for k in range(1, 8):
+        for hv in (8 + k,) + ((0x88 + k,) if way == 0 else ()):
+            fo, fg = str(tmp_path / "o.lfm"), str(tmp_path / "g.lfm")
+            rc, shv = oracle.write(a, fo, hv, 13, way, block_size=(96, 96, 2, 1, 1))
+            assert rc == 0
+            L.write_stack(a, fg, header_version=hv, nnum=13, block_size=(96, 96, 2, 1, 1), way=way)
+            assert open(fo, "rb").read() == open(fg, "rb").read(), (way, hex(hv))
+            assert np.array_equal(L.read_stack(fg, way=way), a)
+
+
 def test_c_abi_entry_points(L, tmp_path):
     """the six reference entry points: write, header, full read (malloc'd + in place), ROI read"""
     import ctypes as C
