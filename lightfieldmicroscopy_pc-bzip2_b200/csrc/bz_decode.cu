@@ -287,7 +287,6 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 // =====================================================================================================
 constexpr int IM_NT = 128;
 constexpr int IM_STS = IM_NT + 1;         // word row stride of the packed per-thread lists
-constexpr int IM_SLS = IM_NT + 4;         // byte row stride of the chunk-start lists
 
 extern __shared__ __align__(16) uint8_t im_smem[];
 
@@ -297,8 +296,9 @@ k_imtf(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, DecJob* __restrict_
        uint8_t* __restrict__ bwt_all, uint32_t cap)
 {
 	uint32_t* st = reinterpret_cast<uint32_t*>(im_smem);                               // [64][STS] packed lists
-	uint8_t* sl = im_smem + 64 * IM_STS * 4;                                            // [256][SLS] chunk-start lists
-	uint32_t* red = reinterpret_cast<uint32_t*>(sl + 256 * IM_SLS);                     // [64]
+	// the chunk-start lists reuse the same bytes: element (pos, t) of the permutation P(t) is read into a register just
+	// before element (pos, t) of start(t) is stored (phase B)
+	uint32_t* red = reinterpret_cast<uint32_t*>(im_smem + 64 * IM_STS * 4);             // [64]
 	uint32_t* s_start = red + 64;                                                       // [NT + 1] chunk boundaries (symbol index)
 	uint8_t* unseq = reinterpret_cast<uint8_t*>(s_start + IM_NT + 4);                   // [256]
 	uint8_t* st8 = reinterpret_cast<uint8_t*>(st);
@@ -390,10 +390,10 @@ k_imtf(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, DecJob* __restrict_
 	{
 		uint32_t cur0 = tid, cur1 = tid + IM_NT;              // start(0) = identity
 		for (uint32_t t = 0; t < IM_NT; t++) {
-			sl[tid * IM_SLS + t] = (uint8_t)cur0; sl[(tid + IM_NT) * IM_SLS + t] = (uint8_t)cur1;
+			const uint32_t p0 = ST_BYTE(tid, t), p1 = ST_BYTE(tid + IM_NT, t);      // P(t), before its bytes become start(t)
+			ST_BYTE(tid, t) = (uint8_t)cur0; ST_BYTE(tid + IM_NT, t) = (uint8_t)cur1;
 			__syncthreads();
-			const uint32_t p0 = ST_BYTE(tid, t), p1 = ST_BYTE(tid + IM_NT, t);
-			cur0 = sl[p0 * IM_SLS + t]; cur1 = sl[p1 * IM_SLS + t];      // column t is not written again: no second barrier
+			cur0 = ST_BYTE(p0, t); cur1 = ST_BYTE(p1, t);                 // column t is not written again: no second barrier
 		}
 		__syncthreads();
 	}
@@ -401,7 +401,7 @@ k_imtf(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, DecJob* __restrict_
 	// ---- C. replay: bytes out
 	{
 		uint32_t o = inc - outc;
-		uint32_t front = unseq[sl[0 * IM_SLS + tid]];
+		uint32_t front = unseq[ST_BYTE(0, tid)];
 		uint32_t i = a0;
 		while (i < a1) {
 			const uint32_t sym = mtfv[i];
@@ -412,7 +412,7 @@ k_imtf(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, DecJob* __restrict_
 				o += run;
 				continue;
 			}
-			front = unseq[sl[(uint32_t)qs[i] * IM_SLS + tid]];
+			front = unseq[ST_BYTE((uint32_t)qs[i], tid)];
 			L[o++] = (uint8_t)front;
 			i++;
 		}
@@ -421,7 +421,7 @@ k_imtf(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, DecJob* __restrict_
 	if (tid == 0) { J.n = total; if (J.orig_ptr >= total) J.status = 2; }
 }
 
-size_t imtf_smem_bytes() { return (size_t)64 * IM_STS * 4 + (size_t)256 * IM_SLS + 64 * 4 + (IM_NT + 4) * 4 + 256 + 64; }
+size_t imtf_smem_bytes() { return (size_t)64 * IM_STS * 4 + 64 * 4 + (IM_NT + 4) * 4 + 256 + 64; }
 
 // =====================================================================================================
 // k_inv_bwt : one persistent CTA per block.

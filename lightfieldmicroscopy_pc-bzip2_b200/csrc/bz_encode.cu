@@ -191,7 +191,6 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 //      block scan, symbols written to mtfv.   (compress.c:121-232)
 // =====================================================================================================
 constexpr int MTF_NT = 128;
-constexpr int MTF_RLS = MTF_NT + 4;        // byte row stride of the recency lists (bank-conflict-free both ways)
 constexpr int MTF_STS = MTF_NT + 1;        // word row stride of the packed start states
 
 extern __shared__ __align__(16) uint8_t mtf_smem[];
@@ -200,8 +199,9 @@ __global__ void __launch_bounds__(MTF_NT)
 k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scratch, one slot per block */, uint32_t cap,
       EncJob* __restrict__ jobs, uint32_t njobs, uint16_t* __restrict__ mtfv_all, uint32_t mcap)
 {
-	uint8_t* rl = mtf_smem;                                                                 // [256][RLS] recency lists, byte (pos, t)
-	uint32_t* st = reinterpret_cast<uint32_t*>(mtf_smem + 256 * MTF_RLS);                   // [64][STS] lists, 4 positions per word
+	// [64][STS] words, 4 list positions per word: first the chunks' recency lists, then -- column by column, as phase 2
+	// consumes them -- the chunks' start states (element (pos, t) of both lives in the same byte)
+	uint32_t* st = reinterpret_cast<uint32_t*>(mtf_smem);
 	uint32_t* seen = st + 64 * MTF_STS;                                                     // [8][NT] membership bitmaps
 	uint32_t* cnt = seen + 8 * MTF_NT;                                                      // [NT]
 	uint32_t* zin = cnt + MTF_NT;                                                           // [NT]
@@ -250,7 +250,7 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 			if (i4 - 4 + k < c1) {
 				const uint32_t c = seqmap[(word >> (8 * k)) & 255u];
 				const uint32_t wv = seen[(c >> 5) * MTF_NT + tid], bit = 1u << (c & 31);
-				if (!(wv & bit)) { seen[(c >> 5) * MTF_NT + tid] = wv | bit; rl[my_cnt * MTF_RLS + tid] = (uint8_t)c; my_cnt++; }
+				if (!(wv & bit)) { seen[(c >> 5) * MTF_NT + tid] = wv | bit; ST_BYTE(my_cnt, tid) = (uint8_t)c; my_cnt++; }
 			}
 		}
 	}
@@ -260,6 +260,7 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 	// ---- 2. start state of every chunk; thread j owns list positions j and j + NT
 	uint32_t mine0 = tid, mine1 = tid + MTF_NT;               // initial list: yy[i] = i
 	for (uint32_t t = 0; t < MTF_NT; t++) {
+		const uint32_t r0 = ST_BYTE(tid, t), r1 = ST_BYTE(tid + MTF_NT, t);       // recency list of chunk t, read before its bytes are reused
 		ST_BYTE(tid, t) = (uint8_t)mine0; ST_BYTE(tid + MTF_NT, t) = (uint8_t)mine1;
 		const uint32_t ct = cnt[t];
 		if (ct == 0) continue;                                // empty chunk (only past the end of the block)
@@ -274,8 +275,8 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 		const uint32_t lt = (1u << lane) - 1u;
 		if (keep0) tmp[ct + before0 + __popc(bal0 & lt)] = (uint8_t)mine0;
 		if (keep1) tmp[ct + before1 + __popc(bal1 & lt)] = (uint8_t)mine1;
-		if (tid < ct) tmp[tid] = rl[tid * MTF_RLS + t];
-		if (tid + MTF_NT < ct) tmp[tid + MTF_NT] = rl[(tid + MTF_NT) * MTF_RLS + t];
+		if (tid < ct) tmp[tid] = (uint8_t)r0;
+		if (tid + MTF_NT < ct) tmp[tid + MTF_NT] = (uint8_t)r1;
 		__syncthreads();
 		mine0 = tmp[tid]; mine1 = tmp[tid + MTF_NT];
 	}
@@ -396,7 +397,7 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 	if (tid == 0) { jobs[job].n_mtf = total; jobs[job].n_in_use = n_in_use; }
 }
 
-size_t mtf_smem_bytes() { return (size_t)256 * MTF_RLS + (size_t)64 * MTF_STS * 4 + 8 * MTF_NT * 4 + (MTF_NT * 2 + 64) * 4 + 512; }
+size_t mtf_smem_bytes() { return (size_t)64 * MTF_STS * 4 + 8 * MTF_NT * 4 + (MTF_NT * 2 + 64) * 4 + 512; }
 
 // =====================================================================================================
 // k_huff_pack : one CTA (8 warps) per block; warp t owns coding table t.
