@@ -447,14 +447,20 @@ __device__ __forceinline__ void hp_build_tree(uint64_t* heap, uint16_t* parent, 
 			const uint32_t tw = (uint32_t)(tmp >> 32);
 			int z = 1;
 			if (n_heap >= 1) {
+				// the children of BOTH possible next positions are fetched while this level is being decided, so the
+				// level-to-level chain is two compares and a select instead of a shared-memory round trip
+				ulonglong2 ch = *reinterpret_cast<const ulonglong2*>(heap + 2);               // children of the root
 				for (;;) {
 					const int y = z << 1;
-					const ulonglong2 ch = *reinterpret_cast<const ulonglong2*>(heap + y);     // children y, y+1
+					const int gy = min(2 * y, HP_HEAP - 4);                                   // grandchildren 4z .. 4z+3 (clamped: unused past the heap)
+					const ulonglong2 g0 = *reinterpret_cast<const ulonglong2*>(heap + gy);
+					const ulonglong2 g1 = *reinterpret_cast<const ulonglong2*>(heap + gy + 2);
 					const uint32_t w0 = (uint32_t)(ch.x >> 32), w1 = (uint32_t)(ch.y >> 32);
 					const bool right = w1 < w0;
 					const uint64_t c = right ? ch.y : ch.x;
 					if (tw < (right ? w1 : w0)) break;                                         // HP_INF below the heap: always stops
 					heap[z] = c; z = y + (right ? 1 : 0);
+					ch = right ? g1 : g0;
 				}
 				heap[z] = tmp;
 			}
@@ -499,7 +505,7 @@ __device__ __forceinline__ void or_bits(uint32_t* out, uint32_t bitpos, uint32_t
 
 __global__ void __launch_bounds__(HP_NT)
 k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __restrict__ jobs, uint32_t njobs,
-            uint8_t* __restrict__ sel_all, uint32_t selcap, uint8_t* __restrict__ out_all, uint32_t ocap, int level)
+            uint8_t* __restrict__ sel_all, uint32_t selcap, uint8_t* __restrict__ out_all, uint32_t ocap, int level, int spread)
 {
 	__shared__ uint32_t freq[kMaxAlpha + 6];
 	__shared__ uint32_t rfreq[kGroups][kMaxAlpha + 2];
@@ -622,7 +628,10 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 		for (;;) {
 			__syncthreads();
 			if (tid == 0) s_redo = 0;
-			if (wid == 0 && (int)lane < ng && ((redo >> lane) & 1u)) hp_build_tree(hheap[lane], hparent[lane], hlw[lane], alpha);
+			// small grids (latency matters, issue slots are plentiful): one warp per table, no divergence between the tables;
+			// large grids (throughput matters): the tables side by side in the lanes of one warp
+			if (spread) { if ((int)wid < ng && lane == 0 && ((redo >> wid) & 1u)) hp_build_tree(hheap[wid], hparent[wid], hlw[wid], alpha); }
+			else if (wid == 0 && (int)lane < ng && ((redo >> lane) & 1u)) hp_build_tree(hheap[lane], hparent[lane], hlw[lane], alpha);
 			__syncthreads();
 			if ((int)wid < ng && ((redo >> wid) & 1u)) {
 				const uint16_t* parent = hparent[wid];
@@ -888,7 +897,7 @@ void launch_huff_pack(const uint16_t* mtfv, uint32_t mcap, EncJob* jobs, uint32_
 {
 	const size_t smem = sizeof(uint64_t) * kGroups * HP_HEAP;
 	cudaFuncSetAttribute(k_huff_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	k_huff_pack<<<njobs, HP_NT, smem, st>>>(mtfv, mcap, jobs, njobs, sel, selcap, out, ocap, level);
+	k_huff_pack<<<njobs, HP_NT, smem, st>>>(mtfv, mcap, jobs, njobs, sel, selcap, out, ocap, level, 0);
 }
 
 }  // namespace lfm
