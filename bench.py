@@ -14,6 +14,7 @@ independent objects): weak scaling, no collective on the data path, value = all 
             writeImage/readImageFull without the disk), H2D + D2H inside the timed region
   roofline  dominant kernel (k_bwt): algorithmic bytes (post-RLE1 block in + last column out = 2 n per block) per
             launch / mean launch time from CUDA events on the engine stream; peak = MEASURED_PEAKS.json hbm_gbs
+  predictor_roofline  the HBM-bound kernels of the path (forward / inverse predictor) alone on a 32-frame stack, 4 B/px
   cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref, its CUDA predictor + threaded CPU bzip2,
             all host cores) on the same frame, file on /dev/shm; falls back to the oracle port if oracle/_ref is absent.
 Inputs rotate through a pool larger than L2 (24 frames = 201 MB > 126 MB), so no step finds its input in L2.
@@ -40,6 +41,8 @@ WORKLOADS = {
     "c3s": (16, 2048, 2048, 13, 1, 0, "configs[2] slice: 2048x2048x16 uint16 z-stack, Nnum=13, angle predictor, 2-D entropy selection, 96x96x8 blocks"),
 }
 POOL = 24
+# DRAM bytes of ONE k_bwt launch measured by ncu --set full (read + write), per workload (profiles/)
+NCU_TRAFFIC = {"c2": 20328960 + 89560064, "c3s": 4150188000 + 6526617000}
 
 
 def synth_pool(nframes, H, W, nnum, count, rank):
@@ -254,6 +257,33 @@ def main():
             e2e["h2d"] += a.nbytes + nblob; e2e["d2h"] += nblob + a.nbytes
     barrier()
 
+    # ---- predictor kernels alone (the HBM-bound stage the north star quotes a roofline target for): forward and inverse
+    # on a 32-frame 2048x2048 stack (268 MB, larger than L2), algorithmic traffic 4 B/px, timed by CUDA events on the
+    # engine stream inside lfmDebugPredictDevice.  Rank 0 only.
+    pred_roof = None
+    if rank == 0:
+        try:
+            PF = 32
+            big = torch.from_numpy(np.ascontiguousarray(np.tile(pool[0][:1], (PF, 1, 1))).view(np.int16)).cuda()
+            big += torch.arange(PF, dtype=torch.int16, device="cuda").view(PF, 1, 1)        # frames differ
+            symb = torch.empty_like(big); back = torch.empty_like(big)
+            xyz_b = L._u32x5(W, H, PF, 1, 1)
+            ms = C.c_float()
+            pred_roof = {"stack": "%dx%dx%d uint16 (%.0f MB)" % (W, H, PF, big.numel() * 2 / 1e6), "bytes_per_px": 4, "runs": {}}
+            for wy, kk in ((1, 4), (2, 4), (0, 4)):
+                L.set_way(wy)
+                for inv, src, dst in ((0, big, symb), (1, symb, back)):
+                    assert L.lib.lfmDebugPredictDevice(src.data_ptr(), dst.data_ptr(), xyz_b, nnum, kk, 0, inv, 2, C.byref(ms)) == 0
+                    assert L.lib.lfmDebugPredictDevice(src.data_ptr(), dst.data_ptr(), xyz_b, nnum, kk, 0, inv, 5, C.byref(ms)) == 0
+                    gbs = 4.0 * big.numel() / (ms.value * 1e-3) / 1e9
+                    pred_roof["runs"]["way%d_k%d_%s" % (wy, kk, "inverse" if inv else "forward")] = {"ms": ms.value, "achieved_gbs": gbs}
+                assert torch.equal(back, big), "predictor round trip mismatch"
+            L.set_way(way)
+            del big, symb, back
+        except Exception as ex:
+            pred_roof = {"error": repr(ex)}
+            L.set_way(way)
+
     t_step = torch.tensor([t_all, e2e["tc"] + e2e["td"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_step, op=dist.ReduceOp.MAX)
@@ -289,9 +319,14 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": e2e["h2d"] // args.steps, "d2h_bytes_per_step": e2e["d2h"] // args.steps,
                         "compress_gbs": raw * args.steps / e2e["tc"] / 1e9, "decompress_gbs": raw * args.steps / e2e["td"] / 1e9},
                 "gpu_launches": int(acc["launches"]),
-                "roofline": {"bound": "hbm", "kernel": "k_bwt (rotation sort of all 96x96 blocks of the frame set, one launch)",
-                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "peak_source": peak_src, "algorithmic_bytes_per_launch": 2 * n_post_rle, "launch_ms": bwt_ms},
+                "roofline": {"bound": "hbm", "kernel": "k_bwt (rotation sort of all 96x96 blocks of the frame set, one launch; the largest kernel of the step)",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": NCU_TRAFFIC.get(args.workload),
+                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_bwt, one launch, ncu --set full (profiles/r1_02_ncu_full_c2.md, r1_03_ncu_full_c3f_bwt_invbwt.md)",
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": 2 * n_post_rle, "launch_ms": bwt_ms,
+                             "note": "a block sort is latency / shared-memory bound, not HBM bound: the HBM roofline is quoted as the contract asks; the HBM-bound kernels of the path are the predictors, see predictor_roofline"},
+                "predictor_roofline": None if pred_roof is None else dict(pred_roof, peak=peak, unit="GB/s",
+                    frac={k: v["achieved_gbs"] / peak for k, v in pred_roof.get("runs", {}).items()}),
                 "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

@@ -81,6 +81,13 @@ const char* lfmLastError(void);
    info[8] = { nblock, crc, origPtr, nInUse, nMTF, nGroups, nSelectors, streamBytes } */
 int lfmDebugEncodeBlock(const void* bytes, uint32_t n, uint8_t* rle1, uint8_t* bwt, uint16_t* mtfv, uint8_t* stream, uint32_t info[8]);
 
+/* measurement hook: run ONLY the predictor kernels on a device-resident stack, `reps` times back to back, and return
+   the mean device time per repetition (CUDA events on the engine stream).  inverse = 0: forward predictor + symbolize
+   d_in (pixels) -> d_out (symbols); inverse = 1: unsymbolize + inverse predictor d_in (symbols) -> d_out (pixels).
+   k = 1..7, way = current lfmSetPredictorWay. Algorithmic traffic: 4 bytes per pixel. */
+int lfmDebugPredictDevice(const void* d_in, void* d_out, const uint32_t xyzct[KLB_DATA_DIMS], uint8_t Nnum, int k, int video,
+                          int inverse, int reps, float* ms_per_rep);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,8 @@ lib.lfmGetLastStats.argtypes = [C.POINTER(LfmStats)]; lib.lfmGetLastStats.restyp
 lib.lfmLastError.restype = C.c_char_p
 lib.lfmDebugEncodeBlock.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.lfmDebugEncodeBlock.restype = C.c_int
+lib.lfmDebugPredictDevice.argtypes = [C.c_void_p, C.c_void_p, _u32x5, C.c_uint8, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+lib.lfmDebugPredictDevice.restype = C.c_int
 
 _libc = C.CDLL(None)
 _libc.free.argtypes = [C.c_void_p]
@@ -88,7 +90,7 @@ _libc.free.argtypes = [C.c_void_p]
 EXPORTS = ["writeKLBstack", "writeKLBstackSlices", "readKLBheader", "readKLBstack", "readKLBstackInPlace", "readKLBroiInPlace",
            "lfmSetPredictorWay", "lfmGetPredictorWay", "lfmSetDevices", "writeLFMstackEx", "readLFMheaderEx",
            "lfmCompressToMemory", "lfmCompressToBuffer", "lfmDecompressFromMemory", "lfmCompressDevice", "lfmDecompressDevice", "lfmNumBlocks",
-           "lfmGetLastStats", "lfmLastError", "lfmDebugEncodeBlock"]
+           "lfmGetLastStats", "lfmLastError", "lfmDebugEncodeBlock", "lfmDebugPredictDevice"]
 
 
 class LfmError(RuntimeError):

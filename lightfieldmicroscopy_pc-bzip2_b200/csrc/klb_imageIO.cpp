@@ -665,6 +665,33 @@ int lfmDecompressDevice(const void* d_payload, const uint64_t* blockOffset, uint
 int lfmGetLastStats(lfm_stats* out) { if (!out) return 1; *out = g_stats; return 0; }
 const char* lfmLastError(void) { return g_err.c_str(); }
 
+int lfmDebugPredictDevice(const void* d_in, void* d_out, const uint32_t xyzct[5], uint8_t Nnum, int k, int video, int inverse,
+                          int reps, float* ms_per_rep)
+{
+	if (current_ndev() <= 0) return LFM_ERR_CUDA;
+	if (reps < 1 || !ms_per_rep) return LFM_ERR_OPEN;
+	Engine& e = Engine::for_device(g_set.first_device);
+	cudaSetDevice(e.device());
+	StackDesc s;
+	for (int d = 0; d < 5; d++) { s.xyzct[d] = xyzct[d]; s.blockSize[d] = xyzct[d]; }
+	s.Nnum = Nnum ? Nnum : 1; s.way = current_way();
+	const uint32_t F = xyzct[2] * xyzct[3] * xyzct[4];
+	cudaStream_t st = (cudaStream_t)e.stream();
+	cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+	int rc = 0;
+	cudaEventRecord(a, st);
+	for (int r = 0; r < reps && rc == 0; r++)
+		rc = inverse ? e.unpredict((const uint16_t*)d_in, (uint16_t*)d_out, s, k, video, 0, F)
+		             : e.predict((const uint16_t*)d_in, (uint16_t*)d_out, s, k, video, 0, F);
+	cudaEventRecord(b, st);
+	cudaStreamSynchronize(st);
+	float ms = 0.f;
+	if (rc == 0 && cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); rc = LFM_ERR_CUDA; }
+	cudaEventDestroy(a); cudaEventDestroy(b);
+	*ms_per_rep = ms / (float)reps;
+	return rc;
+}
+
 int lfmDebugEncodeBlock(const void* bytes, uint32_t n, uint8_t* rle1, uint8_t* bwt, uint16_t* mtfv, uint8_t* stream, uint32_t info[8])
 {
 	if (n == 0 || (n & 1)) return LFM_ERR_OPEN;

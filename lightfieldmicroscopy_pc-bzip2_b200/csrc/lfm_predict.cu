@@ -459,64 +459,118 @@ k_unpredict_angle(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H,
 //   writes -- no synchronisation at all), then the strip is written back coalesced.
 constexpr int UG_MAX_SMEM = 200 * 1024;
 
+// One CTA decodes G sub-images that are neighbours in u (same v): a gathered 32-byte sector then carries G useful
+// pixels instead of one, and the decoded pixels -- staged in shared memory, in place of the residuals -- leave as
+// G-pixel runs: the sub-aperture gather / scatter is L2-sector bound.
+template <int WAY, int K>
 __global__ void __launch_bounds__(1024)
-k_unpredict_grid(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T, int way, int k,
-                 uint32_t z_start, uint32_t z_step, uint32_t uv_per_frame)
+k_unpredict_grid(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T,
+                 uint32_t z_start, uint32_t z_step, int G, int ugroups, int vcount, int nxr)
 {
 	extern __shared__ __align__(16) uint8_t ug_smem[];
 	const uint32_t tid = threadIdx.x;
-	const uint32_t f = blockIdx.x / uv_per_frame, uv = blockIdx.x - f * uv_per_frame;
-	const int v = (int)(uv / (uint32_t)T), u = (int)(uv - (uint32_t)v * (uint32_t)T);      // (0,0) for the DC grid
-	const int nx = (W - u + T - 1) / T, ny = (H - v + T - 1) / T;                         // grid points of this sub-image
-	if (nx <= 0 || ny <= 0) return;
+	uint32_t bq = blockIdx.x;
+	const int ug = (int)(bq % (uint32_t)ugroups); bq /= (uint32_t)ugroups;
+	const int v = (int)(bq % (uint32_t)vcount);                                              // (0,0) only for the DC grid
+	const uint32_t f = bq / (uint32_t)vcount;
+	const int u0 = ug * G;
+	const int gcount = min(G, (WAY == 2 ? T : 1) - u0);                                      // sub-images of this CTA
+	const int nx0 = (W - u0 + T - 1) / T, ny = (H - v + T - 1) / T;                          // grid points (widest sub-image)
+	if (nx0 <= 0 || ny <= 0 || gcount <= 0) return;
 	const uint64_t fpx = (uint64_t)W * H;
 	const uint32_t z = z_start + f * z_step;
-	const uint16_t* s = sym + (uint64_t)z * fpx + (size_t)v * W + u;
-	uint16_t* o = out + (uint64_t)z * fpx + (size_t)v * W + u;
-	int16_t* res = reinterpret_cast<int16_t*>(ug_smem);                                    // [ny][nx] residuals
-	uint16_t* line = reinterpret_cast<uint16_t*>(ug_smem) + (((size_t)nx * ny + 7) & ~(size_t)7);   // [2][nx + 1]
+	const uint16_t* s = sym + (uint64_t)z * fpx + (size_t)v * W + u0;
+	uint16_t* o = out + (uint64_t)z * fpx + (size_t)v * W + u0;
+	const uint32_t plane = ((uint32_t)nx0 * (uint32_t)ny + 7u) & ~7u;
+	int16_t* res = reinterpret_cast<int16_t*>(ug_smem);                                      // [G][ny][nx0] residuals, then pixels
+	uint16_t* line = reinterpret_cast<uint16_t*>(ug_smem) + (size_t)G * plane;               // [G][2][nx0 + 1]
 	const size_t rowstep = (size_t)T * W;
 
-	// ---- gather (unsymbolize on the way in)
-	const uint32_t total = (uint32_t)nx * (uint32_t)ny;
-	for (uint32_t i0 = tid; i0 < total; i0 += blockDim.x * 8) {
-		uint16_t q[8];
-		#pragma unroll
-		for (int r = 0; r < 8; r++) {
-			const uint32_t i = i0 + r * blockDim.x;
-			if (i < total) { const uint32_t gy = i / (uint32_t)nx, gx = i - gy * (uint32_t)nx; q[r] = __ldg(s + gy * rowstep + (size_t)gx * T); }
+	// ---- gather (unsymbolize on the way in).  Work item = (grid row gy, element e of the row), e = gx * gcount + g:
+	// neighbouring threads read neighbouring pixels of one tile, then the next tile
+	const uint32_t rowlen = (uint32_t)nx0 * (uint32_t)gcount;
+	const uint32_t rpp = max(1u, blockDim.x / rowlen);                                      // grid rows per pass
+	const uint32_t er = tid / rowlen, ee = tid - er * rowlen;                               // my row slot, my element
+	const uint32_t egx = ee / (uint32_t)gcount, eg = ee - egx * (uint32_t)gcount;
+	const bool eok = er < rpp && egx * T + u0 + eg < (uint32_t)W;
+	const size_t eoff = (size_t)egx * T + eg;
+	int16_t* eres = res + eg * plane + egx;
+	if (rowlen <= blockDim.x) {
+		for (uint32_t gy0 = 0; gy0 < (uint32_t)ny; gy0 += rpp * 8) {
+			uint16_t q[8];
+			#pragma unroll
+			for (int r = 0; r < 8; r++) { const uint32_t gy = gy0 + r * rpp + er; q[r] = 0; if (eok && gy < (uint32_t)ny) q[r] = __ldg(s + gy * rowstep + eoff); }
+			#pragma unroll
+			for (int r = 0; r < 8; r++) { const uint32_t gy = gy0 + r * rpp + er; if (er < rpp && gy < (uint32_t)ny) eres[gy * nx0] = (int16_t)unsymbolize16(q[r]); }
 		}
-		#pragma unroll
-		for (int r = 0; r < 8; r++) { const uint32_t i = i0 + r * blockDim.x; if (i < total) res[i] = (int16_t)unsymbolize16(q[r]); }
+	} else {
+		for (uint32_t gy = 0; gy < (uint32_t)ny; gy++)
+			for (uint32_t e = tid; e < rowlen; e += blockDim.x) {
+				const uint32_t gx = e / (uint32_t)gcount, g = e - gx * (uint32_t)gcount;
+				uint16_t qv = 0;
+				if (gx * T + u0 + g < (uint32_t)W) qv = __ldg(s + gy * rowstep + (size_t)gx * T + g);
+				res[g * plane + gy * nx0 + gx] = (int16_t)unsymbolize16(qv);
+			}
 	}
+	// thread (g, tx)
+	const int g = (int)(tid / (uint32_t)nxr), tx = (int)(tid - (uint32_t)g * (uint32_t)nxr);
+	const int u = u0 + g;
+	const int nx = (g < gcount) ? (W - u + T - 1) / T : 0;                                   // this sub-image's width
 	// way space: tile (0,0) is an ordinary intra-tile DPCM decoded beforehand (k_unpredict_seed); DC grid: predictor 0
 	int first = 0;
-	if (tid == 0 && way == 2) first = (int)__ldcg(o);
+	if (tx == 0 && nx > 0 && WAY == 2) first = (int)__ldcg(o + g);
 	__syncthreads();
 
 	// ---- wavefront
-	const int tx = (int)tid;
+	int16_t* myres = res + (size_t)g * plane;
+	uint16_t* myline = line + (size_t)g * 2 * (nx0 + 1);
 	int up = 0, upleft = 0;
-	const int nsteps = nx + ny - 1;
+	const int nsteps = nx0 + ny - 1;
 	for (int d = 0; d < nsteps; d++) {
 		const int ty = d - tx;
-		const uint16_t* rd = line + ((d + 1) & 1) * (nx + 1);           // written at step d-1
-		uint16_t* wr = line + (d & 1) * (nx + 1);
+		const uint16_t* rd = myline + ((d + 1) & 1) * (nx0 + 1);        // written at step d-1
+		uint16_t* wr = myline + (d & 1) * (nx0 + 1);
 		if (tx < nx && ty >= 0 && ty < ny) {
 			const int left = tx > 0 ? (int)rd[tx - 1] : 0;
+			int16_t* cell = myres + (size_t)ty * nx0 + tx;
 			int val;
-			if (d == 0) val = (way == 2) ? first : (int)(uint16_t)res[0];
+			if (d == 0) val = (WAY == 2) ? first : (int)(uint16_t)*cell;
 			else {
 				auto px = [&](int dx, int dy) -> int { return dx == 0 ? up : (dy == 0 ? left : upleft); };
-				const int p = predict0(px, T, way, k, tx, ty, u, v);
-				val = (int)(uint16_t)((int)res[(size_t)ty * nx + tx] + p);
+				const int p = predict0(px, T, WAY, K, tx, ty, u, v);
+				val = (int)(uint16_t)((int)*cell + p);
 			}
 			wr[tx] = (uint16_t)val;
-			o[(size_t)ty * rowstep + (size_t)tx * T] = (uint16_t)val;
+			*cell = (int16_t)val;
 			upleft = left; up = val;
 		}
 		__syncthreads();
 	}
+
+	// ---- scatter the decoded sub-images, same traversal as the gather
+	if (rowlen <= blockDim.x) {
+		for (uint32_t gy = er; gy < (uint32_t)ny; gy += rpp)
+			if (eok) o[gy * rowstep + eoff] = (uint16_t)eres[gy * nx0];
+	} else {
+		for (uint32_t gy = 0; gy < (uint32_t)ny; gy++)
+			for (uint32_t e = tid; e < rowlen; e += blockDim.x) {
+				const uint32_t gx = e / (uint32_t)gcount, g2 = e - gx * (uint32_t)gcount;
+				if (gx * T + u0 + g2 < (uint32_t)W) o[gy * rowstep + (size_t)gx * T + g2] = (uint16_t)res[g2 * plane + gy * nx0 + gx];
+			}
+	}
+}
+
+template <int WAY>
+static void launch_unpredict_grid(const uint16_t* sym, uint16_t* out, int W, int H, int T, int k, uint32_t z_start, uint32_t z_step,
+                                  unsigned grid, unsigned block, size_t smem, int G, int ugroups, int vcount, int nxr, cudaStream_t st)
+{
+	#define LFM_UG(KK) do { cudaFuncSetAttribute(k_unpredict_grid<WAY, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+		k_unpredict_grid<WAY, KK><<<grid, block, smem, st>>>(sym, out, W, H, T, z_start, z_step, G, ugroups, vcount, nxr); } while (0)
+	switch (k) {
+	case 1: LFM_UG(1); break; case 2: LFM_UG(2); break; case 3: LFM_UG(3); break; case 4: LFM_UG(4); break;
+	case 5: LFM_UG(5); break; case 6: LFM_UG(6); break; default: LFM_UG(7); break;
+	}
+	#undef LFM_UG
 }
 
 constexpr int UT_NT = 128;       // tiles (= threads) per CTA
@@ -544,11 +598,15 @@ k_unpredict_tiles_angle(const uint16_t* __restrict__ sym, uint16_t* out, int W, 
 
 	// ---- stage the strip (residual symbols)
 	if (vec) {
-		const int wv = sw >> 3;
-		for (int i = (int)tid; i < wv * th; i += UT_NT) {
-			const int r = i / wv, cx = i - r * wv;
-			reinterpret_cast<uint4*>(sm + (size_t)r * pitch)[cx] = __ldg(reinterpret_cast<const uint4*>(s + (size_t)r * W) + cx);
+		const int wv = sw >> 3;                                   // asynchronous 16-byte copies: the whole strip in flight at once
+		for (int r = 0; r < th; r++) {
+			const uint4* gp = reinterpret_cast<const uint4*>(s + (size_t)r * W);
+			const uint32_t dsm = (uint32_t)__cvta_generic_to_shared(sm + (size_t)r * pitch);
+			for (int cx = (int)tid; cx < wv; cx += UT_NT)
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dsm + (uint32_t)cx * 16u), "l"(gp + cx) : "memory");
 		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
 	} else {
 		for (int i = (int)tid; i < sw * th; i += UT_NT) { const int r = i / sw, cx = i - r * sw; sm[(size_t)r * pitch + cx] = __ldg(s + (size_t)r * W + cx); }
 	}
@@ -562,10 +620,28 @@ k_unpredict_tiles_angle(const uint16_t* __restrict__ sym, uint16_t* out, int W, 
 		t0[0] = __ldcg(o + (size_t)tid * T);                              // the DC, decoded by k_unpredict_grid
 		for (int v = 0; v < th; v++) {
 			uint16_t* row = t0 + (size_t)v * pitch;
-			for (int u = (v == 0) ? 1 : 0; u < tw; u++) {
-				auto px = [&](int dx, int dy) -> int { return (int)row[u + dx + dy * pitch]; };
-				const int p = predict0(px, T, 1, K, tx, ty, u, v);
-				row[u] = (uint16_t)(unsymbolize16(row[u]) + p);
+			if (v > 0 && tx > 0 && ty > 0) {
+				// interior tile, v > 0: straight-line rule; left / up-left ride in registers, so the only value on the
+				// pixel-to-pixel dependency chain is the previous result (the row above is an independent shared load)
+				const uint16_t* above = row - pitch;
+				int up = (int)above[0];
+				int left = (int)(uint16_t)(unsymbolize16(row[0]) + up);           // u == 0: predicted from the pixel above
+				row[0] = (uint16_t)left;
+				int ul = up;
+				for (int u = 1; u < tw; u++) {
+					up = (int)above[u];
+					auto near = [&](int dx, int dy) -> int { return dy == 0 ? left : (dx == 0 ? up : ul); };
+					const int p = predict_interior<1, K>(near, near, T, u, v);
+					left = (int)(uint16_t)(unsymbolize16(row[u]) + p);
+					row[u] = (uint16_t)left;
+					ul = up;
+				}
+			} else {
+				for (int u = (v == 0) ? 1 : 0; u < tw; u++) {
+					auto px = [&](int dx, int dy) -> int { return (int)row[u + dx + dy * pitch]; };
+					const int p = predict0(px, T, 1, K, tx, ty, u, v);
+					row[u] = (uint16_t)(unsymbolize16(row[u]) + p);
+				}
 			}
 		}
 	}
@@ -649,19 +725,22 @@ int launch_unpredict(const uint16_t* sym, uint16_t* out, int W, int H, int T, in
 	if (count == 0) return 0;
 	const int tilesX = (W + T - 1) / T, tilesY = (H + T - 1) / T;
 	const unsigned wpb = UF_NT / 32;
-	const size_t grid_smem = ((((size_t)tilesX * tilesY + 7) & ~(size_t)7) + 2 * ((size_t)tilesX + 1)) * 2 + 16;
-	const bool grid_ok = tilesX <= 1024 && grid_smem <= (size_t)UG_MAX_SMEM;
-	const unsigned grid_nt = (unsigned)std::max(32, (tilesX + 31) & ~31);
+	// sub-images per CTA for the way "space" (neighbours in u share 32-byte sectors): as many as shared memory / 1024 threads allow
+	const size_t plane_b = ((((size_t)tilesX * tilesY + 7) & ~(size_t)7) + 2 * ((size_t)tilesX + 1)) * 2;
+	const int nxr = std::max(32, (tilesX + 31) & ~31);
+	int G = std::min(4, T);
+	while (G > 1 && ((size_t)G * plane_b + 16 > (size_t)UG_MAX_SMEM || G * nxr > 1024)) G--;
+	const bool grid_ok = nxr <= 1024 && plane_b + 16 <= (size_t)UG_MAX_SMEM;
 	if (!video && way == 2 && grid_ok) {                    // tile (0,0), then T*T sub-aperture recurrences per frame
 		k_unpredict_seed<<<(count + wpb - 1) / wpb, UF_NT, 0, st>>>(sym, out, W, H, T, way, k, z_start, z_step, count, 0);
-		cudaFuncSetAttribute(k_unpredict_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_smem);
-		k_unpredict_grid<<<(unsigned)((uint64_t)count * T * T), grid_nt, grid_smem, st>>>(sym, out, W, H, T, 2, k, z_start, z_step, (uint32_t)(T * T));
+		const size_t smem = (size_t)G * plane_b + 16;
+		const int ugroups = (T + G - 1) / G;
+		launch_unpredict_grid<2>(sym, out, W, H, T, k, z_start, z_step, (unsigned)((uint64_t)count * T * ugroups), (unsigned)(G * nxr), smem, G, ugroups, T, nxr, st);
 		return cudaGetLastError() == cudaSuccess ? 0 : 1;
 	}
 	const size_t strip_smem = (size_t)T * T * UT_NT * 2 + 16;
 	if (!video && way == 1 && k != 2 && grid_ok && strip_smem <= (size_t)UG_MAX_SMEM) {   // DC grid, then every tile on its own
-		cudaFuncSetAttribute(k_unpredict_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_smem);
-		k_unpredict_grid<<<count, grid_nt, grid_smem, st>>>(sym, out, W, H, T, 1, k, z_start, z_step, 1u);
+		launch_unpredict_grid<1>(sym, out, W, H, T, k, z_start, z_step, count, (unsigned)nxr, plane_b + 16, 1, 1, 1, nxr, st);
 		const int chunks = (tilesX + UT_NT - 1) / UT_NT;
 		switch (k) {
 		case 1: launch_tiles_angle<1>(sym, out, W, H, T, z_start, z_step, count, tilesX, tilesY, chunks, strip_smem, st); break;

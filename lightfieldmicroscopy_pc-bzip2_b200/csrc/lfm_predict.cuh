@@ -181,8 +181,7 @@ __device__ __forceinline__ uint16_t symbolize16(int residual)
 }
 __device__ __forceinline__ int unsymbolize16(uint16_t s)
 {
-	int neg = s & 1;
-	return (int)(int16_t)((1 - 2 * neg) * (((int)s + neg) / 2));
+	return ((int)s >> 1) ^ -((int)s & 1);         // even: s/2;  odd: ~(s >> 1) = -(s + 1)/2   (== (1 - 2 neg) * ((s + neg) / 2))
 }
 
 }  // namespace lfm
