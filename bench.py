@@ -39,6 +39,8 @@ WORKLOADS = {
     # name: (frames per step, H, W, Nnum, way, headerVersion, description)
     "c2": (1, 2048, 2048, 15, 2, 8 + 4, "configs[1]: synthetic 2048x2048 uint16 LF frame, Nnum=15, space predictor 4 + bzip2, 96x96x1 blocks"),
     "c3s": (16, 2048, 2048, 13, 1, 0, "configs[2] slice: 2048x2048x16 uint16 z-stack, Nnum=13, angle predictor, 2-D entropy selection, 96x96x8 blocks"),
+    "c4s": (64, 1024, 1024, 13, 0, 0x80, "configs[3] slice: 64 frames of a 1024x1024 video stack (presented as z, Appendix F.5), Nnum=13, way tiles, video bit + 2-D entropy selection, 96x96x8 blocks"),
+    "c5s": (16, 4096, 4096, 13, 0, 0, "configs[4] slice: 4096x4096x16 uint16 stack, Nnum=13, way tiles, 2-D entropy selection, 96x96x8 blocks (full decode)"),
 }
 POOL = 24
 # DRAM bytes of ONE k_bwt launch measured by ncu --set full (read + write), per workload (profiles/)

@@ -10,6 +10,7 @@
 //     of interior tiles), which makes every image column one long chain. Rows then only depend on earlier rows, plus
 //     short left-to-right chains inside the first tile column / the first image row, which one thread walks.
 #include <algorithm>
+#include <cstdlib>
 #include <cooperative_groups.h>
 #include "lfm_device.cuh"
 #include "lfm_predict.cuh"
@@ -667,6 +668,133 @@ static void launch_tiles_angle(const uint16_t* sym, uint16_t* out, int W, int H,
 	k_unpredict_tiles_angle<K><<<(unsigned)((uint64_t)count * tilesY * chunks), UT_NT, smem, st>>>(sym, out, W, H, T, z_start, z_step, tilesX, tilesY, chunks);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Universal shared-memory inverse (any way, predictor, video): one CTA per FRAME walks the frame block by block --
+// a block = one tile row x up to 64 tiles -- in raster order.  Everything a block needs from earlier blocks (T+1 decoded
+// rows above, T+1 decoded columns to the left, the previous frame for odd video frames) is re-read from the output in
+// global memory (written by this CTA, or by the previous launch), so only the block and its halo live in shared memory.
+// Inside a block the pixels are decoded along the wavefront  w = (tile index) + u + v  -- every operand of the rule
+// function lies in an earlier block or has a smaller w -- with one CTA barrier per step.  Thread = (anti-diagonal r of a
+// tile, position on it): at step w it decodes tile w - r.  Frames are independent CTAs: this is the throughput path for
+// stacks and videos (hundreds of frames); a single frame is better served by the cluster kernel above.
+constexpr int US_TILES = 64;             // tiles per block
+
+template <int WAY, int K>
+__global__ void __launch_bounds__(1024)
+k_unpredict_strips(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T, int video,
+                   uint32_t z_start, uint32_t z_step, int hw, int pitch)
+{
+	extern __shared__ __align__(16) uint8_t us_smem[];
+	uint16_t* cur = reinterpret_cast<uint16_t*>(us_smem);                 // [T][pitch]      symbols -> pixels, column hw = block column 0
+	uint16_t* prv = cur + (size_t)T * pitch;                               // [T + 1][pitch]  decoded rows y0-T-1 .. y0-1
+	uint16_t* pfr = prv + (size_t)(T + 1) * pitch;                         // [T][pitch]      previous frame (odd video frames only)
+	const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+	const uint64_t fpx = (uint64_t)W * H;
+	const uint32_t z = z_start + blockIdx.x * z_step;
+	const uint16_t* s = sym + (uint64_t)z * fpx;
+	uint16_t* o = out + (uint64_t)z * fpx;
+	const bool zflag = (video & (int)z & 1) != 0;
+	const int tilesX = (W + T - 1) / T, tilesY = (H + T - 1) / T;
+	const int halo = T + 1;
+	const int ncand = (2 * T - 1) * T;                                     // (anti-diagonal, position) pairs of a tile
+	const int dr = nt / T, dl = nt - dr * T;                               // stride of the candidate loop in (r, l) form
+
+	for (int ty = 0; ty < tilesY; ty++) {
+		const int y0 = ty * T, th = min(T, H - y0);
+		for (int tb0 = 0; tb0 < tilesX; tb0 += US_TILES) {
+			const int ntb = min(US_TILES, tilesX - tb0);
+			const int x0 = tb0 * T, cw = min(W - x0, ntb * T);             // block columns [x0, x0 + cw)
+			const int xl = max(0, x0 - halo);                              // first halo column
+			// ---- stage: symbols of the block, decoded halo (rows above incl. their left halo, columns to the left), previous frame
+			if (((W & 7) == 0) && (((((uintptr_t)sym | (uintptr_t)out)) & 15) == 0)) {
+				// rows are whole 16-byte vectors and block / halo starts are multiples of 8 pixels: asynchronous 16-byte copies,
+				// everything in flight at once (.cg: served by L2, so this CTA's earlier stores are seen)
+				auto copy_rows = [&](uint16_t* dst_row0, const uint16_t* src_row0, int rows, int xa, int xb) {   // columns [xa, xb) of `rows` rows
+					const int nv = (xb - xa) >> 3;
+					for (int i = tid; i < rows * nv; i += nt) {
+						const int r = i / nv, cv = i - r * nv;
+						const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_row0 + (size_t)r * pitch + hw + (xa - x0) + cv * 8);
+						asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(src_row0 + (size_t)r * W + xa + cv * 8) : "memory");
+					}
+				};
+				const int xh = max(0, x0 - hw);
+				const int ya = max(0, y0 - halo);
+				copy_rows(cur, s + (size_t)y0 * W, th, x0, x0 + cw);
+				copy_rows(prv + (size_t)(ya - (y0 - halo)) * pitch, o + (size_t)ya * W, y0 - ya, xh, x0 + cw);
+				copy_rows(cur, o + (size_t)y0 * W, th, xh, x0);
+				if (zflag) copy_rows(pfr, o + (size_t)y0 * W - fpx, th, x0, x0 + cw);
+				asm volatile("cp.async.commit_group;" ::: "memory");
+				asm volatile("cp.async.wait_group 0;" ::: "memory");
+			} else {
+				for (int i = tid; i < th * cw; i += nt) { const int r = i / cw, c = i - r * cw; cur[r * pitch + hw + c] = __ldg(s + (size_t)(y0 + r) * W + x0 + c); }
+				const int hwid = x0 + cw - xl;                             // halo rows span [xl, x0 + cw)
+				const int ya = max(0, y0 - halo);
+				for (int i = tid; i < (y0 - ya) * hwid; i += nt) {
+					const int r = i / hwid, c = i - r * hwid;
+					prv[(ya + r - (y0 - halo)) * pitch + hw + (xl + c - x0)] = __ldcg(o + (size_t)(ya + r) * W + xl + c);
+				}
+				const int lw = x0 - xl;
+				for (int i = tid; i < th * lw; i += nt) { const int r = i / lw, c = i - r * lw; cur[r * pitch + hw + (xl + c - x0)] = __ldcg(o + (size_t)(y0 + r) * W + xl + c); }
+				if (zflag) for (int i = tid; i < th * cw; i += nt) { const int r = i / cw, c = i - r * cw; pfr[r * pitch + hw + c] = __ldcg(o + (size_t)(y0 + r) * W + x0 + c - fpx); }
+			}
+			__syncthreads();
+			// ---- wavefront over the block
+			const int nsteps = ntb + 2 * T - 2;
+			for (int w = 0; w < nsteps; w++) {
+				int r = tid / T, l = tid - r * T;
+				for (int i = tid; i < ncand; i += nt) {
+					const int tb = w - r;
+					const int u = max(0, r - (T - 1)) + l, v = r - u;
+					if (tb >= 0 && tb < ntb && v >= 0 && u < T) {
+						const int tx = tb0 + tb, xb = tb * T + u;          // xb: column inside the block
+						if (x0 + xb < W && v < th) {
+							uint16_t* c = cur + v * pitch + hw + xb;
+							auto px = [&](int dx, int dy) -> int {
+								const int yy = v + dy;
+								return (int)(yy >= 0 ? c[dy * pitch + dx] : prv[(yy + halo) * pitch + hw + xb + dx]);
+							};
+							int p = predict0(px, T, WAY, K, tx, ty, u, v);
+							if (zflag) { const int P = (int)pfr[v * pitch + hw + xb]; p = (x0 + xb == 0 && y0 + v == 0) ? P : ((p + P) >> 1); }
+							*c = (uint16_t)(unsymbolize16(*c) + p);
+						}
+					}
+					r += dr; l += dl; if (l >= T) { l -= T; r++; }
+				}
+				__syncthreads();
+			}
+			// ---- write the decoded block
+			if (((W & 7) == 0) && ((((uintptr_t)out) & 15) == 0)) {
+				const int nv = cw >> 3;
+				for (int i = tid; i < th * nv; i += nt) {
+					const int r = i / nv, cv = i - r * nv;
+					*reinterpret_cast<uint4*>(o + (size_t)(y0 + r) * W + x0 + cv * 8) = *reinterpret_cast<const uint4*>(cur + (size_t)r * pitch + hw + cv * 8);
+				}
+			} else {
+				for (int i = tid; i < th * cw; i += nt) { const int r = i / cw, c = i - r * cw; o[(size_t)(y0 + r) * W + x0 + c] = cur[r * pitch + hw + c]; }
+			}
+			__syncthreads();
+		}
+	}
+}
+
+template <int WAY>
+static int launch_unpredict_strips(const uint16_t* sym, uint16_t* out, int W, int H, int T, int k, int video,
+                                   uint32_t z_start, uint32_t z_step, uint32_t count, cudaStream_t st)
+{
+	const int hw = (T + 1 + 7) & ~7, pitch = hw + ((US_TILES * T + 7) & ~7);
+	const size_t smem = (size_t)(3 * T + 1) * pitch * 2;
+	if (smem > (size_t)UG_MAX_SMEM) return 2;                   // Nnum too large for this path
+	const unsigned nt = (unsigned)std::min(1024, ((2 * T - 1) * T + 31) & ~31);
+	#define LFM_US(KK) do { cudaFuncSetAttribute(k_unpredict_strips<WAY, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+		k_unpredict_strips<WAY, KK><<<count, nt, smem, st>>>(sym, out, W, H, T, video, z_start, z_step, hw, pitch); } while (0)
+	switch (k) {
+	case 1: LFM_US(1); break; case 2: LFM_US(2); break; case 3: LFM_US(3); break; case 4: LFM_US(4); break;
+	case 5: LFM_US(5); break; case 6: LFM_US(6); break; default: LFM_US(7); break;
+	}
+	#undef LFM_US
+	return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 template <int WAY, int K>
 static void launch_predict_fwd_wk(const uint16_t* img, uint16_t* sym, int W, int H, int T, int video, uint32_t z0, uint32_t nz,
                                   cudaStream_t st)
@@ -763,6 +891,15 @@ int launch_unpredict(const uint16_t* sym, uint16_t* out, int W, int H, int T, in
 		const uint64_t warps = (uint64_t)count * tilesX * tilesY;
 		k_unpredict_angle<<<(unsigned)((warps + wpb - 1) / wpb), UF_NT, 0, st>>>(sym, out, W, H, T, k, z_start, z_step, count);
 		return cudaGetLastError() == cudaSuccess ? 0 : 1;
+	}
+	// remaining cases (way tiles, video, predictor 2 of tiles/angle): many frames -> one CTA per frame in shared memory;
+	// few frames -> the cluster wavefront below (all SMs on one frame)
+	static const int strips_min = getenv("LFM_B200_STRIPS_MIN") ? atoi(getenv("LFM_B200_STRIPS_MIN")) : 128;
+	if ((int)count >= strips_min) {
+		const int rcs = way == 0 ? launch_unpredict_strips<0>(sym, out, W, H, T, k, video, z_start, z_step, count, st)
+		              : way == 1 ? launch_unpredict_strips<1>(sym, out, W, H, T, k, video, z_start, z_step, count, st)
+		                         : launch_unpredict_strips<2>(sym, out, W, H, T, k, video, z_start, z_step, count, st);
+		if (rcs != 2) return rcs;
 	}
 	const uint64_t steps = (k == 2 && way != 2) ? (uint64_t)H : (uint64_t)(tilesX + tilesY + 2 * T);
 	const uint64_t per_step = ((uint64_t)W * H + steps - 1) / steps;              // mean ready pixels per step and frame

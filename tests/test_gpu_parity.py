@@ -17,6 +17,7 @@ G = json.load(open(os.path.join(GOLDEN, "golden.json")))
 @pytest.fixture(scope="module")
 def L():
     os.environ["LFM_B200_DEBUG_POISON"] = "1"      # poison decode buffers so ordering bugs cannot hide behind stale data
+    os.environ["LFM_B200_STRIPS_MIN"] = "8"        # stacks of >= 8 frames take the one-CTA-per-frame inverse, smaller ones the cluster kernel
     import lfm_b200
     import torch
     assert torch.cuda.is_available(), "gpu tests need a CUDA device"
@@ -121,7 +122,8 @@ def test_vector_width_frames_all_predictors(L, oracle, tmp_path, way):
     """row length a multiple of 8 pixels (the two-pixels-per-thread forward kernel and the vectorised inverse strips):
     every predictor of every way, file bytes == oracle file bytes, exact round trip"""
     rng = np.random.default_rng(5 + way)
-    a = (lf_synth((2, 120, 272), 13, seed=9).astype(np.int64) + rng.integers(0, 300, (2, 120, 272))).astype(np.uint16)
+    nz = 18 if way == 0 else 2          # way tiles: enough frames for the one-CTA-per-frame inverse, video halves included
+    a = (lf_synth((nz, 120, 272), 13, seed=9).astype(np.int64) + rng.integers(0, 300, (nz, 120, 272))).astype(np.uint16)
     for k in range(1, 8):
         for hv in (8 + k,) + ((0x88 + k,) if way == 0 else ()):
             fo, fg = str(tmp_path / "o.lfm"), str(tmp_path / "g.lfm")
