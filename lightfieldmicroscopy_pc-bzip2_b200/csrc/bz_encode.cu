@@ -25,7 +25,7 @@ namespace lfm {
 //   D. CRC-32: per-chunk table CRC, combined in a binary tree with carry-less multiplications by x^(8 len) mod P.
 // (bzlib.c:216-354 ADD_CHAR_TO_BLOCK / add_pair_to_block / flush_RL; bzlib_private.h:157-171)
 // =====================================================================================================
-constexpr int RLE_NT = 256;
+constexpr int RLE_NT = 256;                 // small blocks; blocks above 48 KB run with 1024 threads (one CTA per SM: occupancy)
 constexpr uint32_t kCrcPoly = 0x04C11DB7u;
 
 __device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b)      // a * b in GF(2)[x] / P, bit k <-> x^k
@@ -55,18 +55,19 @@ __device__ __forceinline__ uint32_t rle_g(uint32_t x)                        // 
 
 extern __shared__ __align__(16) uint8_t rle_smem[];
 
-__global__ void __launch_bounds__(RLE_NT)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t njobs,
        uint8_t* __restrict__ txt_all, uint8_t* __restrict__ raw_all /* = BWT slots, free at this point */, uint32_t cap,
        EncJob* __restrict__ jobs, int stage_in_smem)
 {
 	__shared__ uint32_t crc_tab[256];
 	__shared__ uint32_t red[64];
-	__shared__ uint32_t s_a[RLE_NT], s_b[RLE_NT];
+	__shared__ uint32_t s_a[NT], s_b[NT];
 	const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
 	const uint32_t job = blockIdx.x;
 	if (job >= njobs) return;
-	crc_tab[tid] = crc_table_entry(tid);
+	if (tid < 256) crc_tab[tid] = crc_table_entry(tid);
 
 	uint32_t c0[5], ext[5];
 	block_box(g, first_block + job, c0, ext);
@@ -76,7 +77,7 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 	uint8_t* stage = stage_in_smem ? rle_smem : raw_all + (size_t)job * cap;
 
 	// ---- A. gather (one row per warp at a time)
-	for (uint32_t r = wid; r < rows; r += RLE_NT / 32) {
+	for (uint32_t r = wid; r < rows; r += NT / 32) {
 		uint32_t y = r % ext[1], q = r / ext[1];
 		uint32_t z = q % ext[2]; q /= ext[2];
 		uint32_t c = q % ext[3], t = q / ext[3];
@@ -89,9 +90,9 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 	const uint8_t* b = stage;
 
 	// ---- B. chunks (right aligned) and run boundaries
-	uint32_t CH = ((gcount + RLE_NT - 1) / RLE_NT + 3) & ~3u;              // whole words, and an odd number of them:
+	uint32_t CH = ((gcount + NT - 1) / NT + 3) & ~3u;              // whole words, and an odd number of them:
 	if (((CH >> 2) & 1u) == 0) CH += 4;                                 // threads then hit distinct shared-memory banks
-	const uint32_t after = (RLE_NT - 1 - tid) * CH;                     // bytes owned by later threads
+	const uint32_t after = (NT - 1 - tid) * CH;                     // bytes owned by later threads
 	const uint32_t e1 = gcount > after ? gcount - after : 0;
 	const uint32_t e0 = e1 > CH ? e1 - CH : 0;
 	const uint32_t NONE = 0xFFFFFFFFu;
@@ -100,14 +101,21 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 		if (i == 0 || b[i] != b[i - 1]) { if (first_head == NONE) first_head = i; last_head = i; }
 	}
 	// start of the run that is open at my chunk start = last head before e0 (max-scan; heads ascend with the thread)
-	const uint32_t incl = block_scan_max<RLE_NT>(last_head == NONE ? 0u : last_head + 1u, red);     // +1 so that 0 = none
+	const uint32_t incl = block_scan_max<NT>(last_head == NONE ? 0u : last_head + 1u, red);     // +1 so that 0 = none
 	uint32_t prev_incl = __shfl_up_sync(0xffffffffu, incl, 1);
 	if (lane == 0) prev_incl = wid ? red[wid - 1] : 0;
 	const uint32_t open_start = prev_incl ? prev_incl - 1u : 0u;
 	// first head after my chunk (gcount if none): reverse min-scan done through shared memory
 	s_a[tid] = first_head;
 	__syncthreads();
-	if (tid == 0) { uint32_t nh = gcount; for (int t = RLE_NT - 1; t >= 0; t--) { uint32_t f = s_a[t]; s_b[t] = nh; if (f != NONE) nh = f; } }
+	{
+		// thread r looks at chunk NT-1-r: an inclusive max-scan of ~first_head over r is a suffix min-scan over the chunks
+		const uint32_t rv = s_a[NT - 1 - tid];
+		const uint32_t rincl = block_scan_max<NT>(~rv, red);                           // NONE -> 0
+		uint32_t rprev = __shfl_up_sync(0xffffffffu, rincl, 1);
+		if (lane == 0) rprev = wid ? red[wid - 1] : 0;
+		s_b[NT - 1 - tid] = rprev ? ~rprev : gcount;                                      // heads strictly after the chunk
+	}
 	__syncthreads();
 	const uint32_t next_head = s_b[tid];
 
@@ -123,7 +131,7 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 			i = e;
 		}
 	}
-	uint32_t total; const uint32_t incs = block_scan_add<RLE_NT>(outc, red, &total);
+	uint32_t total; const uint32_t incs = block_scan_add<NT>(outc, red, &total);
 	const uint32_t n = total;
 	uint32_t crc = 0;
 	{
@@ -156,7 +164,7 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 	__syncthreads();
 	{
 		uint32_t M = crc_xpow8(CH);                                     // x^(8 CH): shift by one full chunk
-		for (uint32_t stride = 1; stride < RLE_NT; stride <<= 1) {
+		for (uint32_t stride = 1; stride < NT; stride <<= 1) {
 			if ((tid & (2 * stride - 1)) == 0) s_a[tid] = crc_mulmod(s_a[tid], M) ^ s_a[tid + stride];
 			M = crc_mulmod(M, M);
 			__syncthreads();
@@ -883,8 +891,13 @@ void launch_rle1(const uint16_t* sym, const Geom& g, uint64_t first_block, uint3
 {
 	const int in_smem = max_raw_bytes + 16 <= 200 * 1024;
 	const size_t smem = in_smem ? (size_t)max_raw_bytes + 16 : 0;
-	cudaFuncSetAttribute(k_rle1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	k_rle1<<<njobs, RLE_NT, smem, st>>>(sym, g, first_block, njobs, txt, raw_scratch, cap, jobs, in_smem);
+	if (max_raw_bytes > 48 * 1024) {
+		cudaFuncSetAttribute(k_rle1<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		k_rle1<1024><<<njobs, 1024, smem, st>>>(sym, g, first_block, njobs, txt, raw_scratch, cap, jobs, in_smem);
+	} else {
+		cudaFuncSetAttribute(k_rle1<RLE_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		k_rle1<RLE_NT><<<njobs, RLE_NT, smem, st>>>(sym, g, first_block, njobs, txt, raw_scratch, cap, jobs, in_smem);
+	}
 }
 void launch_mtf(const uint8_t* bwt, uint8_t* rank_scratch, uint32_t cap, EncJob* jobs, uint32_t njobs, uint16_t* mtfv, uint32_t mcap, cudaStream_t st)
 {
