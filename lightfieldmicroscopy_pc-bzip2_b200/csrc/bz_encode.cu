@@ -59,7 +59,7 @@ template <int NT>
 __global__ void __launch_bounds__(NT)
 k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t njobs,
        uint8_t* __restrict__ txt_all, uint8_t* __restrict__ raw_all /* = BWT slots, free at this point */, uint32_t cap,
-       EncJob* __restrict__ jobs, int stage_in_smem)
+       EncJob* __restrict__ jobs, int stage_in_smem, uint32_t nblock_max)
 {
 	__shared__ uint32_t crc_tab[256];
 	__shared__ uint32_t red[64];
@@ -179,7 +179,9 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 	}
 	if (tid == 0) {
 		EncJob& J = jobs[job];
-		J.raw_bytes = gcount; J.n = n; J.crc = ~s_a[0]; J.status = 0; J.periodic = 0; J.orig_ptr = 0;
+		// more bytes than one bzip2 block holds (bzlib.c:  nblockMAX = 100000 * level - 19): would be a multi-block stream
+		const bool too_big = n > nblock_max;
+		J.raw_bytes = gcount; J.n = too_big ? 0u : n; J.crc = ~s_a[0]; J.status = too_big ? 4u : 0u; J.periodic = 0; J.orig_ptr = 0;
 		// the inUse map (bzlib.c:226, :243-258) is exactly "byte values with a non-zero count in the block": k_bwt derives
 		// it from the byte histogram it needs anyway
 		for (int k = 0; k < 8; k++) J.in_use[k] = 0;
@@ -887,16 +889,16 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 
 // ------------------------------------------------------------------------------------------------ launchers
 void launch_rle1(const uint16_t* sym, const Geom& g, uint64_t first_block, uint32_t njobs, uint8_t* txt, uint8_t* raw_scratch,
-                 uint32_t cap, uint32_t max_raw_bytes, EncJob* jobs, cudaStream_t st)
+                 uint32_t cap, uint32_t max_raw_bytes, uint32_t nblock_max, EncJob* jobs, cudaStream_t st)
 {
 	const int in_smem = max_raw_bytes + 16 <= 200 * 1024;
 	const size_t smem = in_smem ? (size_t)max_raw_bytes + 16 : 0;
 	if (max_raw_bytes > 48 * 1024) {
 		cudaFuncSetAttribute(k_rle1<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		k_rle1<1024><<<njobs, 1024, smem, st>>>(sym, g, first_block, njobs, txt, raw_scratch, cap, jobs, in_smem);
+		k_rle1<1024><<<njobs, 1024, smem, st>>>(sym, g, first_block, njobs, txt, raw_scratch, cap, jobs, in_smem, nblock_max);
 	} else {
 		cudaFuncSetAttribute(k_rle1<RLE_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		k_rle1<RLE_NT><<<njobs, RLE_NT, smem, st>>>(sym, g, first_block, njobs, txt, raw_scratch, cap, jobs, in_smem);
+		k_rle1<RLE_NT><<<njobs, RLE_NT, smem, st>>>(sym, g, first_block, njobs, txt, raw_scratch, cap, jobs, in_smem, nblock_max);
 	}
 }
 void launch_mtf(const uint8_t* bwt, uint8_t* rank_scratch, uint32_t cap, EncJob* jobs, uint32_t njobs, uint16_t* mtfv, uint32_t mcap, cudaStream_t st)

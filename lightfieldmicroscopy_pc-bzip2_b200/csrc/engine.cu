@@ -92,6 +92,12 @@ Engine::Engine(int device) : device_(device)
 	for (int i = 0; i < 4; i++) { cudaEvent_t e; cudaEventCreate(&e); ev_[i] = e; }
 }
 
+void* Engine::pooled_event(size_t i)
+{
+	while (ev_pool_.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ev_pool_.push_back(e); }
+	return ev_pool_[i];
+}
+
 static double elapsed_or_zero(void* a, void* b)
 {
 	float ms = 0.f;
@@ -252,10 +258,8 @@ int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t 
 	cudaStream_t st = (cudaStream_t)stream_;
 	const Geom g = make_geom(s);
 	const EncSizes z = enc_sizes(s);
-	if (!z.single_block_ok) {
-		err_ = "block size needs multi-block bzip2 streams (not implemented): keep blockBytes*1.25 < 100000*level-19";
-		return LFM_ERR_UNSUPPORTED;
-	}
+	// a KLB block whose run-length coded size exceeds one bzip2 block (100000*level - 19 bytes) would need a multi-block
+	// stream: detected per block at run time by k_rle1 (status 4) -- with the default block sizes it cannot happen
 	if (count == 0) { *d_payload = nullptr; *payload_bytes = 0; return LFM_OK; }
 	const size_t per_job = (size_t)z.cap * 3 + (size_t)z.mcap * 2 + z.selcap + z.ocap + sizeof(EncJob);
 	uint64_t B = std::min<uint64_t>(count, std::max<uint64_t>(1, ((size_t)6 << 30) / per_job));
@@ -279,12 +283,12 @@ int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t 
 	cudaMemsetAsync(tot, 0, sizeof(Totals), st);
 
 	std::vector<cudaEvent_t> evs;
-	auto mark = [&]() { if (stt) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); evs.push_back(e); } };
+	auto mark = [&]() { if (stt) { cudaEvent_t e = (cudaEvent_t)pooled_event(evs.size()); cudaEventRecord(e, st); evs.push_back(e); } };
 	uint64_t launches = 0;
 	for (uint64_t b0 = 0; b0 < count; b0 += B) {
 		const uint32_t nj = (uint32_t)std::min<uint64_t>(B, count - b0);
 		mark();
-		launch_rle1(d_sym, g, first + b0, nj, (uint8_t*)txt_.p, (uint8_t*)bwt_.p, z.cap, (uint32_t)blockBytes, (EncJob*)jobs_.p, st);
+		launch_rle1(d_sym, g, first + b0, nj, (uint8_t*)txt_.p, (uint8_t*)bwt_.p, z.cap, (uint32_t)blockBytes, (uint32_t)(100000 * z.level - 19), (EncJob*)jobs_.p, st);
 		mark();
 		launch_bwt((uint8_t*)txt_.p, z.cap, (EncJob*)jobs_.p, nj, (uint8_t*)bwt_.p, (uint32_t*)scratch_.p,
 		           (int)std::min<uint32_t>(nj, (uint32_t)grid), z.text_in_smem, st);
@@ -312,11 +316,11 @@ int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t 
 			cudaEventElapsedTime(&ms, evs[i + 2], evs[i + 3]); stt->ms_mtf += ms;
 			cudaEventElapsedTime(&ms, evs[i + 3], evs[i + 4]); stt->ms_huff += ms;
 		}
-		for (auto e : evs) cudaEventDestroy(e);
 		stt->launches += launches;
 		stt->periodic_blocks += h.periodic;
 	}
 	if (h.overflow) { err_ = "payload buffer overflow"; return LFM_ERR_BZIP; }
+	if (h.err & 4u) { err_ = "a KLB block does not fit one bzip2 block after run-length coding (multi-block streams are not implemented)"; return LFM_ERR_UNSUPPORTED; }
 	if (h.err) { err_ = "block encoder reported an error"; return LFM_ERR_BZIP; }
 	*d_payload = (const uint8_t*)payload_.p;
 	*payload_bytes = h.running;
@@ -347,7 +351,6 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 	if (count == 0) return LFM_OK;
 	const Geom g = make_geom(s);
 	const EncSizes z = enc_sizes(s);
-	if (!z.single_block_ok) { err_ = "block size needs multi-block bzip2 streams (not implemented)"; return LFM_ERR_UNSUPPORTED; }
 	uint64_t blockBytes = 2; for (int i = 0; i < 5; i++) blockBytes *= s.blockSize[i];
 	const size_t per_job = (size_t)z.cap * 2 + (size_t)z.mcap * 2 + sizeof(DecJob) + 24;
 	uint64_t B = std::min<uint64_t>(count, std::max<uint64_t>(1, ((size_t)6 << 30) / per_job));
@@ -368,7 +371,7 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 	cudaMemcpyAsync(dend_.p, end, count * 8, cudaMemcpyHostToDevice, st);
 	cudaMemcpyAsync(dids_.p, block_ids, count * 8, cudaMemcpyHostToDevice, st);
 	std::vector<cudaEvent_t> evs;
-	auto mark = [&]() { if (stt) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); evs.push_back(e); } };
+	auto mark = [&]() { if (stt) { cudaEvent_t e = (cudaEvent_t)pooled_event(evs.size()); cudaEventRecord(e, st); evs.push_back(e); } };
 	uint64_t launches = 0;
 	for (uint64_t b0 = 0; b0 < count; b0 += B) {
 		const uint32_t nj = (uint32_t)std::min<uint64_t>(B, count - b0);
@@ -395,7 +398,6 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 			cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]); stt->ms_ibwt += ms;
 			cudaEventElapsedTime(&ms, evs[i + 2], evs[i + 3]); stt->ms_unrle += ms;
 		}
-		for (auto e : evs) cudaEventDestroy(e);
 		stt->launches += launches;
 	}
 	if (hflag) {

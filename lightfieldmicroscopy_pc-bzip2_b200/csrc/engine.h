@@ -106,6 +106,8 @@ private:
 	uint32_t last_cap_ = 0, last_mcap_ = 0, last_njobs_ = 0;
 	void* pin_ = nullptr; size_t pin_cap_ = 0;
 	void* ev_[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	std::vector<void*> ev_pool_;     // stage-timing events, created once and reused (event creation costs host time per call)
+	void* pooled_event(size_t i);
 };
 
 }  // namespace lfm

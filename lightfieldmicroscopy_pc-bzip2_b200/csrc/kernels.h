@@ -14,7 +14,7 @@ void launch_select(const uint16_t* const cand_ptrs[8], int ncand, uint64_t fpx, 
                    uint8_t* sorted, uint32_t sstride, uint32_t* hist, float* e_out, cudaStream_t st);
 // bz_encode.cu
 void launch_rle1(const uint16_t* sym, const Geom& g, uint64_t first_block, uint32_t njobs, uint8_t* txt, uint8_t* raw_scratch,
-                 uint32_t cap, uint32_t max_raw_bytes, EncJob* jobs, cudaStream_t st);
+                 uint32_t cap, uint32_t max_raw_bytes, uint32_t nblock_max, EncJob* jobs, cudaStream_t st);
 void launch_mtf(const uint8_t* bwt, uint8_t* rank_scratch, uint32_t cap, EncJob* jobs, uint32_t njobs, uint16_t* mtfv, uint32_t mcap, cudaStream_t st);
 void launch_huff_pack(const uint16_t* mtfv, uint32_t mcap, EncJob* jobs, uint32_t njobs, uint8_t* sel, uint32_t selcap,
                       uint8_t* out, uint32_t ocap, int level, cudaStream_t st);

@@ -134,6 +134,24 @@ def test_vector_width_frames_all_predictors(L, oracle, tmp_path, way):
             assert np.array_equal(L.read_stack(fg, way=way), a)
 
 
+def test_large_klb_blocks_single_bzip2_block(L, oracle, tmp_path):
+    """128x128x6 KLB blocks (196608 bytes, bzip2 level 2: one of the block shapes timed in docs/CompressionComparison.xlsx):
+    the text no longer fits shared memory in the block sort, and a block only fits ONE bzip2 block when its run-length
+    coded size stays below 100000*level-19 -- checked per block at run time"""
+    a = lf_synth((6, 256, 256), 13, seed=21)
+    fo, fg = str(tmp_path / "o.lfm"), str(tmp_path / "g.lfm")
+    rc, shv = oracle.write(a, fo, 8 + 4, 13, 0, block_size=(128, 128, 6, 1, 1))
+    assert rc == 0
+    L.write_stack(a, fg, header_version=8 + 4, nnum=13, block_size=(128, 128, 6, 1, 1), way=0)
+    assert open(fo, "rb").read() == open(fg, "rb").read()
+    assert np.array_equal(L.read_stack(fg, way=0), a)
+    # runs of exactly four equal bytes grow by 25 % under bzip2's first run-length stage: 245760 > 199981 -> refused with code 7
+    b = np.repeat(np.arange(6 * 256 * 256 // 2, dtype=np.uint32) % 251 * 257, 2).astype(np.uint16).reshape(6, 256, 256)
+    with pytest.raises(L.LfmError) as ei:
+        L.write_stack(b, fg, header_version=8, nnum=13, block_size=(128, 128, 6, 1, 1), way=0)
+    assert ei.value.code == 7
+
+
 def test_c_abi_entry_points(L, tmp_path):
     """the six reference entry points: write, header, full read (malloc'd + in place), ROI read"""
     import ctypes as C
