@@ -795,6 +795,253 @@ static int launch_unpredict_strips(const uint16_t* sym, uint16_t* out, int W, in
 	return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Band-pipelined inverse (way "tiles" incl. video; any way whose rule only looks at the operands listed below; not
+// predictor 2 of the ways tiles / angle, whose U crosses the tile border).
+//
+// A CTA owns a BAND of R tile rows of one frame; thread (j, u, v) owns in-tile position (u, v) of band row j and walks
+// along its tile row: at wavefront step w it decodes tile  tx = w - (u + v + j + 1).  Every operand of the rule function
+// is then the output of a thread of the same CTA one or two steps earlier:
+//     (-1,0) (0,-1) (-T,0) (0,-T)                          step w-1     (left, up, same pixel of the left / upper tile)
+//     (-1,-1) (-T,-T) (-1,-T) (0,-T-1) (-T,-1) (-T-1,0)    step w-2
+// so the chain runs through a 4-deep shared-memory ring of "what every thread produced at step s" with ONE named
+// barrier per step and all R*T*T threads busy in the steady state -- no fill / drain per block of tiles.  The row above
+// the band (last tile row of the previous band, decoded by ANOTHER CTA) enters the ring as virtual row 0, fed by the
+// threads of band row 0 from global memory.  Residual symbols, the row above and (video) the previous frame are
+// prefetched UB_D steps ahead into registers, so no global latency sits on the chain; decoded pixels are stored as they
+// are produced.
+// Bands of a frame form a software pipeline through global progress flags (number of wavefront steps the band has
+// completed: the band below may run R + UB_D + 1 steps behind, it never waits for whole tiles).  Three helper warps keep
+// every fence off the compute threads:
+//   signal    joins each step's barrier and releases the step count to the CTA (the barrier orders the pixel stores
+//             of the compute threads before that release);
+//   publisher free running: acquires the step count, gpu-scope fence, stores the progress flag -- the fence costs
+//             microseconds while stores are in flight, and nobody inside the CTA waits for it;
+//   poller    reads the flag of the band above, fences, and passes the count on through shared memory, where the threads
+//             of band row 0 look before they prefetch from the row above (ld.global.cg, issued after the value was
+//             seen: L2 already holds the data).
+// The compute threads never execute a fence, so their register prefetch queues stay in flight across steps.  CTAs are
+// numbered band-major (all frames' band b before any band b+1): a CTA only waits for a CTA with a smaller index, and
+// the bands in flight belong to as many different frames as possible.
+constexpr int UB_D = 4;                 // prefetch distance, wavefront steps
+constexpr int UB_HELPERS = 96;          // three helper warps: signal, publisher, poller (one lane each is active)
+
+__device__ __forceinline__ uint32_t ub_ld_acquire_cta(const uint32_t* p)
+{
+	uint32_t v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory"); return v;
+}
+__device__ __forceinline__ void ub_st_release_cta(uint32_t* p, uint32_t v)
+{
+	asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ub_ld_relaxed_gpu(const uint32_t* p)
+{
+	uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void ub_st_relaxed_gpu(uint32_t* p, uint32_t v)
+{
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void ub_fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+template <int WAY, int K, int ZF>
+__global__ void __launch_bounds__(1024, 1)   // at most 64 registers: two CTAs of <= 512 threads (or four of 256) share an SM
+k_unpredict_bands(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T,
+                  uint32_t z_start, uint32_t z_step, uint32_t count, int R, int ncomp, uint32_t* flags)
+{
+	extern __shared__ __align__(16) uint8_t ub_smem[];
+	__shared__ uint32_t s_avail, s_step;
+	__builtin_assume(T >= 2);
+	const int tid = (int)threadIdx.x;
+	const int TT = T * T;
+	const int tilesX = (W + T - 1) / T, tilesY = (H + T - 1) / T;
+	const int nbands = (tilesY + R - 1) / R;
+	const uint32_t fi = blockIdx.x % count;
+	const int band = (int)(blockIdx.x / count);
+	const uint32_t z = z_start + fi * z_step;
+	const uint64_t fpx = (uint64_t)W * H;
+	const int last_skew = 2 * T - 2 + R;                         // u + v + j + 1 of the band's last thread
+	const int nsteps = tilesX + last_skew;
+	uint32_t* f_mine = flags + (size_t)fi * nbands + band;
+	const uint32_t* f_above = f_mine - 1;
+	if (tid == 0) s_step = 0;
+	if (tid == 0) s_avail = band == 0 ? 0x7fffffffu : 0u;     // wavefront steps the band above has completed
+	const int RS = (R + 1) * TT + T + 2;                        // ring row: T+2 guard elements, virtual row 0, R band rows
+	uint16_t* ring = reinterpret_cast<uint16_t*>(ub_smem);
+	for (int i = tid; i < 4 * RS; i += (int)blockDim.x) ring[i] = 0;
+	__syncthreads();
+
+	const int nsteps_run = (nsteps + UB_D - 1) / UB_D * UB_D;    // the step loop is unrolled by UB_D
+	if (tid >= ncomp) {
+		// ---- helper warps: all global synchronisation
+		if (tid < ncomp + 32) {
+			// signal warp: joins EVERY compute barrier (it has no memory operations of its own in flight, so it never delays
+			// one) and releases the count of complete steps to the CTA -- the barrier orders the compute threads' pixel
+			// stores before this release
+			for (int w = 0; w <= nsteps_run; w++) {
+				asm volatile("bar.sync 1, %0;" :: "r"(ncomp + 32) : "memory");      // steps < w are complete
+				if (tid == ncomp) ub_st_release_cta(&s_step, w >= nsteps_run ? 0x7fffffffu : (uint32_t)w);
+			}
+		} else if (tid == ncomp + 32) {
+			// publisher lane, free running: acquire the step count, gpu-scope fence, store the progress flag.  The fence takes
+			// microseconds under load; nothing waits for it except the band below.
+			uint32_t published = 0;
+			while (published < 0x7fffffffu) {
+				const uint32_t sd = ub_ld_acquire_cta(&s_step);
+				if (sd > published) { ub_fence_gpu(); ub_st_relaxed_gpu(f_mine, sd); published = sd; }
+			}
+		} else if (tid == ncomp + 64 && band > 0) {             // poller of the band above
+			uint32_t avail = 0;
+			while (avail < 0x7fffffffu) {
+				const uint32_t f = ub_ld_relaxed_gpu(f_above);
+				if (f > avail) { ub_fence_gpu(); avail = f; *(volatile uint32_t*)&s_avail = f; }
+			}
+		}
+		return;
+	}
+
+	// ---- compute threads
+	// thread -> (band row j, u, v), ordered by rule class so that (almost) every warp runs ONE branch of the rule function:
+	// first the general pixels (u > 0, v > 0) of all band rows, then the first columns (u == 0), the first rows (v == 0), the DCs
+	int j, u, v;
+	{
+		const int T1 = T - 1, G = T1 * T1, NG = R * G, NA = R * T1;
+		if (tid < NG) { j = tid / G; const int i = tid - j * G; v = 1 + i / T1; u = 1 + i - (v - 1) * T1; }
+		else if (tid < NG + NA) { const int i = tid - NG; j = i / T1; u = 0; v = 1 + i - j * T1; }
+		else if (tid < NG + 2 * NA) { const int i = tid - NG - NA; j = i / T1; v = 0; u = 1 + i - j * T1; }
+		else if (tid < R * TT) { j = tid - NG - 2 * NA; u = 0; v = 0; }
+		else { j = R; u = 0; v = 0; }                               // padding threads of the last warp
+	}
+	const int p = v * T + u;
+	const int ty = band * R + j, y = ty * T + v;
+	const bool row_ok = j < R && ty < tilesY && y < H;
+	const bool feeds_above = row_ok && j == 0 && band > 0;
+	const int skew = u + v + j + 1;
+	const int tyc = ty > 0 ? 1 : 0;                             // the rules only ask whether tx / ty are zero
+	const unsigned ntx = row_ok ? (unsigned)((W - u + T - 1) / T) : 0u;     // tiles t of my row with t * T + u < W
+	const int yy = row_ok ? y : 0;
+	// ring: 4 rows (slot = step & 3, static inside the unrolled loop), my element first
+	uint16_t* const rme = ring + T + 2 + (j + 1) * TT + p;
+	// running pointers: tile tx + UB_D of the symbol row (and previous frame), tile tx + 1 + UB_D of the row above, tile tx of the output
+	int tx = -skew;
+	const int64_t rowoff = (int64_t)z * (int64_t)fpx + (int64_t)yy * W + u;
+	const uint16_t* sp = sym + rowoff + (int64_t)(tx + UB_D) * T;
+	const uint16_t* pp = out + rowoff - (int64_t)fpx + (int64_t)(tx + UB_D) * T;        // previous frame (odd video frames)
+	const uint16_t* ap = out + rowoff - (int64_t)T * W + (int64_t)(tx + 1 + UB_D) * T;  // same (u, v) one tile row up
+	uint16_t* op = out + rowoff + (int64_t)tx * T;
+	// The pixel above my tile ta = w - u - v (entering the ring at step w) was produced by the last row of the band above
+	// at ITS step ta + u + v + R = w + R: the prefetch for step w + UB_D needs w + UB_D + R + 1 complete steps up there.
+	auto wait_above = [&](int w_use) {
+		const uint32_t need = (uint32_t)(w_use + R + 1);
+		while (*(volatile uint32_t*)&s_avail < need) { }          // written by the poller lane after its gpu-scope fence
+	};
+
+	uint32_t sq[UB_D], aq[UB_D];                                // sq: symbol | previous-frame pixel << 16
+	#pragma unroll
+	for (int d = 0; d < UB_D; d++) {
+		const unsigned t = (unsigned)(d - skew);
+		sq[d] = 0; aq[d] = 0;
+		if (t < ntx) {
+			sq[d] = (uint32_t)__ldg(sp + (int64_t)(d - UB_D) * T);
+			if (ZF) sq[d] |= (uint32_t)__ldcg(pp + (int64_t)(d - UB_D) * T) << 16;
+		}
+		if (feeds_above && t + 1u < ntx) { wait_above(d); aq[d] = (uint32_t)__ldcg(ap + (int64_t)(d - UB_D) * T); }
+	}
+	int my_prev = 0, ut_prev = 0;                                // my pixel / the pixel above it, one tile to the left
+
+	for (int w0 = 0; w0 < nsteps; w0 += UB_D) {
+		#pragma unroll
+		for (int d = 0; d < UB_D; d++) {
+			uint16_t* const C = rme + (d & 3) * RS;                  // written this step
+			const uint16_t* const P1 = rme + ((d + 3) & 3) * RS;     // one step ago
+			const uint16_t* const P2 = rme + ((d + 2) & 3) * RS;     // two steps ago
+			asm volatile("bar.sync 1, %0;" :: "r"(ncomp + 32) : "memory");    // compute threads + the signal warp
+			const uint32_t q = sq[d];
+			{	// refill the queue for step w + UB_D
+				uint32_t nv = 0;
+				if ((unsigned)(tx + UB_D) < ntx) {
+					nv = (uint32_t)__ldg(sp);
+					if (ZF) nv |= (uint32_t)__ldcg(pp) << 16;
+				}
+				sq[d] = nv;
+				sp += T; if (ZF) pp += T;
+			}
+			if (feeds_above) {                                      // virtual row 0: the pixel above tile tx + 1
+				C[-TT] = (uint16_t)aq[d];
+				const unsigned t = (unsigned)(tx + 1 + UB_D);
+				if (t < ntx) { wait_above(w0 + d + UB_D); aq[d] = (uint32_t)__ldcg(ap); }
+				ap += T;
+			}
+			if ((unsigned)tx < ntx) {
+				const int ut = (int)P1[-TT];
+				auto px = [&](int dx, int dy) -> int {
+					const bool fx = dx <= -T, fy = dy <= -T;
+					const int nx = fx ? dx + T : dx, ny = fy ? dy + T : dy;          // near part: 0 or -1
+					if (nx == 0 && ny == 0) return (fx && fy) ? ut_prev : fx ? my_prev : ut;
+					const int back = (fx ? 1 : 0) + (fy ? 1 : 0) - nx - ny;          // 1 or 2 steps ago
+					const uint16_t* base = back == 1 ? P1 : P2;
+					return (int)base[(fy ? -TT : 0) + nx + ny * T];
+				};
+				int pr = tx == 0 ? predict0(px, T, WAY, K, 0, tyc, u, v) : predict0(px, T, WAY, K, 1, tyc, u, v);
+				if (ZF) pr = (tx == 0 && ty == 0 && u == 0 && v == 0) ? (int)(q >> 16) : ((pr + (int)(q >> 16)) >> 1);
+				const uint16_t val = (uint16_t)(unsymbolize16((uint16_t)q) + pr);
+				C[0] = val;
+				*op = val;
+				my_prev = (int)val; ut_prev = ut;
+			}
+			op += T; tx++;
+		}
+	}
+	asm volatile("bar.sync 1, %0;" :: "r"(ncomp + 32) : "memory");                            // w == nsteps_run: everything is stored
+}
+
+// per-device progress flags of the band pipeline (grown on demand; launches on one device are stream-ordered by the engine)
+static uint32_t* ub_flags(size_t n)
+{
+	static uint32_t* buf[64] = { nullptr }; static size_t cap[64] = { 0 };
+	int dev = 0; cudaGetDevice(&dev); dev &= 63;
+	if (cap[dev] < n) {
+		if (buf[dev]) cudaFree(buf[dev]);
+		buf[dev] = nullptr; cap[dev] = 0;
+		const size_t want = n + n / 2 + 1024;
+		if (cudaMalloc(&buf[dev], want * 4) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+		cap[dev] = want;
+	}
+	return buf[dev];
+}
+
+// returns 0 ok, 1 launch error, 2 shape not supported by this path
+template <int WAY>
+static int launch_unpredict_bands(const uint16_t* sym, uint16_t* out, int W, int H, int T, int k, int zflag,
+                                  uint32_t z_start, uint32_t z_step, uint32_t count, cudaStream_t st)
+{
+	const int TT = T * T;
+	int R = 0;
+	while ((((R + 1) * TT + 31) & ~31) + UB_HELPERS <= 1024) R++;
+	if (R == 0) return 2;
+	static const int r_max = getenv("LFM_B200_BANDS_R") ? atoi(getenv("LFM_B200_BANDS_R")) : 1024;
+	const int tilesY = (H + T - 1) / T;
+	R = std::max(1, std::min(std::min(R, r_max), tilesY));
+	const int ncomp = (R * TT + 31) & ~31;
+	const int nbands = (tilesY + R - 1) / R;
+	const uint64_t nctas = (uint64_t)nbands * count;
+	if (nctas > 0x7fffffffull) return 2;
+	uint32_t* flags = ub_flags((size_t)nctas);
+	if (!flags) return 2;
+	cudaMemsetAsync(flags, 0, (size_t)nctas * 4, st);
+	const size_t smem = (size_t)4 * ((R + 1) * TT + T + 2) * 2;
+	#define LFM_UB(KK) do { if (zflag) k_unpredict_bands<WAY, KK, 1><<<(unsigned)nctas, ncomp + UB_HELPERS, smem, st>>>(sym, out, W, H, T, z_start, z_step, count, R, ncomp, flags); \
+		else k_unpredict_bands<WAY, KK, 0><<<(unsigned)nctas, ncomp + UB_HELPERS, smem, st>>>(sym, out, W, H, T, z_start, z_step, count, R, ncomp, flags); } while (0)
+	switch (k) {
+	case 1: LFM_UB(1); break; case 3: LFM_UB(3); break; case 4: LFM_UB(4); break;
+	case 5: LFM_UB(5); break; case 6: LFM_UB(6); break; case 7: LFM_UB(7); break;
+	case 2: if (WAY == 2) { LFM_UB(2); break; } return 2;
+	default: return 2;
+	}
+	#undef LFM_UB
+	return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 template <int WAY, int K>
 static void launch_predict_fwd_wk(const uint16_t* img, uint16_t* sym, int W, int H, int T, int video, uint32_t z0, uint32_t nz,
                                   cudaStream_t st)
@@ -851,6 +1098,12 @@ int launch_unpredict(const uint16_t* sym, uint16_t* out, int W, int H, int T, in
 {
 	(void)sm_count;
 	if (count == 0) return 0;
+	static const int bands_all = getenv("LFM_B200_BANDS") ? atoi(getenv("LFM_B200_BANDS")) : 1;
+	if (bands_all >= 2 && !video && ((way == 1 && k != 2) || way == 2)) {      // measurement switch: every way through the band pipeline
+		const int rcb = way == 1 ? launch_unpredict_bands<1>(sym, out, W, H, T, k, 0, z_start, z_step, count, st)
+		                         : launch_unpredict_bands<2>(sym, out, W, H, T, k, 0, z_start, z_step, count, st);
+		if (rcb != 2) return rcb;
+	}
 	const int tilesX = (W + T - 1) / T, tilesY = (H + T - 1) / T;
 	const unsigned wpb = UF_NT / 32;
 	// sub-images per CTA for the way "space" (neighbours in u share 32-byte sectors): as many as shared memory / 1024 threads allow
@@ -891,6 +1144,15 @@ int launch_unpredict(const uint16_t* sym, uint16_t* out, int W, int H, int T, in
 		const uint64_t warps = (uint64_t)count * tilesX * tilesY;
 		k_unpredict_angle<<<(unsigned)((warps + wpb - 1) / wpb), UF_NT, 0, st>>>(sym, out, W, H, T, k, z_start, z_step, count);
 		return cudaGetLastError() == cudaSuccess ? 0 : 1;
+	}
+	// way tiles (image stacks and video), every predictor but 2: the band pipeline
+	static const int bands_on = getenv("LFM_B200_BANDS") ? atoi(getenv("LFM_B200_BANDS")) : 1;
+	// (a single frame is a chain of tilesY / R bands, each ~R + UB_D + 10 steps behind the one above: one or two frames are
+	// served faster by the cluster wavefront below, which puts 8 SMs on every frame)
+	static const int bands_min = getenv("LFM_B200_BANDS_MIN") ? atoi(getenv("LFM_B200_BANDS_MIN")) : 3;
+	if (bands_on && way == 0 && k != 2 && (int)count >= bands_min) {
+		const int rcb = launch_unpredict_bands<0>(sym, out, W, H, T, k, (video && (z_start & 1u)) ? 1 : 0, z_start, z_step, count, st);
+		if (rcb != 2) return rcb;
 	}
 	// remaining cases (way tiles, video, predictor 2 of tiles/angle): many frames -> one CTA per frame in shared memory;
 	// few frames -> the cluster wavefront below (all SMs on one frame)

@@ -263,3 +263,29 @@ def test_two_gpus_in_process_sharding(L, tmp_path):
         assert np.array_equal(L.decompress_from_bytes(two, a.shape, way=0), a)
     finally:
         L.set_devices(0, 1)
+
+
+@pytest.mark.parametrize("shape_t", [((40, 300, 520), 13), ((7, 95, 333), 15), ((160, 64, 200), 5)])
+def test_inverse_band_pipeline_many_frames(L, shape_t):
+    """way tiles, stacks of >= 3 frames: the band-pipelined inverse (one CTA per band of tile rows, bands of a frame chained
+    through progress flags, more bands than fit the GPU at once).  Every predictor, image and video mode: the inverse applied
+    to the forward kernel's symbols restores the stack exactly (the forward kernel is pinned to the oracle by the file tests)."""
+    import ctypes as C
+    import torch
+    (F, H, W), T = shape_t
+    rng = np.random.default_rng(F)
+    a = (lf_synth((F, H, W), T, seed=3).astype(np.int64) + rng.integers(0, 500, (F, H, W))).astype(np.uint16)
+    d = torch.from_numpy(a.view(np.int16)).cuda()
+    sym = torch.empty_like(d); back = torch.empty_like(d)
+    xyz = L._u32x5(W, H, F, 1, 1)
+    ms = C.c_float()
+    prev = L.set_way(0)
+    try:
+        for k in range(1, 8):
+            for video in (0, 1):
+                back.fill_(-21555)
+                assert L.lib.lfmDebugPredictDevice(d.data_ptr(), sym.data_ptr(), xyz, T, k, video, 0, 1, C.byref(ms)) == 0
+                assert L.lib.lfmDebugPredictDevice(sym.data_ptr(), back.data_ptr(), xyz, T, k, video, 1, 1, C.byref(ms)) == 0
+                assert torch.equal(back, d), (k, video)
+    finally:
+        L.set_way(prev if prev is not None and prev >= 0 else 0)
