@@ -43,7 +43,7 @@ extern __shared__ __align__(16) uint8_t dec_smem[];
 __global__ void __launch_bounds__(128)
 k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ begin, const uint64_t* __restrict__ end,
               uint32_t njobs, DecJob* __restrict__ jobs, uint16_t* __restrict__ mtfv_all, uint32_t mcap, uint32_t cap,
-              uint32_t selcap)
+              uint32_t selcap, uint32_t nsub)
 {
 	const uint32_t lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
 	const uint32_t job = blockIdx.x * nw + w;
@@ -53,12 +53,16 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	uint8_t* selector = dec_smem + (size_t)w * per_warp + sizeof(DecWarpSmem);
 	uint32_t* sw = reinterpret_cast<uint32_t*>(selector + selcap);
 	uint16_t* so = reinterpret_cast<uint16_t*>(sw + DEC_RING);           // decoded symbols, flushed 32 at a time
-	DecJob& J = jobs[job];
-	uint16_t* mtfv = mtfv_all + (size_t)job * mcap;
+	// the stream's bzip2 blocks go to records job * nsub + kb (kb = 0, 1, ...); errors are reported in record 0
+	DecJob& J0 = jobs[(size_t)job * nsub];
 	const uint8_t* src = payload + begin[job];
 	const uint64_t nbytes = end[job] - begin[job];
-	#define FAIL(code) do { if (lane == 0) { J.status = (code); J.n = 0; J.n_mtf = 0; } return; } while (0)
-	if (lane == 0) { J.n = 0; J.n_mtf = 0; J.out_bytes = 0; J.orig_ptr = 0; J.stored_crc = 0; J.status = 0; }
+	#define FAIL(code) do { if (lane == 0) { J0.status = (code); J0.n = 0; J0.n_mtf = 0; } return; } while (0)
+	for (uint32_t k = lane; k < nsub; k += 32) {
+		DecJob& Jk = jobs[(size_t)job * nsub + k];
+		Jk.n = 0; Jk.n_mtf = 0; Jk.out_bytes = 0; Jk.orig_ptr = 0; Jk.stored_crc = 0; Jk.status = 0; Jk.flags = kSubUnused; Jk.level = 0; Jk.max_block = 0;
+	}
+	__syncwarp();
 
 	// ---- the stream is staged through a ring of big-endian words: word i = bytes 4i..4i+3, zero past the end
 	const uint32_t nwords = (uint32_t)((nbytes + 3) / 4);
@@ -103,8 +107,13 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	if (level < 1 || level > 9) FAIL(1);
 	const uint32_t max_block = min((uint32_t)(100000 * level), cap);
 	uint32_t m1 = get(24), m2 = get(24);
-	if (m1 == 0x177245 && m2 == 0x385090) { if (lane == 0) J.level = (uint32_t)level; return; }      // empty stream
+	uint32_t combined = 0, kb = 0;
+	for (;; kb++) {                                        // one bzip2 block per iteration (decompress.c:196-487)
+	if (m1 == 0x177245 && m2 == 0x385090) break;           // end of stream
 	if (m1 != 0x314159 || m2 != 0x265359) FAIL(2);
+	if (kb >= nsub) FAIL(4);                               // more blocks than this block geometry can produce
+	DecJob& J = jobs[(size_t)job * nsub + kb];
+	uint16_t* mtfv = mtfv_all + ((size_t)job * nsub + kb) * mcap;
 	const uint32_t stored_crc = get(32);
 	if (get(1)) FAIL(4);                                   // randomised blocks are never produced (compress.c:629)
 	const uint32_t orig_ptr = get(24);
@@ -262,16 +271,22 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	if (flushed + lane < nsym) mtfv[flushed + lane] = so[(flushed + lane) & (DEC_OUT - 1)];
 	bb = ((uint64_t)hi << 32) | lo;
 	if (bc <= 32u) { bb |= (uint64_t)nxt << (32u - bc); bc += 32u; wi++; nxt = sw[wi & (DEC_RING - 1)]; }      // back to the header reader's invariant
-	// the stream must end here: end-of-stream magic + combined CRC (single block: == block CRC)
-	uint32_t e1 = get(24), e2 = get(24);
-	if (e1 == 0x314159 && e2 == 0x265359) FAIL(4);            // multi-block stream: not supported in this version
-	if (e1 != 0x177245 || e2 != 0x385090) FAIL(2);
-	if (get(32) != stored_crc) FAIL(3);
 	if (wi > wi_limit) FAIL(2);
 	if (lane == 0) {
 		J.n_mtf = nsym; J.n_in_use = n_in_use; J.orig_ptr = orig_ptr; J.stored_crc = stored_crc; J.level = (uint32_t)level; J.status = 0;
-		J.max_block = max_block;
+		J.max_block = max_block; J.flags = kb == 0 ? kSubFirst : 0u;
 		for (int k = 0; k < 8; k++) J.in_use[k] = iu[k];
+	}
+	combined = ((combined << 1) | (combined >> 31)) ^ stored_crc;         // bzlib.c / decompress.c: calculatedCombinedCRC
+	m1 = get(24); m2 = get(24);                            // next block header or end-of-stream magic
+	}
+	// end of stream: combined CRC of all blocks (single block: == block CRC)
+	if (get(32) != combined) FAIL(3);
+	if (wi > wi_limit) FAIL(2);
+	__syncwarp();
+	if (lane == 0) {
+		if (kb == 0) { J0.level = (uint32_t)level; J0.flags = kSubFirst | kSubLast; }      // empty stream
+		else jobs[(size_t)job * nsub + kb - 1].flags |= kSubLast;
 	}
 	#undef FAIL
 }
@@ -610,8 +625,8 @@ extern __shared__ __align__(16) uint8_t ur_smem[];
 
 template <int NT>
 __global__ void __launch_bounds__(NT)
-k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* = BWT slots, dead by now */, uint32_t cap,
-        DecJob* __restrict__ jobs, uint32_t njobs, uint16_t* __restrict__ sym, Geom g, const uint64_t* __restrict__ block_ids,
+k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* = BWT slots, dead by now */, uint32_t cap /* sub-slot */,
+        uint32_t nsub, DecJob* __restrict__ jobs, uint32_t njobs, uint16_t* __restrict__ sym, Geom g, const uint64_t* __restrict__ block_ids,
         int stage_in_smem)
 {
 	__shared__ uint32_t crc_tab[256];
@@ -622,103 +637,114 @@ k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* 
 	__shared__ uint32_t s_total;
 	__shared__ uint32_t red[64];
 	const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
-	const uint32_t job = blockIdx.x;
+	const uint32_t job = blockIdx.x;                                    // KLB block; its bzip2 blocks are records job * nsub + k
 	if (job >= njobs) return;
-	DecJob& J = jobs[job];
-	if (J.status != 0) return;
+	DecJob& J0 = jobs[(size_t)job * nsub];
+	for (uint32_t k = 0; k < nsub; k++) if (jobs[(size_t)job * nsub + k].status != 0) return;
 	if (tid < 256) crc_tab[tid] = crc_table_entry(tid);
-	const uint8_t* txt = txt_all + (size_t)job * cap;
-	const uint32_t n = J.n;
 	uint32_t c0[5], ext[5];
 	block_box(g, block_ids[job], c0, ext);
 	const uint32_t rows = ext[1] * ext[2] * ext[3] * ext[4], rowpx = ext[0];
 	const uint32_t gcount = rows * rowpx * 2;
-	uint8_t* stage = stage_in_smem ? ur_smem : stage_all + (size_t)job * cap;
+	uint8_t* stage = stage_in_smem ? ur_smem : stage_all + (size_t)job * nsub * cap;
 
-	// ---- 1. chunk maps
-	const uint32_t CH = (n + NT - 1) / NT;
-	const uint32_t a0 = min(n, tid * CH), a1 = min(n, a0 + CH);
-	{
-		// all five entry states in one pass over the chunk (each byte is loaded once)
-		uint32_t st[5] = { 0, 1, 2, 3, 4 }, cn[5] = { 0, 0, 0, 0, 0 };
-		uint32_t prev = a0 > 0 ? txt[a0 - 1] : 0x100u;
-		for (uint32_t i = a0; i < a1; i++) {
-			const uint32_t ch = txt[i];
-			const bool eq = (ch == prev);
-			#pragma unroll
-			for (int m = 0; m < 5; m++) {
-				if (st[m] == 4) { cn[m] += ch; st[m] = 0; }
-				else { st[m] = (st[m] >= 1 && eq) ? st[m] + 1 : 1; cn[m]++; }
+	uint32_t obase = 0;                                                 // bytes of the KLB block decoded by the blocks before this one
+	for (uint32_t kb = 0; kb < nsub; kb++) {
+		DecJob& J = jobs[(size_t)job * nsub + kb];
+		if (J.flags & kSubUnused) break;
+		const uint8_t* txt = txt_all + ((size_t)job * nsub + kb) * cap;
+		const uint32_t n = J.n;
+		__syncthreads();
+		// ---- 1. chunk maps
+		const uint32_t CH = (n + NT - 1) / NT;
+		const uint32_t a0 = min(n, tid * CH), a1 = min(n, a0 + CH);
+		{
+			// all five entry states in one pass over the chunk (each byte is loaded once)
+			uint32_t st[5] = { 0, 1, 2, 3, 4 }, cn[5] = { 0, 0, 0, 0, 0 };
+			uint32_t prev = a0 > 0 ? txt[a0 - 1] : 0x100u;
+			for (uint32_t i = a0; i < a1; i++) {
+				const uint32_t ch = txt[i];
+				const bool eq = (ch == prev);
+				#pragma unroll
+				for (int m = 0; m < 5; m++) {
+					if (st[m] == 4) { cn[m] += ch; st[m] = 0; }
+					else { st[m] = (st[m] >= 1 && eq) ? st[m] + 1 : 1; cn[m]++; }
+				}
+				prev = ch;
 			}
-			prev = ch;
-		}
-		uint32_t fn = 0;
-		#pragma unroll
-		for (int m = 0; m < 5; m++) { fn |= st[m] << (3 * m); s_cnt[tid][m] = cn[m]; }
-		s_fn[tid] = fn;
-	}
-	__syncthreads();
-	// ---- 2. entry state / output offset of every chunk: inclusive scan of the composed transition maps (composition
-	// is associative), applied to the start state 0; then a block scan of the byte counts for those entry states
-	{
-		auto compose = [](uint32_t f, uint32_t g2) -> uint32_t {                      // first f, then g2
-			uint32_t h = 0;
+			uint32_t fn = 0;
 			#pragma unroll
-			for (int m = 0; m < 5; m++) { const uint32_t mid = (f >> (3 * m)) & 7u; h |= ((g2 >> (3 * mid)) & 7u) << (3 * m); }
-			return h;
-		};
-		const uint32_t ident = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
-		uint32_t f = s_fn[tid];
-		#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { const uint32_t pf = __shfl_up_sync(0xffffffffu, f, o); if (lane >= (uint32_t)o) f = compose(pf, f); }
-		if (lane == 31) s_in[wid] = f;                                                // s_in doubles as the warp totals for a moment
-		__syncthreads();
-		uint32_t before = ident;
-		for (uint32_t ww = 0; ww < wid; ww++) before = compose(before, s_in[ww]);
-		uint32_t ef = __shfl_up_sync(0xffffffffu, f, 1);
-		if (lane == 0) ef = ident;
-		const uint32_t excl = compose(before, ef);                                    // map of everything before my chunk
-		const uint32_t st_in = excl & 7u;                                              // applied to state 0
-		__syncthreads();
-		s_in[tid] = st_in;
-		uint32_t tot; const uint32_t incs = block_scan_add<NT>(s_cnt[tid][st_in], red, &tot);
-		s_off[tid] = incs - s_cnt[tid][st_in];
-		if (tid == 0) s_total = tot;
-	}
-	__syncthreads();
-	if (s_total != gcount) { if (tid == 0) { J.status = 2; J.out_bytes = s_total; } return; }
-	// ---- 3. replay into the staging copy
-	{
-		uint32_t st = s_in[tid], o = s_off[tid];
-		for (uint32_t i = a0; i < a1; i++) {
-			const uint32_t ch = txt[i];
-			if (st == 4) { const uint32_t pv = txt[i - 1]; for (uint32_t k = 0; k < ch; k++) stage[o + k] = (uint8_t)pv; o += ch; st = 0; }
-			else { st = (st >= 1 && i > 0 && ch == txt[i - 1]) ? st + 1 : 1; stage[o++] = (uint8_t)ch; }
+			for (int m = 0; m < 5; m++) { fn |= st[m] << (3 * m); s_cnt[tid][m] = cn[m]; }
+			s_fn[tid] = fn;
 		}
-	}
-	__syncthreads();
-	// ---- 4. CRC of the staged block (chunks right aligned: only the first non-empty one is short)
-	{
-		uint32_t CC = ((gcount + NT - 1) / NT + 3) & ~3u;
-		if (((CC >> 2) & 1u) == 0) CC += 4;
-		const uint32_t after = (NT - 1 - tid) * CC;
-		const uint32_t e1 = gcount > after ? gcount - after : 0;
-		const uint32_t e0 = e1 > CC ? e1 - CC : 0;
-		uint32_t crc = 0;
-		if (e1 > e0) {
-			crc = (e0 == 0) ? 0xFFFFFFFFu : 0u;
-			for (uint32_t j = e0; j < e1; j++) crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ stage[j]];
-		}
-		s_crc[tid] = crc;
 		__syncthreads();
-		uint32_t M = ur_xpow8(CC);
-		for (uint32_t stride = 1; stride < NT; stride <<= 1) {
-			if ((tid & (2 * stride - 1)) == 0) s_crc[tid] = ur_mulmod(s_crc[tid], M) ^ s_crc[tid + stride];
-			M = ur_mulmod(M, M);
+		// ---- 2. entry state / output offset of every chunk: inclusive scan of the composed transition maps (composition
+		// is associative), applied to the start state 0; then a block scan of the byte counts for those entry states
+		{
+			auto compose = [](uint32_t f, uint32_t g2) -> uint32_t {                      // first f, then g2
+				uint32_t h = 0;
+				#pragma unroll
+				for (int m = 0; m < 5; m++) { const uint32_t mid = (f >> (3 * m)) & 7u; h |= ((g2 >> (3 * mid)) & 7u) << (3 * m); }
+				return h;
+			};
+			const uint32_t ident = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
+			uint32_t f = s_fn[tid];
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const uint32_t pf = __shfl_up_sync(0xffffffffu, f, o); if (lane >= (uint32_t)o) f = compose(pf, f); }
+			if (lane == 31) s_in[wid] = f;                                                // s_in doubles as the warp totals for a moment
 			__syncthreads();
+			uint32_t before = ident;
+			for (uint32_t ww = 0; ww < wid; ww++) before = compose(before, s_in[ww]);
+			uint32_t ef = __shfl_up_sync(0xffffffffu, f, 1);
+			if (lane == 0) ef = ident;
+			const uint32_t excl = compose(before, ef);                                    // map of everything before my chunk
+			const uint32_t st_in = excl & 7u;                                              // applied to state 0
+			__syncthreads();
+			s_in[tid] = st_in;
+			uint32_t tot; const uint32_t incs = block_scan_add<NT>(s_cnt[tid][st_in], red, &tot);
+			s_off[tid] = incs - s_cnt[tid][st_in];
+			if (tid == 0) s_total = tot;
 		}
+		__syncthreads();
+		const uint32_t len = s_total;
+		if (len > gcount - obase) { if (tid == 0) { J0.status = 2; J0.out_bytes = obase + len; } return; }     // more than the KLB block holds
+		// ---- 3. replay into the staging copy
+		{
+			uint32_t st = s_in[tid], o = obase + s_off[tid];
+			for (uint32_t i = a0; i < a1; i++) {
+				const uint32_t ch = txt[i];
+				if (st == 4) { const uint32_t pv = txt[i - 1]; for (uint32_t k = 0; k < ch; k++) stage[o + k] = (uint8_t)pv; o += ch; st = 0; }
+				else { st = (st >= 1 && i > 0 && ch == txt[i - 1]) ? st + 1 : 1; stage[o++] = (uint8_t)ch; }
+			}
+		}
+		__syncthreads();
+		// ---- 4. CRC of this block's bytes (chunks right aligned: only the first non-empty one is short)
+		{
+			uint32_t CC = ((len + NT - 1) / NT + 3) & ~3u;
+			if (((CC >> 2) & 1u) == 0) CC += 4;
+			const uint32_t after = (NT - 1 - tid) * CC;
+			const uint32_t e1 = len > after ? len - after : 0;
+			const uint32_t e0 = e1 > CC ? e1 - CC : 0;
+			uint32_t crc = 0;
+			if (e1 > e0) {
+				crc = (e0 == 0) ? 0xFFFFFFFFu : 0u;
+				for (uint32_t j = obase + e0; j < obase + e1; j++) crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ stage[j]];
+			}
+			s_crc[tid] = crc;
+			__syncthreads();
+			uint32_t M = ur_xpow8(CC);
+			for (uint32_t stride = 1; stride < NT; stride <<= 1) {
+				if ((tid & (2 * stride - 1)) == 0) s_crc[tid] = ur_mulmod(s_crc[tid], M) ^ s_crc[tid + stride];
+				M = ur_mulmod(M, M);
+				__syncthreads();
+			}
+		}
+		if (~s_crc[0] != J.stored_crc) { if (tid == 0) J0.status = 3; return; }
+		if (tid == 0) J.out_bytes = len;
+		obase += len;
 	}
-	if (~s_crc[0] != J.stored_crc) { if (tid == 0) J.status = 3; return; }
+	if (obase != gcount) { if (tid == 0) { J0.status = 2; J0.out_bytes = obase; } return; }
+	__syncthreads();
 	// ---- 5. scatter rows into the image
 	for (uint32_t r = wid; r < rows; r += NT / 32) {
 		uint32_t y = r % ext[1], q = r / ext[1];
@@ -729,11 +755,10 @@ k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* 
 		const uint16_t* srcrow = reinterpret_cast<const uint16_t*>(stage) + (size_t)r * rowpx;
 		for (uint32_t x = lane; x < rowpx; x += 32) row[x] = srcrow[x];
 	}
-	if (tid == 0) J.out_bytes = gcount;
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t* end, uint32_t njobs, DecJob* jobs,
+int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t* end, uint32_t njobs, uint32_t nsub, DecJob* jobs,
                   uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap, cudaStream_t st)
 {
 	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)DEC_RING * 4 + (size_t)DEC_OUT * 2;
@@ -741,10 +766,10 @@ int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t*
 	if (nw < 1) return 1;
 	const size_t smem = per_warp * nw;
 	cudaFuncSetAttribute(k_huff_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	k_huff_decode<<<(njobs + nw - 1) / nw, nw * 32, smem, st>>>(payload, begin, end, njobs, jobs, mtfv, mcap, cap, selcap);
+	k_huff_decode<<<(njobs + nw - 1) / nw, nw * 32, smem, st>>>(payload, begin, end, njobs, jobs, mtfv, mcap, cap, selcap, nsub);
 	const size_t smem2 = imtf_smem_bytes();
 	cudaFuncSetAttribute(k_imtf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-	k_imtf<<<njobs, IM_NT, smem2, st>>>(mtfv, mcap, jobs, njobs, q_scratch, bwt, cap);
+	k_imtf<<<njobs * nsub, IM_NT, smem2, st>>>(mtfv, mcap, jobs, njobs * nsub, q_scratch, bwt, cap);
 	return 0;
 }
 size_t inv_bwt_scratch_elems(int grid, uint32_t cap) { return (size_t)grid * cap + (size_t)grid * 2 * IB_VIS; }
@@ -755,14 +780,14 @@ void launch_inv_bwt(const uint8_t* bwt, uint32_t cap, DecJob* jobs, uint32_t njo
 	cudaFuncSetAttribute(k_inv_bwt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	k_inv_bwt<<<grid, BWT_NT, smem, st>>>(bwt, cap, jobs, njobs, tt_scratch, txt);
 }
-void launch_unrle(const uint8_t* txt, uint8_t* stage_scratch, uint32_t cap, uint32_t max_raw_bytes, DecJob* jobs, uint32_t njobs,
+void launch_unrle(const uint8_t* txt, uint8_t* stage_scratch, uint32_t cap, uint32_t nsub, uint32_t max_raw_bytes, DecJob* jobs, uint32_t njobs,
                   uint16_t* sym, const Geom& g, const uint64_t* block_ids, cudaStream_t st)
 {
 	const int in_smem = max_raw_bytes + 16 <= 200 * 1024;
 	const size_t smem = in_smem ? (size_t)max_raw_bytes + 16 : 0;
 	// (a 1024-thread variant for the 147 KB blocks was measured slower: 2.08 ms against 1.67 ms on the 16-frame stack)
 	cudaFuncSetAttribute(k_unrle<UR_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	k_unrle<UR_NT><<<njobs, UR_NT, smem, st>>>(txt, stage_scratch, cap, jobs, njobs, sym, g, block_ids, in_smem);
+	k_unrle<UR_NT><<<njobs, UR_NT, smem, st>>>(txt, stage_scratch, cap, nsub, jobs, njobs, sym, g, block_ids, in_smem);
 }
 
 }  // namespace lfm

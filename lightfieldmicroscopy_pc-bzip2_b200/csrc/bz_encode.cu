@@ -8,6 +8,7 @@
 //   k_huff_pack coding-table selection, 4 refinement passes, exact bzip2 Huffman code lengths, canonical codes,
 //               MSB-first bit packing and stream framing     (compress.c:240-600 sendMTFValues, huffman.c:63-166,
 //               compress.c:603-676 BZ2_compressBlock header/trailer)
+#include <cstdio>
 #include "lfm_device.cuh"
 
 namespace lfm {
@@ -58,12 +59,14 @@ extern __shared__ __align__(16) uint8_t rle_smem[];
 template <int NT>
 __global__ void __launch_bounds__(NT)
 k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t njobs,
-       uint8_t* __restrict__ txt_all, uint8_t* __restrict__ raw_all /* = BWT slots, free at this point */, uint32_t cap,
-       EncJob* __restrict__ jobs, int stage_in_smem, uint32_t nblock_max)
+       uint8_t* __restrict__ txt_all, uint8_t* __restrict__ raw_all /* = BWT slots, free at this point */, uint32_t cap /* sub-slot */,
+       uint32_t nsub, EncJob* __restrict__ jobs, int stage_in_smem, uint32_t nblock_max)
 {
 	__shared__ uint32_t crc_tab[256];
 	__shared__ uint32_t red[64];
 	__shared__ uint32_t s_a[NT], s_b[NT];
+	__shared__ uint32_t s_bout[kMaxSub + 1], s_bin[kMaxSub + 1];      // bzip2 block boundaries: output (post-RLE1) / input byte offsets
+	__shared__ uint32_t s_min;
 	const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
 	const uint32_t job = blockIdx.x;
 	if (job >= njobs) return;
@@ -73,8 +76,8 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 	block_box(g, first_block + job, c0, ext);
 	const uint32_t rows = ext[1] * ext[2] * ext[3] * ext[4], rowpx = ext[0];
 	const uint32_t gcount = rows * rowpx * 2;
-	uint8_t* out = txt_all + (size_t)job * cap;
-	uint8_t* stage = stage_in_smem ? rle_smem : raw_all + (size_t)job * cap;
+	uint8_t* out0 = txt_all + (size_t)job * nsub * cap;                 // bzip2 block k of this KLB block goes to out0 + k * cap
+	uint8_t* stage = stage_in_smem ? rle_smem : raw_all + (size_t)job * nsub * cap;
 
 	// ---- A. gather (one row per warp at a time)
 	for (uint32_t r = wid; r < rows; r += NT / 32) {
@@ -119,7 +122,7 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 	__syncthreads();
 	const uint32_t next_head = s_b[tid];
 
-	// ---- C. count, scan, write. Walk the chunk run segment by run segment.
+	// ---- C. count, scan, [block boundaries], write. Walk the chunk run segment by run segment.
 	uint32_t outc = 0;
 	{
 		uint32_t i = e0, rs = open_start;
@@ -133,8 +136,11 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 	}
 	uint32_t total; const uint32_t incs = block_scan_add<NT>(outc, red, &total);
 	const uint32_t n = total;
-	uint32_t crc = 0;
-	{
+
+	// One walk of the chunk in output order.  A RECORD is (a part of) a run of at most 255 equal bytes: up to 4 literals and,
+	// from 4 on, a count byte.  emit(o, byte) is called for every output byte, rec_end(o, in_end) after the last byte of
+	// every record that ends in this chunk's output (o = output offset after it, in_end = input offset after it).
+	auto walk = [&](auto emit, auto rec_end) {
 		uint32_t o = incs - outc, i = e0, rs = open_start;
 		while (i < e1) {
 			if (i == 0 || b[i] != b[i - 1]) rs = i;
@@ -147,45 +153,117 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 			while (p < e) {
 				const uint32_t r = p - rs, q = r % 255u;
 				if (q < 4) {
-					out[o++] = (uint8_t)ch;
-					if (q == 3) { uint32_t reclen = min(255u, run_len - (r - 3)); out[o++] = (uint8_t)(reclen - 4); }
+					const uint32_t reclen = min(255u, run_len - (r - q));
+					emit(o++, (uint8_t)ch);
+					if (q == 3) { emit(o++, (uint8_t)(reclen - 4)); rec_end(o, rs + (r - 3) + reclen); }
+					else if (q + 1 == reclen) rec_end(o, rs + r + 1);
 					p++;
 				} else p += 255u - q;                                   // the rest of this 255-record emits nothing
 			}
 			i = e;
 		}
-		// ---- D. chunk CRC (the first non-empty chunk carries the 0xFFFFFFFF start value)
-		if (e1 > e0) {
-			crc = (e0 == 0) ? 0xFFFFFFFFu : 0u;
-			for (uint32_t j = e0; j < e1; j++) crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ b[j]];
+	};
+
+	// bzip2 closes a block after the record that brings it to nblockMAX bytes or more -- records are flushed when the first
+	// byte of the NEXT record is consumed (ADD_CHAR_TO_BLOCK, bzlib.c:216-258), the test sits before every input byte
+	// (copy_input_until_stop, :300-340), and the end of the input flushes whatever is pending into the current block
+	// (flush_RL, :263): boundary = first record end b >= start + nblockMAX, unless only ONE more output byte follows
+	// (then that byte was the last input byte and joined this block).
+	uint32_t nb = 1;
+	if (tid == 0) { s_bout[0] = 0; s_bin[0] = 0; }
+	if (n > nblock_max + 1) {                                    // uniform
+		const uint32_t o_first = incs - outc, o_last = incs;
+		uint32_t start = 0;                                      // output offset where the open block starts (same in every thread)
+		// at most nsub - 1 boundaries fit the records; one more round detects a stream that needs more than that
+		for (uint32_t round = 0; round < nsub && round + 1 < (uint32_t)kMaxSub; round++) {
+			const uint32_t T = start + nblock_max;
+			if (tid == 0) s_min = NONE;
+			__syncthreads();
+			uint32_t cand = NONE, cand_in = 0;
+			if (T + 1 < n && outc != 0 && o_last >= T && o_first <= T + 4)        // one of my output bytes has index in [T-1, T+4]
+				walk([](uint32_t, uint8_t) {}, [&](uint32_t o, uint32_t in_end) { if (o >= T && cand == NONE) { cand = o; cand_in = in_end; } });
+			if (cand != NONE) atomicMin(&s_min, cand);
+			__syncthreads();
+			const uint32_t bnd = s_min;
+			const bool found = bnd != NONE && bnd + 1 < n;
+			if (found && cand == bnd) { s_bout[nb] = bnd; s_bin[nb] = cand_in; }
+			if (found) { nb++; start = bnd; }
+			__syncthreads();                                         // s_min is reset by thread 0 in the next round
 		}
 	}
-	s_a[tid] = crc;
+	if (tid == 0) { s_bout[nb] = n; s_bin[nb] = gcount; }
 	__syncthreads();
+	// does the stream fit the records reserved for it?  (the last block may still exceed nblockMAX when the loop stopped at kMaxSub)
+	const bool too_big = nb > nsub || (s_bout[nb] - s_bout[nb - 1]) + 8 > cap;
+	if (too_big) {
+		if (tid < nsub) {
+			EncJob& J = jobs[(size_t)job * nsub + tid];
+			J.raw_bytes = gcount; J.n = 0; J.crc = 0; J.orig_ptr = 0; J.n_mtf = 0; J.n_in_use = 0; J.periodic = 0;
+			J.status = tid == 0 ? 4u : 0u; J.flags = kSubUnused; J.total_bits = 0; J.out_bytes = 0; J.stream_crc = 0;
+		}
+		return;
+	}
 	{
-		uint32_t M = crc_xpow8(CH);                                     // x^(8 CH): shift by one full chunk
+		uint32_t kc = 0;
+		const uint32_t o_first = incs - outc;
+		while (kc + 1 < nb && o_first >= s_bout[kc + 1]) kc++;
+		uint8_t* dst = out0 + (size_t)kc * cap - s_bout[kc];
+		uint32_t lim = s_bout[kc + 1];
+		walk([&](uint32_t o, uint8_t v) {
+			if (o >= lim && kc + 1 < nb) { kc++; dst = out0 + (size_t)kc * cap - s_bout[kc]; lim = s_bout[kc + 1]; }
+			dst[o] = v;
+		}, [](uint32_t, uint32_t) {});
+	}
+	__syncthreads();
+	// 8 wrap-around bytes after every block (the sort reads text[i + 0..7]) and zero padding to a multiple of 4
+	for (uint32_t k = tid / 12; k < nb; k += NT / 12) {
+		const uint32_t t = tid % 12, nk = s_bout[k + 1] - s_bout[k];
+		uint8_t* ok = out0 + (size_t)k * cap;
+		const uint32_t pos = nk + t;
+		if (t < 8) ok[pos] = ok[t % nk];
+		else if (pos < ((nk + 8 + 3) & ~3u)) ok[pos] = 0;
+	}
+	// ---- D. CRC-32 of every block's input bytes: per-chunk table CRC (chunks right aligned inside the block's input range: only
+	// the first non-empty one is short and carries the 0xFFFFFFFF start value), combined in a binary tree
+	uint32_t combined = 0;
+	for (uint32_t k = 0; k < nb; k++) {
+		const uint32_t lo = s_bin[k], len = s_bin[k + 1] - lo;
+		uint32_t CC = ((len + NT - 1) / NT + 3) & ~3u;
+		if (((CC >> 2) & 1u) == 0) CC += 4;
+		const uint32_t aft = (NT - 1 - tid) * CC;
+		const uint32_t x1 = len > aft ? len - aft : 0;
+		const uint32_t x0 = x1 > CC ? x1 - CC : 0;
+		uint32_t crc = 0;
+		if (x1 > x0) {
+			crc = (x0 == 0) ? 0xFFFFFFFFu : 0u;
+			for (uint32_t j = lo + x0; j < lo + x1; j++) crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ b[j]];
+		}
+		__syncthreads();
+		s_a[tid] = crc;
+		__syncthreads();
+		uint32_t M = crc_xpow8(CC);                                     // x^(8 CC): shift by one full chunk
 		for (uint32_t stride = 1; stride < NT; stride <<= 1) {
 			if ((tid & (2 * stride - 1)) == 0) s_a[tid] = crc_mulmod(s_a[tid], M) ^ s_a[tid + stride];
 			M = crc_mulmod(M, M);
 			__syncthreads();
 		}
+		if (tid == 0) {
+			EncJob& J = jobs[(size_t)job * nsub + k];
+			const uint32_t bc = ~s_a[0];
+			combined = ((combined << 1) | (combined >> 31)) ^ bc;       // bzlib.c:  combinedCRC = (combinedCRC << 1 | >> 31) ^ blockCRC
+			J.raw_bytes = gcount; J.n = s_bout[k + 1] - s_bout[k]; J.crc = bc; J.status = 0; J.periodic = 0; J.orig_ptr = 0;
+			// the inUse map (bzlib.c:226, :243-258) is exactly "byte values with a non-zero count in the block": k_bwt derives
+			// it from the byte histogram it needs anyway
+			for (int q = 0; q < 8; q++) J.in_use[q] = 0;
+			J.n_in_use = 0;
+			J.flags = (k == 0 ? kSubFirst : 0u) | (k + 1 == nb ? kSubLast : 0u);
+			J.stream_crc = combined; J.total_bits = 0; J.out_bytes = 0;
+		}
 	}
-	// 8 wrap-around bytes after the block (the sort reads text[i + 0..7]) and zero padding to a multiple of 4
-	__syncthreads();
-	if (tid < 12 && n > 0) {
-		uint32_t pos = n + tid;
-		if (tid < 8) out[pos] = out[tid % n];
-		else if (pos < ((n + 8 + 3) & ~3u)) out[pos] = 0;
-	}
-	if (tid == 0) {
-		EncJob& J = jobs[job];
-		// more bytes than one bzip2 block holds (bzlib.c:  nblockMAX = 100000 * level - 19): would be a multi-block stream
-		const bool too_big = n > nblock_max;
-		J.raw_bytes = gcount; J.n = too_big ? 0u : n; J.crc = ~s_a[0]; J.status = too_big ? 4u : 0u; J.periodic = 0; J.orig_ptr = 0;
-		// the inUse map (bzlib.c:226, :243-258) is exactly "byte values with a non-zero count in the block": k_bwt derives
-		// it from the byte histogram it needs anyway
-		for (int k = 0; k < 8; k++) J.in_use[k] = 0;
-		J.n_in_use = 0;
+	if (tid >= nb && tid < nsub) {                               // records this stream does not need
+		EncJob& J = jobs[(size_t)job * nsub + tid];
+		J.raw_bytes = gcount; J.n = 0; J.crc = 0; J.orig_ptr = 0; J.n_mtf = 0; J.n_in_use = 0; J.periodic = 0; J.status = 0;
+		J.flags = kSubUnused; J.total_bits = 0; J.out_bytes = 0; J.stream_crc = 0;
 	}
 }
 
@@ -224,6 +302,7 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 	const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
 	const uint32_t job = blockIdx.x;
 	if (job >= njobs) return;
+	if (jobs[job].flags & kSubUnused) return;               // no bzip2 block in this record
 	const uint32_t n = jobs[job].n;
 	const uint8_t* bwt = bwt_all + (size_t)job * cap;
 	uint8_t* rk = rank_all + (size_t)job * cap;
@@ -545,6 +624,8 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 	uint8_t* selmtf = selector + selcap;
 	uint32_t* out = reinterpret_cast<uint32_t*>(out_all + (size_t)job * ocap);
 
+	if (J.flags & kSubUnused) { if (tid == 0) { J.total_bits = 0; J.out_bytes = 0; J.n_groups = 0; J.n_sel = 0; } return; }
+	const bool first_blk = (J.flags & kSubFirst) != 0, last_blk = (J.flags & kSubLast) != 0;
 	if (J.n == 0) {     // empty input: stream header + trailer only (compress.c:603-676 with nblock == 0)
 		if (tid == 0) {
 			out[0] = 0; out[1] = 0; out[2] = 0; out[3] = 0;
@@ -771,7 +852,7 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 	uint32_t sel_bits; const uint32_t sel_inc = block_scan_add<HP_NT>(sel_bits_local, red, &sel_bits);
 	uint32_t used16n = 0;
 	for (int i = 0; i < 16; i++) if ((J.in_use[i >> 1] >> ((i & 1) * 16)) & 0xffffu) used16n++;
-	const uint32_t fixed_bits = 32 + 48 + 32 + 1 + 24 + 16 + 16 * used16n + 3 + 15;
+	const uint32_t fixed_bits = (first_blk ? 32u : 0u) + 48 + 32 + 1 + 24 + 16 + 16 * used16n + 3 + 15;   // "BZh" + level only before the first block
 	uint32_t len_bits = 0;
 	for (int t = 0; t < ng; t++) len_bits += s_tbits[t];
 	const uint32_t hdr_bits = fixed_bits + sel_bits + len_bits;
@@ -785,7 +866,7 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 	// ---- header: fixed part by thread 0, selectors by everybody, one table of lengths per warp
 	if (tid == 0) {
 		HdrWriter hw{ out, 0, 0, 0 };
-		hw.put(8, 'B'); hw.put(8, 'Z'); hw.put(8, 'h'); hw.put(8, (uint32_t)('0' + level));
+		if (first_blk) { hw.put(8, 'B'); hw.put(8, 'Z'); hw.put(8, 'h'); hw.put(8, (uint32_t)('0' + level)); }
 		hw.put(24, 0x314159); hw.put(24, 0x265359);
 		hw.put(32, J.crc);
 		hw.put(1, 0);
@@ -877,28 +958,32 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 		__syncthreads();
 	}
 
-	// ---- trailer: end-of-stream magic + combined CRC (= block CRC for a single block), pad to a byte
+	// ---- trailer after the last block of the stream: end-of-stream magic + combined CRC; the stream is padded to a byte
+	// when the blocks are put together (k_compact)
 	if (tid == 0) {
-		or_bits(out, bitpos, 24, 0x177245u);
-		or_bits(out, bitpos + 24, 24, 0x385090u);
-		or_bits(out, bitpos + 48, 32, J.crc);
-		uint32_t total = bitpos + 80;
+		uint32_t total = bitpos;
+		if (last_blk) {
+			or_bits(out, bitpos, 24, 0x177245u);
+			or_bits(out, bitpos + 24, 24, 0x385090u);
+			or_bits(out, bitpos + 48, 32, J.stream_crc);
+			total = bitpos + 80;
+		}
 		J.total_bits = total; J.out_bytes = (total + 7) / 8; J.n_groups = (uint32_t)ng; J.n_sel = n_sel;
 	}
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
 void launch_rle1(const uint16_t* sym, const Geom& g, uint64_t first_block, uint32_t njobs, uint8_t* txt, uint8_t* raw_scratch,
-                 uint32_t cap, uint32_t max_raw_bytes, uint32_t nblock_max, EncJob* jobs, cudaStream_t st)
+                 uint32_t cap, uint32_t nsub, uint32_t max_raw_bytes, uint32_t nblock_max, EncJob* jobs, cudaStream_t st)
 {
 	const int in_smem = max_raw_bytes + 16 <= 200 * 1024;
 	const size_t smem = in_smem ? (size_t)max_raw_bytes + 16 : 0;
 	if (max_raw_bytes > 48 * 1024) {
 		cudaFuncSetAttribute(k_rle1<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		k_rle1<1024><<<njobs, 1024, smem, st>>>(sym, g, first_block, njobs, txt, raw_scratch, cap, jobs, in_smem, nblock_max);
+		k_rle1<1024><<<njobs, 1024, smem, st>>>(sym, g, first_block, njobs, txt, raw_scratch, cap, nsub, jobs, in_smem, nblock_max);
 	} else {
 		cudaFuncSetAttribute(k_rle1<RLE_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		k_rle1<RLE_NT><<<njobs, RLE_NT, smem, st>>>(sym, g, first_block, njobs, txt, raw_scratch, cap, jobs, in_smem, nblock_max);
+		k_rle1<RLE_NT><<<njobs, RLE_NT, smem, st>>>(sym, g, first_block, njobs, txt, raw_scratch, cap, nsub, jobs, in_smem, nblock_max);
 	}
 }
 void launch_mtf(const uint8_t* bwt, uint8_t* rank_scratch, uint32_t cap, EncJob* jobs, uint32_t njobs, uint16_t* mtfv, uint32_t mcap, cudaStream_t st)

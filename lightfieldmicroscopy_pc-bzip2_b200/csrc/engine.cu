@@ -13,8 +13,9 @@ namespace lfm {
 
 struct Totals { unsigned long long running; uint32_t err; uint32_t periodic; uint32_t overflow; uint32_t pad; };
 
-// exclusive offsets of the batch's streams inside the payload (running base carried across batches)
-__global__ void k_offsets(const EncJob* __restrict__ jobs, uint32_t njobs, Totals* tot, uint64_t* __restrict__ offs,
+// exclusive offsets of the batch's streams inside the payload (running base carried across batches); a stream is the
+// bit-concatenation of the bzip2 blocks in its `nsub` records, padded to a byte
+__global__ void k_offsets(const EncJob* __restrict__ jobs, uint32_t njobs, uint32_t nsub, Totals* tot, uint64_t* __restrict__ offs,
                           uint32_t* __restrict__ sizes, uint64_t payload_cap)
 {
 	__shared__ uint32_t red[64];
@@ -25,7 +26,15 @@ __global__ void k_offsets(const EncJob* __restrict__ jobs, uint32_t njobs, Total
 	for (uint32_t j0 = 0; j0 < njobs; j0 += 1024) {
 		uint32_t j = j0 + threadIdx.x;
 		uint32_t v = 0;
-		if (j < njobs) { v = jobs[j].out_bytes; err |= jobs[j].status; per += jobs[j].periodic; }
+		if (j < njobs) {
+			uint32_t bits = 0;
+			for (uint32_t k = 0; k < nsub; k++) {
+				const EncJob& J = jobs[(size_t)j * nsub + k];
+				err |= J.status; per += J.periodic;
+				if (!(J.flags & kSubUnused)) bits += J.total_bits;
+			}
+			v = (bits + 7) / 8;
+		}
 		uint32_t total; uint32_t inc = block_scan_add<1024>(v, red, &total);
 		unsigned long long base = s_base;
 		if (j < njobs) { offs[j] = base + inc - v; sizes[j] = v; }
@@ -39,16 +48,47 @@ __global__ void k_offsets(const EncJob* __restrict__ jobs, uint32_t njobs, Total
 	if (threadIdx.x == 0) { tot->running = s_base; if (s_base > payload_cap) tot->overflow = 1; }
 }
 
-// copy each stream from its slot to its final place (byte granular; destination is unaligned by nature)
-__global__ void k_compact(const uint8_t* __restrict__ slots, uint32_t ocap, const uint64_t* __restrict__ offs,
-                          const uint32_t* __restrict__ sizes, uint8_t* __restrict__ payload, uint64_t payload_cap)
+// copy each stream from its slot(s) to its final place (byte granular; destination is unaligned by nature)
+__global__ void k_compact(const uint8_t* __restrict__ slots, uint32_t ocap, const EncJob* __restrict__ jobs, uint32_t nsub,
+                          const uint64_t* __restrict__ offs, const uint32_t* __restrict__ sizes, uint8_t* __restrict__ payload,
+                          uint64_t payload_cap)
 {
+	__shared__ uint32_t s_start[kMaxSub + 1];      // first stream bit of every bzip2 block
 	const uint32_t job = blockIdx.x;
 	const uint32_t n = sizes[job];
 	const uint64_t o = offs[job];
 	if (o + n > payload_cap) return;
-	const uint8_t* src = slots + (size_t)job * ocap;
+	const uint8_t* src = slots + (size_t)job * nsub * ocap;
 	uint8_t* dst = payload + o;
+	uint32_t nu = 0;
+	for (uint32_t k = 0; k < nsub; k++) nu += (jobs[(size_t)job * nsub + k].flags & kSubUnused) ? 0u : 1u;
+	if (nu > 1) {
+		// several bzip2 blocks: block k starts at stream bit s_start[k], anywhere inside a byte (bzip2 does not pad between
+		// blocks, compress.c:603-676).  Every thread assembles whole output bytes from at most two blocks.
+		if (threadIdx.x == 0) {
+			uint32_t acc = 0;
+			for (uint32_t k = 0; k < nu; k++) { s_start[k] = acc; acc += jobs[(size_t)job * nsub + k].total_bits; }
+			s_start[nu] = acc;
+		}
+		__syncthreads();
+		for (uint32_t P = threadIdx.x; P < n; P += blockDim.x) {
+			const uint32_t bit = P * 8;
+			uint32_t k = 0;
+			while (k + 1 < nu && bit >= s_start[k + 1]) k++;
+			uint32_t v = 0, have = 0;
+			while (have < 8 && k < nu) {
+				const uint32_t lb = bit + have - s_start[k], avail = s_start[k + 1] - (bit + have);      // unread bits of block k
+				const uint8_t* sk = src + (size_t)k * ocap;
+				const uint32_t two = ((uint32_t)sk[lb >> 3] << 8) | sk[(lb >> 3) + 1];
+				const uint32_t take = min(8u - have, avail);
+				const uint32_t bits = (two >> (16 - (lb & 7) - take)) & ((1u << take) - 1u);
+				v |= bits << (8 - have - take);
+				have += take; k++;
+			}
+			dst[P] = (uint8_t)v;
+		}
+		return;
+	}
 	// head bytes until dst is 4-aligned, then words assembled from the (4-aligned) source with a byte shift
 	uint32_t head = (uint32_t)((4 - (o & 3)) & 3); if (head > n) head = n;
 	if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
@@ -158,21 +198,27 @@ static Geom make_geom(const StackDesc& s)
 	return g;
 }
 
-struct EncSizes { uint32_t cap, mcap, selcap, ocap; int level; int text_in_smem; bool single_block_ok; };
-static EncSizes enc_sizes(const StackDesc& s)
+// Slot geometry.  A KLB block is one bzip2 stream of `nsub` bzip2 blocks at most: every block but the last holds
+// nblockMAX .. nblockMAX + 4 run-length coded bytes (bzlib.c: nblockMAX = 100000 * level - 19, a block is closed by the
+// record that reaches it), so nsub = floor(maxn / nblockMAX) + 1 and a sub-slot holds nblockMAX + 10 bytes.
+struct EncSizes { uint32_t cap, mcap, selcap, ocap, nsub, nblock_max; int level; int text_in_smem; };
+static int enc_sizes(const StackDesc& s, EncSizes& z)
 {
-	EncSizes z;
 	uint64_t blockBytes = 2;
 	for (int i = 0; i < 5; i++) blockBytes *= s.blockSize[i];
 	z.level = (int)std::min<uint64_t>(9, (blockBytes + 99999) / 100000);     // klb_imageIO.cpp:108
-	uint64_t maxn = blockBytes + blockBytes / 4 + 1;                           // RLE1 worst case: 4 -> 5 bytes
-	z.single_block_ok = maxn < (uint64_t)(100000 * z.level - 19);
-	z.cap = round16(maxn + 8);
+	const uint64_t maxn = blockBytes + blockBytes / 4 + 1;                     // RLE1 worst case: 4 -> 5 bytes
+	z.nblock_max = (uint32_t)(100000 * z.level - 19);
+	const uint64_t nsub = maxn / z.nblock_max + 1;
+	if (nsub > (uint64_t)kMaxSub || blockBytes > 0x7fffffffull / 2) return LFM_ERR_UNSUPPORTED;
+	z.nsub = (uint32_t)nsub;
+	const uint64_t subn = std::min<uint64_t>(maxn, (uint64_t)z.nblock_max + 10);
+	z.cap = round16(subn + 8) + 16;
 	z.mcap = round16((uint64_t)z.cap + 2);
 	z.selcap = round16((uint64_t)z.mcap / kGSize + 2);
-	z.ocap = round16(maxn + maxn / 8 + maxn / 16 + 8192);
+	z.ocap = round16(subn + subn / 8 + subn / 16 + 8192);
 	z.text_in_smem = bwt_smem_bytes(z.cap, 1) <= 227 * 1024;
-	return z;
+	return LFM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ selection
@@ -257,24 +303,25 @@ int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t 
 	cudaSetDevice(device_);
 	cudaStream_t st = (cudaStream_t)stream_;
 	const Geom g = make_geom(s);
-	const EncSizes z = enc_sizes(s);
-	// a KLB block whose run-length coded size exceeds one bzip2 block (100000*level - 19 bytes) would need a multi-block
-	// stream: detected per block at run time by k_rle1 (status 4) -- with the default block sizes it cannot happen
+	EncSizes z;
+	if (enc_sizes(s, z)) { err_ = "KLB block too large: more than kMaxSub bzip2 blocks per stream"; return LFM_ERR_UNSUPPORTED; }
 	if (count == 0) { *d_payload = nullptr; *payload_bytes = 0; return LFM_OK; }
-	const size_t per_job = (size_t)z.cap * 3 + (size_t)z.mcap * 2 + z.selcap + z.ocap + sizeof(EncJob);
+	// per KLB block: nsub records / sub-slots (one per possible bzip2 block of its stream; 1 for the default block shapes)
+	const size_t per_job = ((size_t)z.cap * 3 + (size_t)z.mcap * 2 + (size_t)z.selcap * 2 + z.ocap + sizeof(EncJob)) * z.nsub;
 	uint64_t B = std::min<uint64_t>(count, std::max<uint64_t>(1, ((size_t)6 << 30) / per_job));
 	B = std::min<uint64_t>(B, 16384);
-	const int grid = (int)std::min<uint64_t>(B, (uint64_t)sm_count_);
+	const uint64_t BS = B * z.nsub;                                            // job records per batch
+	const int grid = (int)std::min<uint64_t>(BS, (uint64_t)sm_count_);
 	uint64_t blockBytes = 2; for (int i = 0; i < 5; i++) blockBytes *= s.blockSize[i];
-	uint64_t pcap = std::min<uint64_t>(count * (uint64_t)z.ocap, count * blockBytes + count * blockBytes / 3 + count * 1024 + (1 << 20));
+	uint64_t pcap = std::min<uint64_t>(count * (uint64_t)z.ocap * z.nsub, count * blockBytes + count * blockBytes / 3 + count * 1024 * z.nsub + (1 << 20));
 	int rc;
-	if ((rc = reserve(jobs_, B * sizeof(EncJob)))) return rc;
-	if ((rc = reserve(txt_, B * z.cap))) return rc;
-	if ((rc = reserve(bwt_, B * z.cap))) return rc;
-	if ((rc = reserve(rank_, B * z.cap))) return rc;
-	if ((rc = reserve(mtfv_, B * (size_t)z.mcap * 2))) return rc;
-	if ((rc = reserve(sel_, B * (size_t)z.selcap * 2))) return rc;
-	if ((rc = reserve(out_, B * (size_t)z.ocap + 16))) return rc;
+	if ((rc = reserve(jobs_, BS * sizeof(EncJob)))) return rc;
+	if ((rc = reserve(txt_, BS * z.cap))) return rc;
+	if ((rc = reserve(bwt_, BS * z.cap))) return rc;
+	if ((rc = reserve(rank_, BS * z.cap))) return rc;
+	if ((rc = reserve(mtfv_, BS * (size_t)z.mcap * 2))) return rc;
+	if ((rc = reserve(sel_, BS * (size_t)z.selcap * 2))) return rc;
+	if ((rc = reserve(out_, BS * (size_t)z.ocap + 16))) return rc;
 	if ((rc = reserve(scratch_, (size_t)grid * bwt_scratch_elems_per_cta(z.cap) * 4))) return rc;
 	if ((rc = reserve(payload_, pcap + 16))) return rc;
 	if ((rc = reserve(sizes_, count * 4))) return rc;
@@ -288,19 +335,20 @@ int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t 
 	for (uint64_t b0 = 0; b0 < count; b0 += B) {
 		const uint32_t nj = (uint32_t)std::min<uint64_t>(B, count - b0);
 		mark();
-		launch_rle1(d_sym, g, first + b0, nj, (uint8_t*)txt_.p, (uint8_t*)bwt_.p, z.cap, (uint32_t)blockBytes, (uint32_t)(100000 * z.level - 19), (EncJob*)jobs_.p, st);
+		const uint32_t ns = nj * z.nsub;                                       // job records of this batch
+		launch_rle1(d_sym, g, first + b0, nj, (uint8_t*)txt_.p, (uint8_t*)bwt_.p, z.cap, z.nsub, (uint32_t)blockBytes, z.nblock_max, (EncJob*)jobs_.p, st);
 		mark();
-		launch_bwt((uint8_t*)txt_.p, z.cap, (EncJob*)jobs_.p, nj, (uint8_t*)bwt_.p, (uint32_t*)scratch_.p,
-		           (int)std::min<uint32_t>(nj, (uint32_t)grid), z.text_in_smem, st);
+		launch_bwt((uint8_t*)txt_.p, z.cap, (EncJob*)jobs_.p, ns, (uint8_t*)bwt_.p, (uint32_t*)scratch_.p,
+		           (int)std::min<uint32_t>(ns, (uint32_t)grid), z.text_in_smem, st);
 		mark();
-		launch_mtf((uint8_t*)bwt_.p, (uint8_t*)rank_.p, z.cap, (EncJob*)jobs_.p, nj, (uint16_t*)mtfv_.p, z.mcap, st);
+		launch_mtf((uint8_t*)bwt_.p, (uint8_t*)rank_.p, z.cap, (EncJob*)jobs_.p, ns, (uint16_t*)mtfv_.p, z.mcap, st);
 		mark();
-		launch_huff_pack((uint16_t*)mtfv_.p, z.mcap, (EncJob*)jobs_.p, nj, (uint8_t*)sel_.p, z.selcap, (uint8_t*)out_.p, z.ocap, z.level, st);
-		k_offsets<<<1, 1024, 0, st>>>((EncJob*)jobs_.p, nj, tot, (uint64_t*)offs_.p, (uint32_t*)sizes_.p + b0, pcap);
-		k_compact<<<nj, 256, 0, st>>>((uint8_t*)out_.p, z.ocap, (uint64_t*)offs_.p, (uint32_t*)sizes_.p + b0, (uint8_t*)payload_.p, pcap);
+		launch_huff_pack((uint16_t*)mtfv_.p, z.mcap, (EncJob*)jobs_.p, ns, (uint8_t*)sel_.p, z.selcap, (uint8_t*)out_.p, z.ocap, z.level, st);
+		k_offsets<<<1, 1024, 0, st>>>((EncJob*)jobs_.p, nj, z.nsub, tot, (uint64_t*)offs_.p, (uint32_t*)sizes_.p + b0, pcap);
+		k_compact<<<nj, 256, 0, st>>>((uint8_t*)out_.p, z.ocap, (EncJob*)jobs_.p, z.nsub, (uint64_t*)offs_.p, (uint32_t*)sizes_.p + b0, (uint8_t*)payload_.p, pcap);
 		mark();
 		launches += 6;
-		last_njobs_ = nj;
+		last_njobs_ = ns;
 	}
 	last_cap_ = z.cap; last_mcap_ = z.mcap;
 	Totals h;
@@ -320,7 +368,7 @@ int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t 
 		stt->periodic_blocks += h.periodic;
 	}
 	if (h.overflow) { err_ = "payload buffer overflow"; return LFM_ERR_BZIP; }
-	if (h.err & 4u) { err_ = "a KLB block does not fit one bzip2 block after run-length coding (multi-block streams are not implemented)"; return LFM_ERR_UNSUPPORTED; }
+	if (h.err & 4u) { err_ = "a KLB block needs more bzip2 blocks than the engine reserves per stream"; return LFM_ERR_UNSUPPORTED; }
 	if (h.err) { err_ = "block encoder reported an error"; return LFM_ERR_BZIP; }
 	*d_payload = (const uint8_t*)payload_.p;
 	*payload_bytes = h.running;
@@ -350,22 +398,24 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 	cudaStream_t st = (cudaStream_t)stream_;
 	if (count == 0) return LFM_OK;
 	const Geom g = make_geom(s);
-	const EncSizes z = enc_sizes(s);
+	EncSizes z;
+	if (enc_sizes(s, z)) { err_ = "KLB block too large: more than kMaxSub bzip2 blocks per stream"; return LFM_ERR_UNSUPPORTED; }
 	uint64_t blockBytes = 2; for (int i = 0; i < 5; i++) blockBytes *= s.blockSize[i];
-	const size_t per_job = (size_t)z.cap * 2 + (size_t)z.mcap * 2 + sizeof(DecJob) + 24;
+	const size_t per_job = ((size_t)z.cap * 2 + (size_t)z.mcap * 2 + sizeof(DecJob) + 24) * z.nsub;
 	uint64_t B = std::min<uint64_t>(count, std::max<uint64_t>(1, ((size_t)6 << 30) / per_job));
 	B = std::min<uint64_t>(B, 32768);
-	const int grid = (int)std::min<uint64_t>(B, (uint64_t)sm_count_);
+	const uint64_t BS = B * z.nsub;                                            // job records per batch
+	const int grid = (int)std::min<uint64_t>(BS, (uint64_t)sm_count_);
 	int rc;
-	if ((rc = reserve(djobs_, B * sizeof(DecJob) + 16))) return rc;
-	if ((rc = reserve(bwt_, B * z.cap))) return rc;
-	if ((rc = reserve(txt_, B * z.cap))) return rc;
-	if ((rc = reserve(mtfv_, B * (size_t)z.mcap * 2))) return rc;
+	if ((rc = reserve(djobs_, BS * sizeof(DecJob) + 16))) return rc;
+	if ((rc = reserve(bwt_, BS * z.cap))) return rc;
+	if ((rc = reserve(txt_, BS * z.cap))) return rc;
+	if ((rc = reserve(mtfv_, BS * (size_t)z.mcap * 2))) return rc;
 	if ((rc = reserve(tt_, inv_bwt_scratch_elems(grid, z.cap) * 4))) return rc;
 	if ((rc = reserve(dbegin_, count * 8))) return rc;
 	if ((rc = reserve(dend_, count * 8))) return rc;
 	if ((rc = reserve(dids_, count * 8))) return rc;
-	uint32_t* flag = (uint32_t*)((uint8_t*)djobs_.p + B * sizeof(DecJob));
+	uint32_t* flag = (uint32_t*)((uint8_t*)djobs_.p + BS * sizeof(DecJob));
 	cudaMemsetAsync(flag, 0, 4, st);
 	cudaMemcpyAsync(dbegin_.p, begin, count * 8, cudaMemcpyHostToDevice, st);
 	cudaMemcpyAsync(dend_.p, end, count * 8, cudaMemcpyHostToDevice, st);
@@ -376,14 +426,15 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 	for (uint64_t b0 = 0; b0 < count; b0 += B) {
 		const uint32_t nj = (uint32_t)std::min<uint64_t>(B, count - b0);
 		mark();
-		if (launch_decode(d_payload, (uint64_t*)dbegin_.p + b0, (uint64_t*)dend_.p + b0, nj, (DecJob*)djobs_.p, (uint16_t*)mtfv_.p, z.mcap,
+		const uint32_t ns = nj * z.nsub;                                       // job records of this batch
+		if (launch_decode(d_payload, (uint64_t*)dbegin_.p + b0, (uint64_t*)dend_.p + b0, nj, z.nsub, (DecJob*)djobs_.p, (uint16_t*)mtfv_.p, z.mcap,
 		                  (uint8_t*)txt_.p, (uint8_t*)bwt_.p, z.cap, z.selcap, st)) { err_ = "decoder launch failed"; return LFM_ERR_UNSUPPORTED; }
 		mark();
-		launch_inv_bwt((uint8_t*)bwt_.p, z.cap, (DecJob*)djobs_.p, nj, (uint32_t*)tt_.p, (uint8_t*)txt_.p,
-		               (int)std::min<uint32_t>(nj, (uint32_t)grid), st);
+		launch_inv_bwt((uint8_t*)bwt_.p, z.cap, (DecJob*)djobs_.p, ns, (uint32_t*)tt_.p, (uint8_t*)txt_.p,
+		               (int)std::min<uint32_t>(ns, (uint32_t)grid), st);
 		mark();
-		launch_unrle((uint8_t*)txt_.p, (uint8_t*)bwt_.p, z.cap, (uint32_t)blockBytes, (DecJob*)djobs_.p, nj, d_sym, g, (uint64_t*)dids_.p + b0, st);
-		k_dec_status<<<(nj + 255) / 256, 256, 0, st>>>((DecJob*)djobs_.p, nj, flag);
+		launch_unrle((uint8_t*)txt_.p, (uint8_t*)bwt_.p, z.cap, z.nsub, (uint32_t)blockBytes, (DecJob*)djobs_.p, nj, d_sym, g, (uint64_t*)dids_.p + b0, st);
+		k_dec_status<<<(ns + 255) / 256, 256, 0, st>>>((DecJob*)djobs_.p, ns, flag);
 		mark();
 		launches += 5;
 	}

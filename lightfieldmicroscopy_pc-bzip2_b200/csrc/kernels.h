@@ -14,7 +14,7 @@ void launch_select(const uint16_t* const cand_ptrs[8], int ncand, uint64_t fpx, 
                    uint8_t* sorted, uint32_t sstride, uint32_t* hist, float* e_out, cudaStream_t st);
 // bz_encode.cu
 void launch_rle1(const uint16_t* sym, const Geom& g, uint64_t first_block, uint32_t njobs, uint8_t* txt, uint8_t* raw_scratch,
-                 uint32_t cap, uint32_t max_raw_bytes, uint32_t nblock_max, EncJob* jobs, cudaStream_t st);
+                 uint32_t cap, uint32_t nsub, uint32_t max_raw_bytes, uint32_t nblock_max, EncJob* jobs, cudaStream_t st);
 void launch_mtf(const uint8_t* bwt, uint8_t* rank_scratch, uint32_t cap, EncJob* jobs, uint32_t njobs, uint16_t* mtfv, uint32_t mcap, cudaStream_t st);
 void launch_huff_pack(const uint16_t* mtfv, uint32_t mcap, EncJob* jobs, uint32_t njobs, uint8_t* sel, uint32_t selcap,
                       uint8_t* out, uint32_t ocap, int level, cudaStream_t st);
@@ -24,12 +24,12 @@ size_t bwt_scratch_elems_per_cta(uint32_t cap);
 void launch_bwt(const uint8_t* txt, uint32_t cap, EncJob* jobs, uint32_t njobs, uint8_t* bwt, uint32_t* scratch,
                 int grid, int text_in_smem, cudaStream_t st);
 // bz_decode.cu
-int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t* end, uint32_t njobs, DecJob* jobs,
+int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t* end, uint32_t njobs, uint32_t nsub, DecJob* jobs,
                   uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap, cudaStream_t st);
 size_t inv_bwt_scratch_elems(int grid, uint32_t cap);
 void launch_inv_bwt(const uint8_t* bwt, uint32_t cap, DecJob* jobs, uint32_t njobs, uint32_t* tt_scratch, uint8_t* txt,
                     int grid, cudaStream_t st);
-void launch_unrle(const uint8_t* txt, uint8_t* stage_scratch, uint32_t cap, uint32_t max_raw_bytes, DecJob* jobs, uint32_t njobs,
+void launch_unrle(const uint8_t* txt, uint8_t* stage_scratch, uint32_t cap, uint32_t nsub, uint32_t max_raw_bytes, DecJob* jobs, uint32_t njobs,
                   uint16_t* sym, const Geom& g, const uint64_t* block_ids, cudaStream_t st);
 
 }  // namespace lfm

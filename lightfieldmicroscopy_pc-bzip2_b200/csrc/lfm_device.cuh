@@ -21,9 +21,17 @@ struct Geom {
 	uint64_t stride[5];   // in pixels
 };
 
-// one KLB block = one bzip2 stream; in this version exactly one bzip2 block per stream
+// One KLB block = one bzip2 stream = one or more bzip2 blocks (bzlib.c:  a block is closed once it holds
+// nblockMAX = 100000 * level - 19 run-length coded bytes).  A KLB block owns `nsub` consecutive job records ("sub-jobs",
+// one per possible bzip2 block, nsub = 1 for every block shape that fits one bzip2 block): record job * nsub + k describes
+// bzip2 block k of KLB block `job`; all per-block working arrays are strided by the sub-slot size.
+constexpr uint32_t kSubUnused = 1u;    // EncJob/DecJob.flags: this record holds no bzip2 block
+constexpr uint32_t kSubFirst  = 2u;    // first bzip2 block of its stream (the stream header precedes it)
+constexpr uint32_t kSubLast   = 4u;    // last bzip2 block of its stream (the stream trailer follows it)
+constexpr int kMaxSub = 32;            // bzip2 blocks per KLB block this engine handles
+
 struct EncJob {
-	uint32_t raw_bytes;    // bytes gathered from the image (gcount, klb_imageIO.cpp:146-151)
+	uint32_t raw_bytes;    // bytes gathered from the image (gcount, klb_imageIO.cpp:146-151) -- of the whole KLB block
 	uint32_t n;            // post-RLE1 length (nblock)
 	uint32_t crc;          // block CRC over the pre-RLE bytes
 	uint32_t orig_ptr;
@@ -31,11 +39,14 @@ struct EncJob {
 	uint32_t n_in_use;
 	uint32_t n_groups;
 	uint32_t n_sel;
-	uint32_t total_bits;   // bits of the whole stream before byte padding
-	uint32_t out_bytes;    // stream size
+	uint32_t total_bits;   // bits this record contributes to the stream (before byte padding)
+	uint32_t out_bytes;    // bytes of its slot that hold them
 	uint32_t periodic;
 	uint32_t status;       // 0 ok
 	uint32_t in_use[8];    // 256-bit map
+	uint32_t flags;        // kSub*
+	uint32_t stream_crc;   // last record of a stream: the combined CRC of all its blocks
+	uint32_t pad[2];
 };
 
 struct DecJob {
@@ -45,10 +56,11 @@ struct DecJob {
 	uint32_t orig_ptr;
 	uint32_t stored_crc;
 	uint32_t out_bytes;    // bytes produced by un-RLE1
-	uint32_t status;       // 0 ok, 1 bad magic, 2 corrupt, 3 crc mismatch, 4 unsupported (multi-block / randomised)
+	uint32_t status;       // 0 ok, 1 bad magic, 2 corrupt, 3 crc mismatch, 4 unsupported (randomised / too many blocks)
 	uint32_t level;
 	uint32_t max_block;
-	uint32_t pad[3];
+	uint32_t flags;        // kSub*
+	uint32_t pad[2];
 	uint32_t in_use[8];    // 256-bit symbol map of the block
 };
 

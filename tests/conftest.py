@@ -139,3 +139,30 @@ def has_cuda():
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+def multiblock_cases():
+    """byte strings (even length) whose bzip2 stream at the KLB level rule -- level = min(9, ceil(len / 100000)), one bzip2 block
+    holds 100000 * level - 19 run-length coded bytes -- has more than one block, or sits exactly on the rules that decide it
+    (bzlib.c:216-340: a block is closed by the record that fills it, unless only the last input byte is left)"""
+    rng = np.random.default_rng(77)
+    def norun(n):                     # no two equal neighbours: post-RLE1 length == n
+        a = rng.integers(0, 255, n, dtype=np.uint8)
+        a[1:][a[1:] == a[:-1]] += 1
+        for i in np.nonzero(a[1:] == a[:-1])[0]:
+            a[i + 1] = (int(a[i]) + 7) % 256
+        return a
+    M2 = 199981                       # level 2
+    c = {}
+    c["l2_exact_plus1"] = norun(M2 + 1).tobytes()                    # one byte past a full block: stays ONE block
+    c["l2_exact_plus3"] = norun(M2 + 3).tobytes()                    # second block of 3 bytes
+    t = norun(M2 + 3); t[-1] = t[-2]; c["l2_tail_run2"] = t.tobytes()   # what is left after the boundary is one 2-byte record
+    t = norun(M2 + 5); t[M2 - 3:M2 + 1] = 9; t[M2 - 4] = 8; t[M2 + 1] = 10
+    c["l2_run4_across"] = t.tobytes()                                 # a 4-run (5 output bytes) straddles the block limit
+    c["l2_runs4"] = np.repeat(rng.integers(0, 256, 50000, dtype=np.uint8), 4).tobytes()      # 200000 -> 250000 bytes: two blocks
+    c["l2_runs300"] = np.repeat(rng.integers(0, 256, 666, dtype=np.uint8), 300)[:199800].tobytes()  # long runs, 255-records
+    c["l1_poisson"] = rng.poisson(4, 49990).astype(np.uint16).tobytes()                       # level 1, just below one block
+    t = rng.integers(0, 256, 99996, dtype=np.uint8); c["l1_random_2blocks"] = t.tobytes()   # level 1: 99996 > 99981
+    c["l9_2MB_3blocks"] = rng.poisson(30, 1000000).astype(np.uint16).tobytes()              # level 9, three blocks
+    c["l9_1MB_runs"] = np.repeat(rng.integers(0, 256, 250000, dtype=np.uint8), 4).tobytes()  # level 9: 1 MB -> 1.25 MB, two blocks
+    return c

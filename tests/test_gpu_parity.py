@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, golden_img_tif, lf_synth
+from conftest import GOLDEN, golden_img_tif, lf_synth, multiblock_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -145,11 +145,46 @@ def test_large_klb_blocks_single_bzip2_block(L, oracle, tmp_path):
     L.write_stack(a, fg, header_version=8 + 4, nnum=13, block_size=(128, 128, 6, 1, 1), way=0)
     assert open(fo, "rb").read() == open(fg, "rb").read()
     assert np.array_equal(L.read_stack(fg, way=0), a)
-    # runs of exactly four equal bytes grow by 25 % under bzip2's first run-length stage: 245760 > 199981 -> refused with code 7
+    # runs of exactly four equal bytes grow by 25 % under bzip2's first run-length stage: 245760 > 199981 -> two bzip2 blocks per stream
     b = np.repeat(np.arange(6 * 256 * 256 // 2, dtype=np.uint32) % 251 * 257, 2).astype(np.uint16).reshape(6, 256, 256)
-    with pytest.raises(L.LfmError) as ei:
-        L.write_stack(b, fg, header_version=8, nnum=13, block_size=(128, 128, 6, 1, 1), way=0)
-    assert ei.value.code == 7
+    rc, shv = oracle.write(b, fo, 8, 13, 0, block_size=(128, 128, 6, 1, 1))
+    assert rc == 0
+    L.write_stack(b, fg, header_version=8, nnum=13, block_size=(128, 128, 6, 1, 1), way=0)
+    assert open(fo, "rb").read() == open(fg, "rb").read()
+    assert np.array_equal(L.read_stack(fg, way=0), b)
+
+
+@pytest.mark.parametrize("name", sorted(multiblock_cases().keys()))
+def test_multi_block_streams(L, oracle, tmp_path, name):
+    """one KLB block = one bzip2 stream of SEVERAL bzip2 blocks (block shapes above 100000 * level - 19 run-length coded bytes):
+    the stream in the file equals the oracle's / libbz2's for the same bytes and level (src/klb_imageIO.cpp:108, :217), and decodes back"""
+    data = multiblock_cases()[name]
+    a = np.frombuffer(data, np.uint16).reshape(1, 1, -1)
+    level = min(9, (len(data) + 99999) // 100000)
+    fn = str(tmp_path / "m.lfm")
+    L.write_stack(a, fn, header_version=8, nnum=13, block_size=(a.shape[2], 1, 1, 1, 1), way=0)
+    blob = open(fn, "rb").read()
+    assert blob[0] == 0                                   # predictor off: the block bytes are the raw pixels
+    assert blob[320 + 8:] == oracle.bz2_compress(data, level), "stream differs from the oracle (pinned to BZ2_bzBuffToBuffCompress)"
+    if name != "l2_exact_plus1":                          # libbz2's streaming API closes the block before the last byte there (test_oracle_bz2.py)
+        assert blob[320 + 8:] == bz2.compress(data, level), "stream differs from libbz2"
+    assert bz2.decompress(blob[320 + 8:]) == data
+    assert int.from_bytes(blob[320:328], "little") == len(blob) - 328
+    assert np.array_equal(L.read_stack(fn, way=0), a)
+
+
+def test_multi_block_streams_in_a_stack(L, oracle, tmp_path):
+    """a stack cut into 160x160x8 blocks (409600 bytes, level 5): mixed one- and two-block streams, border blocks, predictor on"""
+    rng = np.random.default_rng(12)
+    a = lf_synth((8, 300, 330), 13, seed=5)
+    a[:, :150, :170] = np.repeat(rng.integers(0, 60000, (8, 150, 85)), 2, axis=2).astype(np.uint16)    # pixel pairs: 4-byte runs
+    for hv, way in ((8, 0), (8 + 4, 0), (8 + 3, 2)):
+        fo, fg = str(tmp_path / "o.lfm"), str(tmp_path / "g.lfm")
+        rc, shv = oracle.write(a, fo, hv, 13, way, block_size=(160, 160, 8, 1, 1))
+        assert rc == 0
+        L.write_stack(a, fg, header_version=hv, nnum=13, block_size=(160, 160, 8, 1, 1), way=way)
+        assert open(fo, "rb").read() == open(fg, "rb").read(), (hv, way)
+        assert np.array_equal(L.read_stack(fg, way=way), a)
 
 
 def test_c_abi_entry_points(L, tmp_path):
