@@ -23,7 +23,7 @@ namespace lfm {
 //   * decoded symbols (RUNA/RUNB/rank+1/EOB) are gathered 32 at a time and stored coalesced.
 // Inverse move-to-front and run expansion are done in parallel by k_imtf.
 // =====================================================================================================
-constexpr int DEC_LB = 10;                       // lookup bits
+constexpr int DEC_LB = 10;                       // lookup bits (9 was measured: 12 KB -> 6 KB per warp, but 16-22 % more time per stream)
 constexpr int DEC_LUT = 1 << DEC_LB;
 
 struct DecWarpSmem {
@@ -37,10 +37,13 @@ struct DecWarpSmem {
 
 constexpr uint32_t DEC_RING = 256;               // staged stream words per warp (power of two)
 constexpr uint32_t DEC_OUT = 128;                // staged output symbols per warp (power of two)
+// selectors are kept as nibbles: shared memory per warp decides how many streams an SM decodes at once (the decoder is
+// pure latency: ~100 cycles per symbol and warp): ~21 KB per warp for 147 KB blocks -> 10 warps per SM
+__host__ __device__ inline size_t dec_sel_bytes(uint32_t selcap) { return (((size_t)selcap + 1) / 2 + 15) & ~(size_t)15; }
 
 extern __shared__ __align__(16) uint8_t dec_smem[];
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ begin, const uint64_t* __restrict__ end,
               uint32_t njobs, DecJob* __restrict__ jobs, uint16_t* __restrict__ mtfv_all, uint32_t mcap, uint32_t cap,
               uint32_t selcap, uint32_t nsub)
@@ -48,10 +51,10 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	const uint32_t lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
 	const uint32_t job = blockIdx.x * nw + w;
 	if (job >= njobs) return;
-	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)DEC_RING * 4 + (size_t)DEC_OUT * 2;
+	const size_t per_warp = sizeof(DecWarpSmem) + dec_sel_bytes(selcap) + (size_t)DEC_RING * 4 + (size_t)DEC_OUT * 2;
 	DecWarpSmem& S = *reinterpret_cast<DecWarpSmem*>(dec_smem + (size_t)w * per_warp);
 	uint8_t* selector = dec_smem + (size_t)w * per_warp + sizeof(DecWarpSmem);
-	uint32_t* sw = reinterpret_cast<uint32_t*>(selector + selcap);
+	uint32_t* sw = reinterpret_cast<uint32_t*>(selector + dec_sel_bytes(selcap));
 	uint16_t* so = reinterpret_cast<uint16_t*>(sw + DEC_RING);           // decoded symbols, flushed 32 at a time
 	// the stream's bzip2 blocks go to records job * nsub + kb (kb = 0, 1, ...); errors are reported in record 0
 	DecJob& J0 = jobs[(size_t)job * nsub];
@@ -145,7 +148,7 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 			uint32_t t = (pos >> (4 * j)) & 15u;
 			uint32_t lowmask = (1u << (4 * j)) - 1u;
 			pos = (pos & ~((lowmask << 4) | 15u)) | ((pos & lowmask) << 4) | t;
-			if (lane == 0) selector[i] = (uint8_t)t;
+			if (lane == 0) selector[i >> 1] = (i & 1) ? (uint8_t)((selector[i >> 1] & 15u) | (t << 4)) : (uint8_t)t;
 		}
 	}
 	for (int t = 0; t < n_groups; t++) {
@@ -209,7 +212,7 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	uint32_t hi = (uint32_t)(bb >> 32), lo = (uint32_t)bb;
 	for (int grp = 0; !done; grp++) {
 		if (grp >= n_sel) FAIL(2);
-		const int t = selector[grp];
+		const int t = (selector[grp >> 1] >> ((grp & 1) * 4)) & 15;
 		if (t >= n_groups) FAIL(2);
 		const uint16_t* lut = S.lut[t];
 		uint32_t k = 0;
@@ -761,8 +764,15 @@ k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* 
 int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t* end, uint32_t njobs, uint32_t nsub, DecJob* jobs,
                   uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap, cudaStream_t st)
 {
-	const size_t per_warp = sizeof(DecWarpSmem) + (size_t)selcap + (size_t)DEC_RING * 4 + (size_t)DEC_OUT * 2;
-	int nw = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
+	const size_t per_warp = sizeof(DecWarpSmem) + dec_sel_bytes(selcap) + (size_t)DEC_RING * 4 + (size_t)DEC_OUT * 2;
+	// warps per CTA: whatever puts the most streams on an SM (227 KB of shared memory, 1 KB reserved per CTA)
+	int nw = 0; size_t best = 0;
+	for (int c = 1; c <= 8; c++) {
+		const size_t cta = per_warp * c + 1024;
+		if (cta > 200 * 1024) break;
+		const size_t warps = std::min<size_t>(32, (227 * 1024) / cta) * c;
+		if (warps >= best) { best = warps; nw = c; }
+	}
 	if (nw < 1) return 1;
 	const size_t smem = per_warp * nw;
 	cudaFuncSetAttribute(k_huff_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
