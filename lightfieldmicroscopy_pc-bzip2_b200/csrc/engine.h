@@ -105,7 +105,11 @@ private:
 	Buf sel_sorted_, sel_hist_, sel_e_, sel_cand_;
 	uint32_t last_cap_ = 0, last_mcap_ = 0, last_njobs_ = 0;
 	void* pin_ = nullptr; size_t pin_cap_ = 0;
-	void* ev_[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	static constexpr int kMaxGroups = 4;   // forked streams a small batch is spread over
+	void* ev_[16] = { nullptr };          // 0-3 predictor timing, 4 fork, 5.. join of every group
+	std::vector<void*> aux_;               // forked streams
+	void* aux_stream(int i);
+	int groups_for(uint32_t nj) const;
 	std::vector<void*> ev_pool_;     // stage-timing events, created once and reused (event creation costs host time per call)
 	void* pooled_event(size_t i);
 };
