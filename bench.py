@@ -12,8 +12,9 @@ independent objects): weak scaling, no collective on the data path, value = all 
   value     device-resident: lfmCompressDevice / lfmDecompressDevice on frames already in HBM
   e2e       host buffers through the reference-facing C ABI (lfmCompressToMemory / lfmDecompressFromMemory =
             writeImage/readImageFull without the disk), H2D + D2H inside the timed region
-  roofline  dominant kernel (k_bwt): algorithmic bytes (post-RLE1 block in + last column out = 2 n per block) per
-            launch / mean launch time from CUDA events on the engine stream; peak = MEASURED_PEAKS.json hbm_gbs
+  roofline  the kernel with the largest device time of the step (picked from the stage times: k_huff_decode / k_huff_pack /
+            k_bwt ... -- every stage is ONE kernel launch per step): algorithmic bytes of that kernel's interface
+            per launch / mean launch time from CUDA events on the engine stream; peak = MEASURED_PEAKS.json hbm_gbs
   predictor_roofline  the HBM-bound kernels of the path (forward / inverse predictor) alone on a 32-frame stack, 4 B/px
   cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref, its CUDA predictor + threaded CPU bzip2,
             all host cores) on the same frame, file on /dev/shm; falls back to the oracle port if oracle/_ref is absent.
@@ -43,8 +44,13 @@ WORKLOADS = {
     "c5s": (16, 4096, 4096, 13, 0, 0, "configs[4] slice: 4096x4096x16 uint16 stack, Nnum=13, way tiles, 2-D entropy selection, 96x96x8 blocks (full decode)"),
 }
 POOL = 24
-# DRAM bytes of ONE k_bwt launch measured by ncu --set full (read + write), per workload (profiles/)
-NCU_TRAFFIC = {"c2": 20328960 + 89560064, "c3s": 4150188000 + 6526617000}
+# DRAM bytes of ONE launch measured by ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum), per (kernel, workload)
+NCU_TRAFFIC = {("k_bwt", "c2"): 20328960 + 89560064, ("k_bwt", "c3s"): 4150188000 + 6526617000}
+try:                                   # later captures: profiles/ncu_traffic.json  {"kernel:workload": bytes}
+    for _k, _v in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).items():
+        NCU_TRAFFIC[tuple(_k.split(":"))] = _v
+except Exception:
+    pass
 
 
 def synth_pool(nframes, H, W, nnum, count, rank):
@@ -202,7 +208,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    acc = dict(tc=0.0, td=0.0, pred=0.0, sel=0.0, bwt=0.0, rle=0.0, mtf=0.0, huff=0.0, dec=0.0, ibwt=0.0, unrle=0.0, unpred=0.0, launches=0, payload=0)
+    acc = dict(tc=0.0, td=0.0, pred=0.0, sel=0.0, bwt=0.0, rle=0.0, mtf=0.0, huff=0.0, dec=0.0, imtf=0.0, ibwt=0.0, unrle=0.0, unpred=0.0, launches=0, payload=0)
 
     def step_device(i, timed):
         d = dpool[i % POOL]
@@ -219,7 +225,7 @@ def main():
         if timed:
             acc["tc"] += t1 - t0; acc["td"] += t2 - t1
             acc["pred"] += sc.ms_predict; acc["sel"] += sc.ms_select; acc["unpred"] += sd.ms_unpredict; acc["bwt"] += sc.ms_bwt; acc["rle"] += sc.ms_rle; acc["mtf"] += sc.ms_mtf; acc["huff"] += sc.ms_huff
-            acc["dec"] += sd.ms_decode; acc["ibwt"] += sd.ms_ibwt; acc["unrle"] += sd.ms_unrle
+            acc["dec"] += sd.ms_decode; acc["imtf"] += sd.ms_imtf; acc["ibwt"] += sd.ms_ibwt; acc["unrle"] += sd.ms_unrle
             acc["launches"] += sc.gpu_launches + sd.gpu_launches; acc["payload"] += pb.value
         return d
 
@@ -303,9 +309,17 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         ratio = raw * args.steps / max(acc["payload"], 1)
         n_post_rle = raw                        # LF-synth frames have no long runs: post-RLE1 length == raw length within 0.1 %
-        bwt_ms = acc["bwt"] / args.steps
-        achieved = 2.0 * n_post_rle / (bwt_ms * 1e-3) / 1e9 if bwt_ms > 0 else 0.0
-        stage_ms = {k: acc[k] / args.steps for k in ("sel", "pred", "rle", "bwt", "mtf", "huff", "dec", "ibwt", "unrle", "unpred")}
+        comp = acc["payload"] / args.steps      # compressed bytes per step
+        stage_ms = {k: acc[k] / args.steps for k in ("sel", "pred", "rle", "bwt", "mtf", "huff", "dec", "imtf", "ibwt", "unrle", "unpred")}
+        # kernel behind every block-codec stage and the algorithmic bytes of its interface per launch:
+        # n = run-length coded block bytes (== raw here), comp = compressed bytes
+        kernels = {"rle": ("k_rle1", raw + n_post_rle), "bwt": ("k_bwt", 2 * n_post_rle), "mtf": ("k_mtf", 2 * n_post_rle),
+                   "huff": ("k_huff_pack", n_post_rle + comp), "dec": ("k_huff_decode", comp + n_post_rle), "imtf": ("k_imtf", 2 * n_post_rle),
+                   "ibwt": ("k_inv_bwt", 2 * n_post_rle), "unrle": ("k_unrle", n_post_rle + raw)}
+        top = max(kernels, key=lambda k: stage_ms[k])
+        kname, kbytes = kernels[top]
+        k_ms = stage_ms[top]
+        achieved = kbytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         try:
             rb = reference_round_trip(pool[:4], nnum, way, hv, 3, 1)
             cpu = {"value": rb["raw"] / (rb["tc"] + rb["td"]) / 1e9, "unit": "GB/s", "cores": rb["cores"], "kind": rb["kind"], "sample": rb["sample"],
@@ -321,12 +335,13 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": e2e["h2d"] // args.steps, "d2h_bytes_per_step": e2e["d2h"] // args.steps,
                         "compress_gbs": raw * args.steps / e2e["tc"] / 1e9, "decompress_gbs": raw * args.steps / e2e["td"] / 1e9},
                 "gpu_launches": int(acc["launches"]),
-                "roofline": {"bound": "hbm", "kernel": "k_bwt (rotation sort of all 96x96 blocks of the frame set, one launch; the largest kernel of the step)",
+                "roofline": {"bound": "hbm", "kernel": "%s (largest device time of the step: %.3f ms of %.3f ms; one launch over all %d KLB blocks)" % (kname, k_ms, ev_ms / args.steps, nb),
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": NCU_TRAFFIC.get(args.workload),
-                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_bwt, one launch, ncu --set full (profiles/r1_02_ncu_full_c2.md, r1_03_ncu_full_c3f_bwt_invbwt.md)",
-                             "peak_source": peak_src, "algorithmic_bytes_per_launch": 2 * n_post_rle, "launch_ms": bwt_ms,
-                             "note": "a block sort is latency / shared-memory bound, not HBM bound: the HBM roofline is quoted as the contract asks; the HBM-bound kernels of the path are the predictors, see predictor_roofline"},
+                             "traffic": NCU_TRAFFIC.get((kname, args.workload)),
+                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/)",
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": kbytes, "launch_ms": k_ms,
+                             "per_kernel": {kernels[k][0]: {"ms": stage_ms[k], "achieved_gbs": kernels[k][1] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else None} for k in kernels},
+                             "note": "the block codec (sort, entropy coding) is latency / shared-memory bound, not HBM bound: the HBM roofline is quoted as the contract asks; the HBM-bound kernels of the path are the predictors, see predictor_roofline"},
                 "predictor_roofline": None if pred_roof is None else dict(pred_roof, peak=peak, unit="GB/s",
                     frac={k: v["achieved_gbs"] / peak for k, v in pred_roof.get("runs", {}).items()}),
                 "cpu_baseline": cpu}

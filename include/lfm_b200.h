@@ -70,6 +70,7 @@ typedef struct {
 	uint64_t gpu_launches;    /* kernels launched */
 	uint64_t periodic_blocks; /* exactly periodic bzip2 blocks met (origPtr tie rule applied) */
 	uint64_t payload_bytes;
+	double ms_imtf;           /* inverse MTF + run expansion (ms_decode is the Huffman decode alone) */
 } lfm_stats;
 int lfmGetLastStats(lfm_stats* out);
 

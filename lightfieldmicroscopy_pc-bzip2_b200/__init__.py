@@ -42,7 +42,7 @@ class LfmStats(C.Structure):
                 ("ms_mtf", C.c_double), ("ms_huff", C.c_double), ("ms_decode", C.c_double), ("ms_ibwt", C.c_double),
                 ("ms_unrle", C.c_double), ("ms_unpredict", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double),
                 ("ms_total", C.c_double), ("gpu_launches", C.c_uint64), ("periodic_blocks", C.c_uint64),
-                ("payload_bytes", C.c_uint64)]
+                ("payload_bytes", C.c_uint64), ("ms_imtf", C.c_double)]
 
 
 # ---- prototypes (include/klb_Cwrapper.h, include/lfm_b200.h)

@@ -762,7 +762,8 @@ k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* 
 
 // ------------------------------------------------------------------------------------------------ launchers
 int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t* end, uint32_t njobs, uint32_t nsub, DecJob* jobs,
-                  uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap, cudaStream_t st)
+                  uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap, cudaStream_t st,
+                  cudaEvent_t between)
 {
 	const size_t per_warp = sizeof(DecWarpSmem) + dec_sel_bytes(selcap) + (size_t)DEC_RING * 4 + (size_t)DEC_OUT * 2;
 	// warps per CTA: whatever puts the most streams on an SM (227 KB of shared memory, 1 KB reserved per CTA)
@@ -777,6 +778,7 @@ int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t*
 	const size_t smem = per_warp * nw;
 	cudaFuncSetAttribute(k_huff_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	k_huff_decode<<<(njobs + nw - 1) / nw, nw * 32, smem, st>>>(payload, begin, end, njobs, jobs, mtfv, mcap, cap, selcap, nsub);
+	if (between) cudaEventRecord(between, st);               // stage timing: Huffman decode | inverse MTF
 	const size_t smem2 = imtf_smem_bytes();
 	cudaFuncSetAttribute(k_imtf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
 	k_imtf<<<njobs * nsub, IM_NT, smem2, st>>>(mtfv, mcap, jobs, njobs * nsub, q_scratch, bwt, cap);

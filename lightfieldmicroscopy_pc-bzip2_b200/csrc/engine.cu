@@ -468,8 +468,10 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 			uint8_t* gtxt = (uint8_t*)txt_.p + r0 * z.cap; uint8_t* gbwt = (uint8_t*)bwt_.p + r0 * z.cap;
 			uint16_t* gmtfv = (uint16_t*)mtfv_.p + r0 * z.mcap;
 			markg();
+			cudaEvent_t mid = nullptr;
+			if (stt) { mid = (cudaEvent_t)pooled_event(evs.size()); evs.push_back(mid); }      // recorded between k_huff_decode and k_imtf
 			if (launch_decode(d_payload, (uint64_t*)dbegin_.p + b0 + j0, (uint64_t*)dend_.p + b0 + j0, gj, z.nsub, gjobs, gmtfv, z.mcap,
-			                  gtxt, gbwt, z.cap, z.selcap, sg)) { err_ = "decoder launch failed"; return LFM_ERR_UNSUPPORTED; }
+			                  gtxt, gbwt, z.cap, z.selcap, sg, mid)) { err_ = "decoder launch failed"; return LFM_ERR_UNSUPPORTED; }
 			markg();
 			const int ggrid = (int)std::min<uint32_t>(gs, (uint32_t)grid);
 			launch_inv_bwt(gbwt, z.cap, gjobs, gs, (uint32_t*)tt_.p + (size_t)gi * inv_bwt_scratch_elems(grid, z.cap), gtxt, ggrid, sg);
@@ -486,11 +488,12 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 	cudaStreamSynchronize(st);
 	if ((rc = check("decompress_blocks"))) return rc;
 	if (stt) {
-		for (size_t i = 0; i + 3 < evs.size(); i += 4) {
+		for (size_t i = 0; i + 4 < evs.size(); i += 5) {
 			float ms;
 			cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); stt->ms_decode += ms;
-			cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]); stt->ms_ibwt += ms;
-			cudaEventElapsedTime(&ms, evs[i + 2], evs[i + 3]); stt->ms_unrle += ms;
+			cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]); stt->ms_imtf += ms;
+			cudaEventElapsedTime(&ms, evs[i + 2], evs[i + 3]); stt->ms_ibwt += ms;
+			cudaEventElapsedTime(&ms, evs[i + 3], evs[i + 4]); stt->ms_unrle += ms;
 		}
 		stt->launches += launches;
 	}

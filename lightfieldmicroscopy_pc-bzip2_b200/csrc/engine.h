@@ -38,7 +38,7 @@ struct CompressStats {
 	uint32_t periodic_blocks = 0;
 };
 struct DecompressStats {
-	double   ms_decode = 0, ms_ibwt = 0, ms_unrle = 0, ms_unpredict = 0, ms_total = 0;
+	double   ms_decode = 0, ms_imtf = 0, ms_ibwt = 0, ms_unrle = 0, ms_unpredict = 0, ms_total = 0;
 	uint64_t launches = 0;
 };
 

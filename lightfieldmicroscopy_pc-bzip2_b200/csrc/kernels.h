@@ -25,7 +25,8 @@ void launch_bwt(const uint8_t* txt, uint32_t cap, EncJob* jobs, uint32_t njobs, 
                 int grid, int text_in_smem, cudaStream_t st);
 // bz_decode.cu
 int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t* end, uint32_t njobs, uint32_t nsub, DecJob* jobs,
-                  uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap, cudaStream_t st);
+                  uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap, cudaStream_t st,
+                  cudaEvent_t between = nullptr);
 size_t inv_bwt_scratch_elems(int grid, uint32_t cap);
 void launch_inv_bwt(const uint8_t* bwt, uint32_t cap, DecJob* jobs, uint32_t njobs, uint32_t* tt_scratch, uint8_t* txt,
                     int grid, cudaStream_t st);

@@ -358,7 +358,7 @@ int decompress_core(const klb_image_header& h, const uint8_t* payload, uint64_t 
 	}
 	for (int d = 0; d < D; d++) {
 		if (rcs[d]) return rcs[d];
-		g_stats.ms_decode = std::max(g_stats.ms_decode, sts[d].ms_decode); g_stats.ms_ibwt = std::max(g_stats.ms_ibwt, sts[d].ms_ibwt);
+		g_stats.ms_decode = std::max(g_stats.ms_decode, sts[d].ms_decode); g_stats.ms_imtf = std::max(g_stats.ms_imtf, sts[d].ms_imtf); g_stats.ms_ibwt = std::max(g_stats.ms_ibwt, sts[d].ms_ibwt);
 		g_stats.ms_unrle = std::max(g_stats.ms_unrle, sts[d].ms_unrle); g_stats.ms_unpredict = std::max(g_stats.ms_unpredict, sts[d].ms_unpredict);
 		g_stats.ms_h2d = std::max(g_stats.ms_h2d, h2d[d]); g_stats.ms_d2h = std::max(g_stats.ms_d2h, d2h[d]);
 		g_stats.gpu_launches += sts[d].launches;
@@ -657,7 +657,7 @@ int lfmDecompressDevice(const void* d_payload, const uint64_t* blockOffset, uint
 		g_stats.ms_unpredict = e.last_unpredict_ms();
 	}
 	g_stats.predictor = k;
-	g_stats.ms_decode = st.ms_decode; g_stats.ms_ibwt = st.ms_ibwt; g_stats.ms_unrle = st.ms_unrle;
+	g_stats.ms_decode = st.ms_decode; g_stats.ms_imtf = st.ms_imtf; g_stats.ms_ibwt = st.ms_ibwt; g_stats.ms_unrle = st.ms_unrle;
 	g_stats.gpu_launches = st.launches;
 	return 0;
 }
