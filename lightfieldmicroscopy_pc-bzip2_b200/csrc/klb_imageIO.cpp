@@ -12,6 +12,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -238,9 +241,56 @@ int fetch_payload(std::vector<ShardOut>& shards, uint8_t* dst)
 }
 
 // ------------------------------------------------------------------------------------------------ decompress core
-// payload: pointer to the first payload byte (after the blockOffset table) in HOST memory
-int decompress_core(const klb_image_header& h, const uint8_t* payload, uint64_t payload_size, uint16_t* out, const klb_ROI* roi)
+// Where the block streams come from: a payload resident in HOST memory (first byte after the blockOffset table), or an open
+// file of which only the byte ranges a shard needs are read (pread) -- an ROI that touches a few slabs of a multi-GB file
+// costs the I/O of those slabs (the random-access use case of the KLB layout, src/klb_imageIO.cpp:524-763).
+struct PayloadSource {
+	const uint8_t* base = nullptr;      // memory-resident payload
+	int fd = -1; uint64_t file_off = 0; // or: file descriptor + offset of the payload inside the file
+	uint64_t size = 0;                  // payload bytes available
+	// the payload byte ranges [r.first, r.second) -> device memory, packed one after the other at dst, on stream st.  File sources
+	// go through two pinned staging buffers of the engine: chunk i+1 is read from the file while chunk i crosses PCIe.
+	// Returns 0, or LFM_ERR_BZIP on a short read.
+	int to_device(Engine& e, void* dst, const std::vector<std::pair<uint64_t, uint64_t>>& ranges, cudaStream_t st) const
+	{
+		uint64_t dpos = 0;
+		if (base) {
+			for (const auto& r : ranges) { cudaMemcpyAsync((uint8_t*)dst + dpos, base + r.first, r.second - r.first, cudaMemcpyHostToDevice, st); dpos += r.second - r.first; }
+			return LFM_OK;
+		}
+		const uint64_t CH = (uint64_t)32 << 20;
+		uint8_t* pin = (uint8_t*)e.pinned(2 * CH);
+		if (!pin) return LFM_ERR_CUDA;
+		cudaEvent_t ev[2]; cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+		int rc = LFM_OK;
+		uint64_t i = 0;
+		for (const auto& r : ranges) {
+			for (uint64_t off = r.first; off < r.second && rc == LFM_OK; off += CH, i++) {
+				const uint64_t len = std::min<uint64_t>(CH, r.second - off);
+				uint8_t* buf = pin + (i & 1) * CH;
+				if (i >= 2) cudaEventSynchronize(ev[i & 1]);          // the copy that last used this buffer has finished
+				uint64_t done = 0;
+				while (done < len) {
+					ssize_t got = pread(fd, buf + done, (size_t)(len - done), (off_t)(file_off + off + done));
+					if (got <= 0) { rc = LFM_ERR_BZIP; break; }
+					done += (uint64_t)got;
+				}
+				if (rc) break;
+				cudaMemcpyAsync((uint8_t*)dst + dpos, buf, len, cudaMemcpyHostToDevice, st);
+				cudaEventRecord(ev[i & 1], st);
+				dpos += len;
+			}
+			if (rc) break;
+		}
+		cudaStreamSynchronize(st);                                // the staging buffers are free again (they are shared with the write path)
+		cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+		return rc;
+	}
+};
+
+int decompress_core(const klb_image_header& h, const PayloadSource& psrc, uint16_t* out, const klb_ROI* roi)
 {
+	const uint64_t payload_size = psrc.size;
 	memset(&g_stats, 0, sizeof(g_stats));
 	int rc = validate(h, false);
 	if (rc) return rc;
@@ -295,30 +345,42 @@ int decompress_core(const klb_image_header& h, const uint8_t* payload, uint64_t 
 		for (uint64_t s : my) { uint64_t a, b; slab_frames(h, L, s, s + 1, a, b); f0 = std::min(f0, a); f1 = std::max(f1, b); }
 		if (k != 0 && video && (f0 & 1)) { rcs[d] = LFM_ERR_UNSUPPORTED; return; }   // odd block depth + video across shards
 		const uint64_t nf = f1 - f0 + 1;
-		// block list: all XY blocks of the slab when a predictor is in use (whole frames are needed), else only ROI hits
+		// block list.  Full read: every block.  ROI without predictor: the blocks that intersect it.  ROI with a predictor: every
+		// operand of the prediction rules lies up and/or left of the pixel (lfm_predict.cuh), so a pixel only depends on the
+		// pixels with x' <= x and y' <= y of its frame (and of the previous frame, video) -> the blocks that start at or before
+		// the ROI's lower right corner; what lies right of / below it keeps zero symbols and decodes to values nobody reads.
 		std::vector<uint64_t> ids, beg, end;
 		for (uint64_t s : my) for (uint64_t b = 0; b < L.blocksPerSlab; b++) {
-			if (k == 0 && !full) {
+			if (!full) {
 				uint64_t bx = b % L.nb[0], by = b / L.nb[0];
 				uint64_t x0 = bx * h.blockSize[0], x1 = std::min<uint64_t>(h.xyzct[0], x0 + h.blockSize[0]) - 1;
 				uint64_t y0 = by * h.blockSize[1], y1 = std::min<uint64_t>(h.xyzct[1], y0 + h.blockSize[1]) - 1;
-				if (x0 > ub[0] || x1 < lb[0] || y0 > ub[1] || y1 < lb[1]) continue;
+				if (x0 > ub[0] || y0 > ub[1]) continue;
+				if (k == 0 && (x1 < lb[0] || y1 < lb[1])) continue;
 			}
 			uint64_t id = s * L.blocksPerSlab + b;
 			ids.push_back(id); beg.push_back(id ? h.blockOffset[id - 1] : 0); end.push_back(h.blockOffset[id]);
 			if (end.back() < beg.back()) { rcs[d] = LFM_ERR_BZIP; return; }
 		}
-		const uint64_t p0 = beg.front(), p1 = end.back();      // ids ascend, so do the byte ranges
+		// byte ranges of the payload to fetch (runs of consecutive needed blocks), packed back to back on the device
+		std::vector<std::pair<uint64_t, uint64_t>> ranges;
+		uint64_t need_bytes = 0;
+		for (size_t i = 0; i < ids.size(); i++) {
+			if (!ranges.empty() && ranges.back().second == beg[i]) ranges.back().second = end[i];
+			else ranges.emplace_back(beg[i], end[i]);
+			const uint64_t len = end[i] - beg[i];
+			beg[i] = need_bytes; end[i] = need_bytes + len;           // position inside the packed device copy
+			need_bytes += len;
+		}
 		Engine& e = Engine::for_device(g_set.first_device + d);
 		cudaSetDevice(e.device());
 		cudaStream_t st = (cudaStream_t)e.stream();
-		if (e.reserve(e.user[UB_PAY], p1 - p0 + 16) || e.reserve(e.user[UB_SYM], nf * L.fpx * 2) || (k != 0 && e.reserve(e.user[UB_IMG], nf * L.fpx * 2))) { rcs[d] = LFM_ERR_CUDA; return; }
+		if (e.reserve(e.user[UB_PAY], need_bytes + 16) || e.reserve(e.user[UB_SYM], nf * L.fpx * 2) || (k != 0 && e.reserve(e.user[UB_IMG], nf * L.fpx * 2))) { rcs[d] = LFM_ERR_CUDA; return; }
 		struct { void* p; } dpay{ e.user[UB_PAY].p }, dsym{ e.user[UB_SYM].p }, dimg{ e.user[UB_IMG].p };
 		double t0 = now_ms();
-		cudaMemcpyAsync(dpay.p, payload + p0, p1 - p0, cudaMemcpyHostToDevice, st);
-		if (k == 0 && !full) cudaMemsetAsync(dsym.p, 0, nf * L.fpx * 2, st);
+		if ((rcs[d] = psrc.to_device(e, dpay.p, ranges, st))) { if (rcs[d] == LFM_ERR_BZIP) std::cerr << "ERROR: lfm_b200: file is truncated" << std::endl; return; }
+		if (!full) cudaMemsetAsync(dsym.p, 0, nf * L.fpx * 2, st);
 		h2d[d] = now_ms() - t0;
-		for (size_t i = 0; i < beg.size(); i++) { beg[i] -= p0; end[i] -= p0; }
 		uint16_t* sym_base = (uint16_t*)dsym.p - f0 * L.fpx;
 		rcs[d] = e.decompress_blocks((const uint8_t*)dpay.p, beg.data(), end.data(), ids.data(), ids.size(), sym_base, desc, &sts[d]);
 		if (rcs[d]) { g_err = e.last_error(); return; }
@@ -438,10 +500,12 @@ int klb_imageIO::readImageFromMemory(const char* fileBytes, size_t fileSize, cha
 	header.resizeBlockOffset(header.calculateNumBlocks());
 	if (fileSize < 320 + header.Nb * 8) return LFM_ERR_BZIP;
 	memcpy(header.blockOffset, fileBytes + 320, header.Nb * 8);
-	return decompress_core(header, (const uint8_t*)fileBytes + 320 + header.Nb * 8, fileSize - 320 - header.Nb * 8, (uint16_t*)imgOut, ROI);
+	PayloadSource ps; ps.base = (const uint8_t*)fileBytes + 320 + header.Nb * 8; ps.size = fileSize - 320 - header.Nb * 8;
+	return decompress_core(header, ps, (uint16_t*)imgOut, ROI);
 }
 
-static int read_file(const std::string& filename, klb_image_header& header, std::vector<uint8_t>& payload)
+// header (+ blockOffset table) of the file, then decode straight from the open file: only the needed byte ranges are read
+static int read_from_file(const std::string& filename, klb_image_header& header, uint16_t* out, const klb_ROI* roi)
 {
 	if (filename.empty()) { std::cerr << "ERROR: Filename has not been defined. We cannot read image" << std::endl; return LFM_ERR_OPEN; }
 	if (header.Nb == 0) {
@@ -449,32 +513,19 @@ static int read_file(const std::string& filename, klb_image_header& header, std:
 		if (err > 0) return err;
 		if (header.Nb == 0) { std::cerr << "ERROR: Image to read has not blocks" << std::endl; return LFM_ERR_BZIP; }
 	}
-	FILE* fid = fopen(filename.c_str(), "rb");
-	if (fid == NULL) { std::cout << "ERROR: blockUncompressor: thread opening file " << filename << std::endl; return LFM_ERR_OPEN; }
-	const uint64_t psize = header.blockOffset[header.Nb - 1];
-	payload.resize(psize);
-	fseek(fid, (long)header.getSizeInBytes(), SEEK_SET);
-	size_t got = fread(payload.data(), 1, psize, fid);
-	fclose(fid);
-	if (got != psize) { std::cerr << "ERROR: lfm_b200: file is truncated" << std::endl; return LFM_ERR_BZIP; }
-	return LFM_OK;
+	const int fd = open(filename.c_str(), O_RDONLY);
+	if (fd < 0) { std::cout << "ERROR: blockUncompressor: thread opening file " << filename << std::endl; return LFM_ERR_OPEN; }
+	struct stat sb;
+	PayloadSource ps; ps.fd = fd; ps.file_off = header.getSizeInBytes();
+	ps.size = (fstat(fd, &sb) == 0 && (uint64_t)sb.st_size > ps.file_off) ? (uint64_t)sb.st_size - ps.file_off : 0;
+	const int rc = decompress_core(header, ps, out, roi);
+	close(fd);
+	return rc;
 }
 
-int klb_imageIO::readImageFull(char* imgOut, int /*numThreads*/)
-{
-	std::vector<uint8_t> payload;
-	int rc = read_file(filename, header, payload);
-	if (rc) return rc;
-	return decompress_core(header, payload.data(), payload.size(), (uint16_t*)imgOut, NULL);
-}
+int klb_imageIO::readImageFull(char* imgOut, int /*numThreads*/) { return read_from_file(filename, header, (uint16_t*)imgOut, NULL); }
 
-int klb_imageIO::readImage(char* img, const klb_ROI* ROI, int /*numThreads*/)
-{
-	std::vector<uint8_t> payload;
-	int rc = read_file(filename, header, payload);
-	if (rc) return rc;
-	return decompress_core(header, payload.data(), payload.size(), (uint16_t*)img, ROI);
-}
+int klb_imageIO::readImage(char* img, const klb_ROI* ROI, int /*numThreads*/) { return read_from_file(filename, header, (uint16_t*)img, ROI); }
 
 // ------------------------------------------------------------------------------------------------ extension C ABI
 extern "C" {

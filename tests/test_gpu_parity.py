@@ -324,3 +324,22 @@ def test_inverse_band_pipeline_many_frames(L, shape_t):
                 assert torch.equal(back, d), (k, video)
     finally:
         L.set_way(prev if prev is not None and prev >= 0 else 0)
+
+
+def test_roi_reads_with_predictors(L, tmp_path):
+    """readImage(ROI) (src/klb_imageIO.cpp:2614-2682) on predicted files: only the slabs the ROI touches are fetched from the file
+    (byte-range reads) and, inside them, only the KLB blocks up / left of the ROI's lower right corner are decoded -- the
+    prediction rules never look right or down -- every way, image and video mode, random boxes, planes and single pixels"""
+    rng = np.random.default_rng(31)
+    a = (lf_synth((9, 150, 170), 13, seed=8).astype(np.int64) + rng.integers(0, 200, (9, 150, 170))).astype(np.uint16)
+    fn = str(tmp_path / "r.lfm")
+    for way, hv in ((0, 0), (0, 8 + 7), (0, 0x80 | 12), (0, 8 + 2), (1, 8 + 5), (1, 8 + 2), (2, 0), (2, 8 + 6), (0, 8)):
+        L.write_stack(a, fn, header_version=hv, nnum=13, block_size=(32, 32, 4, 1, 1), way=way)
+        boxes = [((0, 0, 0), (169, 149, 8)), ((0, 0, 4), (169, 149, 4)), ((169, 149, 8), (169, 149, 8)), ((0, 0, 0), (0, 0, 0)), ((5, 0, 3), (5, 149, 5))]
+        for _ in range(6):
+            lo = [int(rng.integers(0, n)) for n in (170, 150, 9)]
+            hi = [int(rng.integers(lo[i], n)) for i, n in enumerate((170, 150, 9))]
+            boxes.append((tuple(lo), tuple(hi)))
+        for lo, hi in boxes:
+            r = L.read_roi(fn, lo + (0, 0), hi + (0, 0), way=way)
+            assert np.array_equal(r[0, 0], a[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]), (way, hex(hv), lo, hi)
