@@ -114,6 +114,74 @@ struct DevMem {                   // RAII device allocation
 	int alloc(size_t n) { if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) { cudaGetLastError(); p = nullptr; return LFM_ERR_CUDA; } return 0; }
 };
 
+// ------------------------------------------------------------------------------------------------ pageable host memory
+// Callers of the reference API hand in malloc'ed (pageable) stacks.  A plain cudaMemcpy of such memory runs at ~5 GB/s (the
+// driver stages it through small internal buffers); here large copies go through four pinned staging buffers of the engine,
+// filled / drained by a few host threads while the previous chunk crosses PCIe.  Pinned or registered memory (bench.py's e2e
+// buffers) takes the direct path.
+bool is_pageable(const void* p)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+	return a.type == cudaMemoryTypeUnregistered;
+}
+void par_memcpy(void* dst, const void* src, size_t n)
+{
+	const int nt = 4;
+	if (n < ((size_t)4 << 20)) { memcpy(dst, src, n); return; }
+	std::thread th[nt - 1];
+	const size_t part = (n / nt + 63) & ~(size_t)63;
+	for (int i = 1; i < nt; i++) {
+		const size_t o = std::min(n, part * i), len = std::min(n, part * (i + 1)) - o;
+		th[i - 1] = std::thread([=]() { if (len) memcpy((uint8_t*)dst + o, (const uint8_t*)src + o, len); });
+	}
+	memcpy(dst, src, std::min(n, part));
+	for (int i = 1; i < nt; i++) th[i - 1].join();
+}
+constexpr size_t kStageChunk = (size_t)8 << 20;
+constexpr int kStageBufs = 4;
+
+void h2d_staged(Engine& e, void* dst, const void* src, size_t bytes, cudaStream_t st)
+{
+	uint8_t* pin = (bytes >= 2 * kStageChunk && is_pageable(src)) ? (uint8_t*)e.pinned(kStageBufs * kStageChunk) : nullptr;
+	if (!pin) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st); return; }
+	cudaEvent_t ev[kStageBufs];
+	for (auto& x : ev) cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+	size_t i = 0;
+	for (size_t off = 0; off < bytes; off += kStageChunk, i++) {
+		const size_t len = std::min(kStageChunk, bytes - off);
+		uint8_t* buf = pin + (i % kStageBufs) * kStageChunk;
+		if (i >= (size_t)kStageBufs) cudaEventSynchronize(ev[i % kStageBufs]);
+		par_memcpy(buf, (const uint8_t*)src + off, len);
+		cudaMemcpyAsync((uint8_t*)dst + off, buf, len, cudaMemcpyHostToDevice, st);
+		cudaEventRecord(ev[i % kStageBufs], st);
+	}
+	cudaStreamSynchronize(st);                                   // the staging buffers are shared: free them before anyone else asks
+	for (auto& x : ev) cudaEventDestroy(x);
+}
+
+void d2h_staged(Engine& e, void* dst, const void* src, size_t bytes, cudaStream_t st)
+{
+	uint8_t* pin = (bytes >= 2 * kStageChunk && is_pageable(dst)) ? (uint8_t*)e.pinned(kStageBufs * kStageChunk) : nullptr;
+	if (!pin) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st); return; }
+	cudaEvent_t ev[kStageBufs];
+	for (auto& x : ev) cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+	const size_t nch = (bytes + kStageChunk - 1) / kStageChunk;
+	auto issue = [&](size_t i) {
+		const size_t off = i * kStageChunk, len = std::min(kStageChunk, bytes - off);
+		cudaMemcpyAsync(pin + (i % kStageBufs) * kStageChunk, (const uint8_t*)src + off, len, cudaMemcpyDeviceToHost, st);
+		cudaEventRecord(ev[i % kStageBufs], st);
+	};
+	for (size_t i = 0; i < std::min<size_t>(nch, kStageBufs - 1); i++) issue(i);
+	for (size_t i = 0; i < nch; i++) {
+		if (i + kStageBufs - 1 < nch) issue(i + kStageBufs - 1);   // its buffer was drained in the previous iteration
+		cudaEventSynchronize(ev[i % kStageBufs]);
+		const size_t off = i * kStageChunk, len = std::min(kStageChunk, bytes - off);
+		par_memcpy((uint8_t*)dst + off, pin + (i % kStageBufs) * kStageChunk, len);
+	}
+	for (auto& x : ev) cudaEventDestroy(x);
+}
+
 // ------------------------------------------------------------------------------------------------ compress core
 struct ShardOut {
 	std::vector<uint32_t> sizes; int rc = 0; CompressStats st; double ms_h2d = 0, ms_d2h = 0;
@@ -178,7 +246,7 @@ int compress_core(const FrameSource& src, klb_image_header& h, std::vector<Shard
 		if (e.reserve(e.user[UB_IMG], nf * L.fpx * 2) || (k != 0 && e.reserve(e.user[UB_SYM], nf * L.fpx * 2))) { out.rc = LFM_ERR_CUDA; return; }
 		uint16_t* dimg = (uint16_t*)e.user[UB_IMG].p; uint16_t* dsym = (uint16_t*)e.user[UB_SYM].p;
 		double t0 = now_ms();
-		if (src.base) cudaMemcpyAsync(dimg, src.frame(f0, L.fpx), nf * L.fpx * 2, cudaMemcpyHostToDevice, st);
+		if (src.base) h2d_staged(e, dimg, src.frame(f0, L.fpx), nf * L.fpx * 2, st);
 		else for (uint64_t f = 0; f < nf; f++) cudaMemcpyAsync(dimg + f * L.fpx, src.frame(f0 + f, L.fpx), L.fpx * 2, cudaMemcpyHostToDevice, st);
 		const uint16_t* img_base = dimg - f0 * L.fpx;       // virtual base: absolute frame indexing
 		const uint16_t* sym_base = img_base;
@@ -395,7 +463,7 @@ int decompress_core(const klb_image_header& h, const PayloadSource& psrc, uint16
 		if (full) {
 			// this shard's frames, contiguous in the output
 			uint64_t a, b; slab_frames(h, L, my.front(), my.back() + 1, a, b);
-			cudaMemcpyAsync(out + a * L.fpx, res_base + a * L.fpx, (b - a + 1) * L.fpx * 2, cudaMemcpyDeviceToHost, st);
+			d2h_staged(e, out + a * L.fpx, res_base + a * L.fpx, (b - a + 1) * L.fpx * 2, st);
 		} else {
 			// crop: ROI rows are contiguous runs of (ub0-lb0+1) pixels
 			const uint64_t rx = ub[0] - lb[0] + 1, ry = ub[1] - lb[1] + 1;

@@ -343,3 +343,20 @@ def test_roi_reads_with_predictors(L, tmp_path):
         for lo, hi in boxes:
             r = L.read_roi(fn, lo + (0, 0), hi + (0, 0), way=way)
             assert np.array_equal(r[0, 0], a[lo[2]:hi[2] + 1, lo[1]:hi[1] + 1, lo[0]:hi[0] + 1]), (way, hex(hv), lo, hi)
+
+
+def test_pageable_stacks_take_the_staged_copy_path(L, tmp_path):
+    """callers of the reference API pass malloc'ed stacks: copies of >= 16 MB of pageable memory go through the engine's pinned
+    staging buffers (klb_imageIO.cpp h2d_staged / d2h_staged).  Same file bytes as with pinned buffers (direct DMA), exact read back."""
+    import torch
+    a = lf_synth((3, 2048, 2048), 13, seed=17)                       # 25 MB, pageable numpy memory
+    fn = str(tmp_path / "p.lfm")
+    L.write_stack(a, fn, header_version=8 + 4, nnum=13, way=0)
+    hin = torch.from_numpy(a.view(np.int16)).pin_memory()
+    blob = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+    n = L.compress_into(hin.numpy().view(np.uint16), blob.numpy(), header_version=8 + 4, nnum=13, way=0)
+    assert open(fn, "rb").read() == blob.numpy()[:n].tobytes()
+    assert np.array_equal(L.read_stack(fn, way=0), a)
+    back = np.empty_like(a)
+    L.decompress_into(blob.numpy(), n, back, way=0)                  # pinned source, pageable destination
+    assert np.array_equal(back, a)
