@@ -339,7 +339,8 @@ int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t 
 	if ((rc = reserve(mtfv_, BS * (size_t)z.mcap * 2))) return rc;
 	if ((rc = reserve(sel_, BS * (size_t)z.selcap * 2))) return rc;
 	if ((rc = reserve(out_, BS * (size_t)z.ocap + 16))) return rc;
-	if ((rc = reserve(scratch_, (size_t)kMaxGroups * grid * bwt_scratch_elems_per_cta(z.cap) * 4))) return rc;
+	const int Gres = groups_for((uint32_t)B);                                  // forked groups need a scratch region each
+	if ((rc = reserve(scratch_, (size_t)Gres * grid * bwt_scratch_elems_per_cta(z.cap) * 4))) return rc;
 	if ((rc = reserve(payload_, pcap + 16))) return rc;
 	if ((rc = reserve(sizes_, count * 4))) return rc;
 	if ((rc = reserve(offs_, B * 8 + sizeof(Totals)))) return rc;
@@ -442,7 +443,7 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 	if ((rc = reserve(bwt_, BS * z.cap))) return rc;
 	if ((rc = reserve(txt_, BS * z.cap))) return rc;
 	if ((rc = reserve(mtfv_, BS * (size_t)z.mcap * 2))) return rc;
-	if ((rc = reserve(tt_, (size_t)kMaxGroups * inv_bwt_scratch_elems(grid, z.cap) * 4))) return rc;
+	if ((rc = reserve(tt_, (size_t)groups_for((uint32_t)B) * inv_bwt_scratch_elems(grid, z.cap) * 4))) return rc;
 	if ((rc = reserve(dbegin_, count * 8))) return rc;
 	if ((rc = reserve(dend_, count * 8))) return rc;
 	if ((rc = reserve(dids_, count * 8))) return rc;
