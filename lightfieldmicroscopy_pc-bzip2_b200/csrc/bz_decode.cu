@@ -294,6 +294,46 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	#undef FAIL
 }
 
+// Sequential per-thread readers over global arrays: a thread that walks its chunk element by element pays one memory
+// latency per element (ncu: 77-97 % long-scoreboard stalls on those lines); these fetch 16 bytes at a time with one block of
+// lookahead, the element comes out of registers.  Bases are 16-byte aligned (job slots), `lim` = first element never needed.
+struct HalfReader {
+	const uint4* base; uint32_t blk, lim; uint4 cur, nxt;
+	__device__ __forceinline__ void init(const uint16_t* p, uint32_t i, uint32_t lim_) {
+		base = reinterpret_cast<const uint4*>(p); lim = lim_; blk = i >> 3; cur = base[blk];
+		nxt = ((blk + 1) << 3) < lim ? base[blk + 1] : make_uint4(0, 0, 0, 0);
+	}
+	__device__ __forceinline__ uint32_t get(uint32_t i) {
+		const uint32_t b = i >> 3;
+		if (b != blk) {
+			cur = (b == blk + 1) ? nxt : base[b];
+			blk = b;
+			nxt = ((b + 1) << 3) < lim ? base[b + 1] : make_uint4(0, 0, 0, 0);
+		}
+		const uint32_t w = (i >> 1) & 3u;
+		const uint32_t v = w == 0 ? cur.x : w == 1 ? cur.y : w == 2 ? cur.z : cur.w;
+		return (v >> ((i & 1u) * 16u)) & 0xffffu;
+	}
+};
+struct ByteReader {
+	const uint4* base; uint32_t blk, lim; uint4 cur, nxt;
+	__device__ __forceinline__ void init(const uint8_t* p, uint32_t i, uint32_t lim_) {
+		base = reinterpret_cast<const uint4*>(p); lim = lim_; blk = i >> 4; cur = base[blk];
+		nxt = ((blk + 1) << 4) < lim ? base[blk + 1] : make_uint4(0, 0, 0, 0);
+	}
+	__device__ __forceinline__ uint32_t get(uint32_t i) {
+		const uint32_t b = i >> 4;
+		if (b != blk) {
+			cur = (b == blk + 1) ? nxt : base[b];
+			blk = b;
+			nxt = ((b + 1) << 4) < lim ? base[b + 1] : make_uint4(0, 0, 0, 0);
+		}
+		const uint32_t w = (i >> 2) & 3u;
+		const uint32_t v = w == 0 ? cur.x : w == 1 ? cur.y : w == 2 ? cur.z : cur.w;
+		return (v >> ((i & 3u) * 8u)) & 0xffu;
+	}
+};
+
 // =====================================================================================================
 // k_imtf : one CTA per block -- run expansion + inverse move-to-front, in parallel over chunks of symbols.
 // A chunk's effect on the list is a permutation that does not depend on the list it starts from, so
@@ -370,11 +410,19 @@ k_imtf(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, DecJob* __restrict_
 	{
 		uint32_t* my = st + tid;
 		uint32_t i = a0;
+		HalfReader rd;
+		if (a0 < a1) rd.init(mtfv, a0, a1);
 		while (i < a1) {
-			const uint32_t sym = mtfv[i];
+			uint32_t sym = rd.get(i);
 			if (sym <= 1) {                                   // a whole run: bijective base 2
 				uint32_t run = 0, wgt = 1;
-				while (i < a1 && mtfv[i] <= 1) { run += (mtfv[i] + 1u) * wgt; wgt <<= 1; i++; if (run > max_block) { bad = true; break; } }
+				for (;;) {
+					run += (sym + 1u) * wgt; wgt <<= 1; i++;
+					if (run > max_block) { bad = true; break; }
+					if (i >= a1) break;
+					sym = rd.get(i);
+					if (sym > 1) break;
+				}
 				if (bad) break;
 				outc += run;
 				continue;
@@ -421,11 +469,18 @@ k_imtf(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, DecJob* __restrict_
 		uint32_t o = inc - outc;
 		uint32_t front = unseq[ST_BYTE(0, tid)];
 		uint32_t i = a0;
+		HalfReader rd;
+		if (a0 < a1) rd.init(mtfv, a0, a1);
 		while (i < a1) {
-			const uint32_t sym = mtfv[i];
+			uint32_t sym = rd.get(i);
 			if (sym <= 1) {
 				uint32_t run = 0, wgt = 1;
-				while (i < a1 && mtfv[i] <= 1) { run += (mtfv[i] + 1u) * wgt; wgt <<= 1; i++; }
+				for (;;) {
+					run += (sym + 1u) * wgt; wgt <<= 1; i++;
+					if (i >= a1) break;
+					sym = rd.get(i);
+					if (sym > 1) break;
+				}
 				for (uint32_t k = 0; k < run; k++) L[o + k] = (uint8_t)front;
 				o += run;
 				continue;
@@ -665,8 +720,10 @@ k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* 
 			// all five entry states in one pass over the chunk (each byte is loaded once)
 			uint32_t st[5] = { 0, 1, 2, 3, 4 }, cn[5] = { 0, 0, 0, 0, 0 };
 			uint32_t prev = a0 > 0 ? txt[a0 - 1] : 0x100u;
+			ByteReader rd;
+			if (a0 < a1) rd.init(txt, a0, a1);
 			for (uint32_t i = a0; i < a1; i++) {
-				const uint32_t ch = txt[i];
+				const uint32_t ch = rd.get(i);
 				const bool eq = (ch == prev);
 				#pragma unroll
 				for (int m = 0; m < 5; m++) {
@@ -714,10 +771,14 @@ k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* 
 		// ---- 3. replay into the staging copy
 		{
 			uint32_t st = s_in[tid], o = obase + s_off[tid];
+			uint32_t pv = a0 > 0 ? txt[a0 - 1] : 0x100u;             // the byte before (never equal to a byte at the block start)
+			ByteReader rd;
+			if (a0 < a1) rd.init(txt, a0, a1);
 			for (uint32_t i = a0; i < a1; i++) {
-				const uint32_t ch = txt[i];
-				if (st == 4) { const uint32_t pv = txt[i - 1]; for (uint32_t k = 0; k < ch; k++) stage[o + k] = (uint8_t)pv; o += ch; st = 0; }
-				else { st = (st >= 1 && i > 0 && ch == txt[i - 1]) ? st + 1 : 1; stage[o++] = (uint8_t)ch; }
+				const uint32_t ch = rd.get(i);
+				if (st == 4) { for (uint32_t k = 0; k < ch; k++) stage[o + k] = (uint8_t)pv; o += ch; st = 0; }
+				else { st = (st >= 1 && ch == pv) ? st + 1 : 1; stage[o++] = (uint8_t)ch; }
+				pv = ch;
 			}
 		}
 		__syncthreads();
