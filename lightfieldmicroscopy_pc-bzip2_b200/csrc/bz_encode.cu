@@ -278,6 +278,30 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 //   4. zero runs -> RUNA/RUNB (bijective base 2) with the run carried across chunk borders, output offsets by a
 //      block scan, symbols written to mtfv.   (compress.c:121-232)
 // =====================================================================================================
+// Sequential per-thread reader of 32-bit words (forward or backward) through 16-byte register windows with one block of
+// lookahead: a thread walking its chunk word by word pays one global-memory latency per word otherwise (ncu: 88-94 %
+// long-scoreboard stalls on the re-reads of the rank scratch).  `lim` = number of words that may be touched (16-byte blocks
+// that start below it are loaded whole: slots are 16-byte aligned and padded).
+template <int DIR>
+struct WordReader {
+	const uint4* base; uint32_t blk, lim; uint4 cur, nxt;
+	__device__ __forceinline__ uint4 fetch(uint32_t b) const { return (b << 2) < lim ? base[b] : make_uint4(0, 0, 0, 0); }
+	__device__ __forceinline__ void init(const uint32_t* p, uint32_t w, uint32_t lim_) {
+		base = reinterpret_cast<const uint4*>(p); lim = lim_; blk = w >> 2; cur = fetch(blk);
+		nxt = (DIR > 0) ? fetch(blk + 1) : (blk ? fetch(blk - 1) : make_uint4(0, 0, 0, 0));
+	}
+	__device__ __forceinline__ uint32_t get(uint32_t w) {
+		const uint32_t b = w >> 2;
+		if (b != blk) {
+			cur = (b == blk + (uint32_t)DIR) ? nxt : fetch(b);
+			blk = b;
+			nxt = (DIR > 0) ? fetch(b + 1) : (b ? fetch(b - 1) : make_uint4(0, 0, 0, 0));
+		}
+		const uint32_t k = w & 3u;
+		return k == 0 ? cur.x : k == 1 ? cur.y : k == 2 ? cur.z : cur.w;
+	}
+};
+
 constexpr int MTF_NT = 128;
 constexpr int MTF_STS = MTF_NT + 1;        // word row stride of the packed start states
 
@@ -332,8 +356,11 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 	#pragma unroll
 	for (int k = 0; k < 8; k++) seen[k * MTF_NT + tid] = 0;
 	uint32_t my_cnt = 0;
+	const uint32_t nwords = (n + 3) >> 2;
+	WordReader<-1> rb;
+	if (c0 < c1) rb.init(bwt32, (((c1 + 3) & ~3u) - 4) >> 2, nwords);
 	for (uint32_t i4 = (c0 < c1) ? ((c1 + 3) & ~3u) : c0; i4 > c0; i4 -= 4) {   // a non-empty chunk starts on a multiple of 4
-		const uint32_t word = bwt32[(i4 - 4) >> 2];
+		const uint32_t word = rb.get((i4 - 4) >> 2);
 		#pragma unroll
 		for (int k = 3; k >= 0; k--) {
 			if (i4 - 4 + k < c1) {
@@ -375,8 +402,10 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 	{
 		uint32_t* my = st + tid;                               // word w of my list: my[w * STS]
 		uint32_t front = my[0] & 255u;
+		WordReader<1> rf;
+		if (c0 < c1) rf.init(bwt32, c0 >> 2, nwords);
 		for (uint32_t i4 = c0; i4 < c1; i4 += 4) {
-			const uint32_t inw = bwt32[i4 >> 2];
+			const uint32_t inw = rf.get(i4 >> 2);
 			uint32_t outw = 0;
 			#pragma unroll
 			for (int k = 0; k < 4; k++) {
@@ -415,8 +444,10 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 	uint32_t lead = 0, trail = 0;                            // leading / trailing zero ranks of my chunk
 	{
 		bool open = true;
+		WordReader<1> rr1;
+		if (c0 < c1) rr1.init(rk32, c0 >> 2, nwords);
 		for (uint32_t i4 = c0; i4 < c1; i4 += 4) {
-			const uint32_t w = rk32[i4 >> 2];
+			const uint32_t w = rr1.get(i4 >> 2);
 			#pragma unroll
 			for (int k = 0; k < 4; k++) if (i4 + k < c1) {
 				const bool z0 = ((w >> (8 * k)) & 255u) == 0;
@@ -451,8 +482,10 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 	uint32_t outc = 0;
 	{
 		uint32_t z = zin_mine;
+		WordReader<1> rr2;
+		if (c0 < c1) rr2.init(rk32, c0 >> 2, nwords);
 		for (uint32_t i4 = c0; i4 < c1; i4 += 4) {
-			const uint32_t w = rk32[i4 >> 2];
+			const uint32_t w = rr2.get(i4 >> 2);
 			#pragma unroll
 			for (int k = 0; k < 4; k++) if (i4 + k < c1) {
 				if (((w >> (8 * k)) & 255u) == 0) z++;
@@ -472,8 +505,10 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 			uint32_t q = zz - 1;
 			for (;;) { mtfv[o++] = (uint16_t)(q & 1u); if (q < 2) break; q = (q - 2) >> 1; }
 		};
+		WordReader<1> rr3;
+		if (c0 < c1) rr3.init(rk32, c0 >> 2, nwords);
 		for (uint32_t i4 = c0; i4 < c1; i4 += 4) {
-			const uint32_t w = rk32[i4 >> 2];
+			const uint32_t w = rr3.get(i4 >> 2);
 			#pragma unroll
 			for (int k = 0; k < 4; k++) if (i4 + k < c1) {
 				const uint32_t r = (w >> (8 * k)) & 255u;
