@@ -722,7 +722,11 @@ k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* 
 			uint32_t prev = a0 > 0 ? txt[a0 - 1] : 0x100u;
 			ByteReader rd;
 			if (a0 < a1) rd.init(txt, a0, a1);
-			for (uint32_t i = a0; i < a1; i++) {
+			// the five machines fall into step at the first run break that none of them reads as a count byte (a handful of
+			// bytes into the chunk): from there on ONE machine is simulated and its byte count added to all five
+			uint32_t i = a0;
+			bool same = false;
+			for (; i < a1 && !same; i++) {
 				const uint32_t ch = rd.get(i);
 				const bool eq = (ch == prev);
 				#pragma unroll
@@ -731,6 +735,18 @@ k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* 
 					else { st[m] = (st[m] >= 1 && eq) ? st[m] + 1 : 1; cn[m]++; }
 				}
 				prev = ch;
+				same = (st[0] == st[1]) & (st[1] == st[2]) & (st[2] == st[3]) & (st[3] == st[4]);
+			}
+			if (same) {
+				uint32_t s1 = st[0], c1 = 0;
+				for (; i < a1; i++) {
+					const uint32_t ch = rd.get(i);
+					if (s1 == 4) { c1 += ch; s1 = 0; }
+					else { s1 = (s1 >= 1 && ch == prev) ? s1 + 1 : 1; c1++; }
+					prev = ch;
+				}
+				#pragma unroll
+				for (int m = 0; m < 5; m++) { st[m] = s1; cn[m] += c1; }
 			}
 			uint32_t fn = 0;
 			#pragma unroll
