@@ -315,24 +315,6 @@ struct HalfReader {
 		return (v >> ((i & 1u) * 16u)) & 0xffffu;
 	}
 };
-struct ByteReader {
-	const uint4* base; uint32_t blk, lim; uint4 cur, nxt;
-	__device__ __forceinline__ void init(const uint8_t* p, uint32_t i, uint32_t lim_) {
-		base = reinterpret_cast<const uint4*>(p); lim = lim_; blk = i >> 4; cur = base[blk];
-		nxt = ((blk + 1) << 4) < lim ? base[blk + 1] : make_uint4(0, 0, 0, 0);
-	}
-	__device__ __forceinline__ uint32_t get(uint32_t i) {
-		const uint32_t b = i >> 4;
-		if (b != blk) {
-			cur = (b == blk + 1) ? nxt : base[b];
-			blk = b;
-			nxt = ((b + 1) << 4) < lim ? base[b + 1] : make_uint4(0, 0, 0, 0);
-		}
-		const uint32_t w = (i >> 2) & 3u;
-		const uint32_t v = w == 0 ? cur.x : w == 1 ? cur.y : w == 2 ? cur.z : cur.w;
-		return (v >> ((i & 3u) * 8u)) & 0xffu;
-	}
-};
 
 // =====================================================================================================
 // k_imtf : one CTA per block -- run expansion + inverse move-to-front, in parallel over chunks of symbols.

@@ -241,11 +241,15 @@ k_rle1(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, uint32_t 
 		__syncthreads();
 		s_a[tid] = crc;
 		__syncthreads();
-		uint32_t M = crc_xpow8(CC);                                     // x^(8 CC): shift by one full chunk
-		for (uint32_t stride = 1; stride < NT; stride <<= 1) {
-			if ((tid & (2 * stride - 1)) == 0) s_a[tid] = crc_mulmod(s_a[tid], M) ^ s_a[tid + stride];
-			M = crc_mulmod(M, M);
-			__syncthreads();
+		// x^(8 CC 2^k) mod P for the k-th tree level: thread k squares k times (instead of every thread squaring at every level)
+		if (tid < 12) { uint32_t M = crc_xpow8(CC); for (uint32_t q = 0; q < tid; q++) M = crc_mulmod(M, M); s_b[tid] = M; }
+		__syncthreads();
+		{
+			uint32_t lvl = 0;
+			for (uint32_t stride = 1; stride < NT; stride <<= 1, lvl++) {
+				if ((tid & (2 * stride - 1)) == 0) s_a[tid] = crc_mulmod(s_a[tid], s_b[lvl]) ^ s_a[tid + stride];
+				__syncthreads();
+			}
 		}
 		if (tid == 0) {
 			EncJob& J = jobs[(size_t)job * nsub + k];

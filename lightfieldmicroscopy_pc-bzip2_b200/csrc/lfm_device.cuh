@@ -131,6 +131,28 @@ __device__ __forceinline__ void scan256_excl(uint32_t* arr, uint32_t* red)
 	__syncthreads();
 }
 
+// Sequential per-thread byte reader (global, shared or generic pointers): 16 bytes per load with one block of lookahead,
+// the byte comes out of registers -- a thread that walks its chunk byte by byte otherwise pays one memory latency per
+// byte.  The base must be 16-byte aligned; 16-byte blocks that START below `lim` are loaded whole (buffers are padded).
+struct ByteReader {
+	const uint4* base; uint32_t blk, lim; uint4 cur, nxt;
+	__device__ __forceinline__ void init(const uint8_t* p, uint32_t i, uint32_t lim_) {
+		base = reinterpret_cast<const uint4*>(p); lim = lim_; blk = i >> 4; cur = base[blk];
+		nxt = ((blk + 1) << 4) < lim ? base[blk + 1] : make_uint4(0, 0, 0, 0);
+	}
+	__device__ __forceinline__ uint32_t get(uint32_t i) {
+		const uint32_t b = i >> 4;
+		if (b != blk) {
+			cur = (b == blk + 1) ? nxt : base[b];
+			blk = b;
+			nxt = ((b + 1) << 4) < lim ? base[b + 1] : make_uint4(0, 0, 0, 0);
+		}
+		const uint32_t w = (i >> 2) & 3u;
+		const uint32_t v = w == 0 ? cur.x : w == 1 ? cur.y : w == 2 ? cur.z : cur.w;
+		return (v >> ((i & 3u) * 8u)) & 0xffu;
+	}
+};
+
 // bzip2 CRC-32 table (poly 0x04C11DB7, MSB first; crctable.c) computed on the fly
 __device__ __forceinline__ uint32_t crc_table_entry(uint32_t i)
 {
