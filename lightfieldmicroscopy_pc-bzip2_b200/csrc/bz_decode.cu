@@ -793,12 +793,15 @@ k_unrle(const uint8_t* __restrict__ txt_all, uint8_t* __restrict__ stage_all /* 
 				for (uint32_t j = obase + e0; j < obase + e1; j++) crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ stage[j]];
 			}
 			s_crc[tid] = crc;
+			// x^(8 CC 2^k) mod P for the k-th tree level: thread k squares k times (s_fn is free by now)
+			if (tid < 12) { uint32_t M = ur_xpow8(CC); for (uint32_t q = 0; q < tid; q++) M = ur_mulmod(M, M); s_fn[tid] = M; }
 			__syncthreads();
-			uint32_t M = ur_xpow8(CC);
-			for (uint32_t stride = 1; stride < NT; stride <<= 1) {
-				if ((tid & (2 * stride - 1)) == 0) s_crc[tid] = ur_mulmod(s_crc[tid], M) ^ s_crc[tid + stride];
-				M = ur_mulmod(M, M);
-				__syncthreads();
+			{
+				uint32_t lvl = 0;
+				for (uint32_t stride = 1; stride < NT; stride <<= 1, lvl++) {
+					if ((tid & (2 * stride - 1)) == 0) s_crc[tid] = ur_mulmod(s_crc[tid], s_fn[lvl]) ^ s_crc[tid + stride];
+					__syncthreads();
+				}
 			}
 		}
 		if (~s_crc[0] != J.stored_crc) { if (tid == 0) J0.status = 3; return; }
