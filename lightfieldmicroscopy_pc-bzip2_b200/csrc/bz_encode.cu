@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(MTF_NT)
 k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scratch, one slot per block */, uint32_t cap,
       EncJob* __restrict__ jobs, uint32_t njobs, uint16_t* __restrict__ mtfv_all, uint32_t mcap)
 {
-	// [64][STS] words, 4 list positions per word: first the chunks' recency lists, then -- column by column, as phase 2
+	// [32][STS] 64-bit words, 8 list positions per word (the rank search compares 8 entries per shared-memory load): first the chunks' recency lists, then -- column by column, as phase 2
 	// consumes them -- the chunks' start states (element (pos, t) of both lives in the same byte)
 	uint32_t* st = reinterpret_cast<uint32_t*>(mtf_smem);
 	uint32_t* seen = st + 64 * MTF_STS;                                                     // [8][NT] membership bitmaps
@@ -325,7 +325,7 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 	uint8_t* seqmap = reinterpret_cast<uint8_t*>(red + 64);                                 // [256]
 	uint8_t* tmp = seqmap + 256;                                                            // [256]
 	uint8_t* st8 = reinterpret_cast<uint8_t*>(st);
-	#define ST_BYTE(pos, t) st8[(((pos) >> 2) * MTF_STS + (t)) * 4 + ((pos) & 3)]
+	#define ST_BYTE(pos, t) st8[(((pos) >> 3) * MTF_STS + (t)) * 8 + ((pos) & 7)]      // 8 list positions per 64-bit word, words of a thread MTF_STS apart
 
 	const uint32_t tid = threadIdx.x, lane = lane_id(), wid = warp_id();
 	const uint32_t job = blockIdx.x;
@@ -402,10 +402,10 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 	}
 	__syncthreads();
 
-	// ---- 3. sequential move-to-front per chunk on the packed list (4 positions per word)
+	// ---- 3. sequential move-to-front per chunk on the packed list (8 positions per 64-bit word)
 	{
-		uint32_t* my = st + tid;                               // word w of my list: my[w * STS]
-		uint32_t front = my[0] & 255u;
+		uint64_t* my = reinterpret_cast<uint64_t*>(st) + tid;   // word w of my list (8 positions): my[w * STS]
+		uint32_t front = (uint32_t)my[0] & 255u;
 		WordReader<1> rf;
 		if (c0 < c1) rf.init(bwt32, c0 >> 2, nwords);
 		for (uint32_t i4 = c0; i4 < c1; i4 += 4) {
@@ -417,22 +417,22 @@ k_mtf(const uint8_t* __restrict__ bwt_all, uint8_t* __restrict__ rank_all /* scr
 					const uint32_t c = seqmap[(inw >> (8 * k)) & 255u];
 					uint32_t r = 0;
 					if (c != front) {
-						const uint32_t pat = c * 0x01010101u;
-						uint32_t carry = c;
+						const uint64_t pat = (uint64_t)c * 0x0101010101010101ull;
+						uint64_t carry = c;
 						for (uint32_t w = 0; ; w++) {
-							const uint32_t word = my[w * MTF_STS];
-							const uint32_t x = word ^ pat;
-							const uint32_t m = (x - 0x01010101u) & ~x & 0x80808080u;               // 0x80 in (at least) the lowest byte equal to c
+							const uint64_t word = my[w * MTF_STS];
+							const uint64_t x = word ^ pat;
+							const uint64_t m = (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;   // 0x80 in (at least) the lowest byte equal to c
 							if (m) {
-								const uint32_t j = (uint32_t)(__ffs(m) - 1) >> 3;                  // lowest matching byte: borrows only spoil higher ones
-								const uint32_t low = j ? (word & (0xFFFFFFFFu >> (32 - 8 * j))) : 0u;   // bytes below it
-								const uint32_t keep = (j == 3) ? 0u : (word & (0xFFFFFFFFu << (8 * (j + 1))));
+								const uint32_t j = (uint32_t)(__ffsll((long long)m) - 1) >> 3;        // lowest matching byte: borrows only spoil higher ones
+								const uint64_t low = j ? (word & (~0ull >> (64 - 8 * j))) : 0ull;   // bytes below it
+								const uint64_t keep = (j == 7) ? 0ull : (word & (~0ull << (8 * (j + 1))));
 								my[w * MTF_STS] = keep | (low << 8) | carry;
-								r = 4 * w + j;
+								r = 8 * w + j;
 								break;
 							}
 							my[w * MTF_STS] = (word << 8) | carry;
-							carry = word >> 24;
+							carry = word >> 56;
 						}
 						front = c;
 					}
