@@ -252,7 +252,8 @@ int Engine::select_mode(const uint16_t* d_frame0, const StackDesc& s, float entr
 	if ((rc = reserve(sel_cand_, 7 * fpx * 2))) return rc;
 	if ((rc = reserve(sel_sorted_, (size_t)8 * nchunks * sstride))) return rc;
 	if ((rc = reserve(sel_hist_, (size_t)8 * nchunks * 65536 * 4))) return rc;
-	if ((rc = reserve(sel_e_, (size_t)8 * nchunks * 4))) return rc;
+	const size_t e_words = ((size_t)8 * nchunks + 63) & ~(size_t)63;                 // entropies, then the sort's per-part digit counts
+	if ((rc = reserve(sel_e_, (e_words + select_scratch_words(8, nchunks)) * 4))) return rc;
 	const uint16_t* cands[8];
 	cands[0] = d_frame0;
 	for (int k = 1; k < 8; k++) {
@@ -260,7 +261,7 @@ int Engine::select_mode(const uint16_t* d_frame0, const StackDesc& s, float entr
 		launch_predict_fwd(d_frame0, c, W, H, s.Nnum, s.way, k, 0, 0, 1, st);
 		cands[k] = c;
 	}
-	launch_select(cands, 8, fpx, chunk_px, nchunks, (uint8_t*)sel_sorted_.p, sstride, (uint32_t*)sel_hist_.p, (float*)sel_e_.p, st);
+	launch_select(cands, 8, fpx, chunk_px, nchunks, (uint8_t*)sel_sorted_.p, sstride, (uint32_t*)sel_hist_.p, (float*)sel_e_.p, (uint32_t*)sel_e_.p + e_words, st);
 	std::vector<float> e((size_t)8 * nchunks);
 	cudaMemcpyAsync(e.data(), sel_e_.p, e.size() * 4, cudaMemcpyDeviceToHost, st);
 	cudaStreamSynchronize(st);

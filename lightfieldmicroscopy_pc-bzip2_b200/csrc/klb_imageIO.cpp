@@ -218,7 +218,7 @@ int compress_core(const FrameSource& src, klb_image_header& h, std::vector<Shard
 		rc = e.select_mode((const uint16_t*)e.user[UB_F0].p, desc, g_stats.entropy, &k);
 		if (rc) { g_err = e.last_error(); return rc; }
 		g_stats.ms_select = now_ms() - t0;
-		g_stats.selected = 1; g_stats.gpu_launches += 7 + 3;
+		g_stats.selected = 1; g_stats.gpu_launches += 7 + 5;       // 7 candidate predictions + count, starts, sort, histogram, entropy
 	} else {
 		k = hv_in & 0x77 & 0x7F;                       // `hv & 0x7F - 8` parses as hv & 0x77 (src/klb_imageIO.cpp:2380)
 		if (k > 7) { std::cout << "ERROR: The predictors hava not selected!" << std::endl; return LFM_ERR_UNSUPPORTED; }
@@ -708,7 +708,7 @@ int lfmCompressDevice(const void* d_im, const uint32_t xyzct[5], const uint32_t 
 		rc = e.select_mode((const uint16_t*)d_im, desc, g_stats.entropy, &k);
 		if (rc) return rc;
 		g_stats.ms_select = now_ms() - t0;
-		g_stats.selected = 1; g_stats.gpu_launches += 10;
+		g_stats.selected = 1; g_stats.gpu_launches += 12;
 	} else { k = headerVersion & 0x77 & 0x7F; if (k > 7) return LFM_ERR_UNSUPPORTED; }
 	if (k != 0 && video && way != 0) return LFM_ERR_UNSUPPORTED;
 	if (storedHeaderVersion) *storedHeaderVersion = (uint8_t)((headerVersion & 0x80) | k);

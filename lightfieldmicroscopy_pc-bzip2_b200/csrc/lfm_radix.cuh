@@ -92,8 +92,9 @@ __device__ __forceinline__ void radix_scatter(uint32_t m, uint32_t* run, uint32_
 
 // per-warp private histograms (match.any aggregated) of an 8-bit digit over m elements,
 // reduced and exclusive-scanned into run[256]
-template <class DigitOfIndex>
-__device__ __forceinline__ void digit_starts(uint32_t m, uint32_t* run, uint32_t* wcnt, uint32_t* red, DigitOfIndex dig)
+// (SCAN = false: run[] receives the plain digit counts)
+template <bool SCAN, class DigitOfIndex>
+__device__ __forceinline__ void digit_hist(uint32_t m, uint32_t* run, uint32_t* wcnt, uint32_t* red, DigitOfIndex dig)
 {
 	const uint32_t lane = lane_id(), w = warp_id();
 	const uint32_t lt = (1u << lane) - 1u;
@@ -119,7 +120,12 @@ __device__ __forceinline__ void digit_starts(uint32_t m, uint32_t* run, uint32_t
 		run[threadIdx.x] = s;
 	}
 	__syncthreads();
-	scan256_excl<BWT_NT>(run, red);
+	if (SCAN) scan256_excl<BWT_NT>(run, red);
+}
+template <class DigitOfIndex>
+__device__ __forceinline__ void digit_starts(uint32_t m, uint32_t* run, uint32_t* wcnt, uint32_t* red, DigitOfIndex dig)
+{
+	digit_hist<true>(m, run, wcnt, red, dig);
 }
 
 // Walk cnt sorted entries; entry j is a group head when its 64-bit key differs from the key of entry j-1.

@@ -22,3 +22,4 @@ for i in range(5):
         for k in ("decode", "imtf", "ibwt", "unrle", "unpredict"): acc[k] = acc.get(k, 0) + getattr(sd, "ms_" + k) / 3
 torch.cuda.synchronize(); assert torch.equal(out, d)
 print(wl, {k: round(v, 3) for k, v in acc.items()})
+print("select ms", round(sc.ms_select, 3), "selected", sc.selected, "predictor", sc.predictor, [round(x, 4) for x in sc.entropy])
