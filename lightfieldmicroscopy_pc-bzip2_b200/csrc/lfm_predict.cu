@@ -233,7 +233,21 @@ k_predict_fwd2(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int
 	int y = y0;
 	while (y < y1) {
 		const int yend = min(y1, y + (T - v));                    // end of this tile row inside the band
-		if (WAY != 2 && v == 0) { generic_row(y); y++; v++; b += PF_PITCH; op += W; }
+		if (WAY != 2 && v == 0) {
+			if (txa > 0 && ty > 0 && !(WAY == 0 && zf)) {           // first row of an interior tile: straight-line rule
+				const uint32_t c2 = *reinterpret_cast<const uint32_t*>(b);
+				const int c0 = (int)(c2 & 0xffffu), c1 = (int)(c2 >> 16);
+				const int left0 = (int)b[-1];
+				auto neara = [&](int dx, int dy) -> int { return dy == 0 ? left0 : (int)b[dy * PF_PITCH + dx]; };
+				auto nearb = [&](int dx, int dy) -> int { return dy == 0 ? c0 : (int)b[1 + dy * PF_PITCH + dx]; };
+				auto fara = [&](int dx, int dy) -> int { return (int)b[dy * PF_PITCH + dx]; };
+				auto farb = [&](int dx, int dy) -> int { return (int)b[1 + dy * PF_PITCH + dx]; };
+				const int pa = predict_interior_v0<WAY, K>(neara, fara, T, ua);
+				const int pb = predict_interior_v0<WAY, K>(nearb, farb, T, ub);
+				*reinterpret_cast<uint32_t*>(op) = (uint32_t)symbolize16(c0 - pa) | ((uint32_t)symbolize16(c1 - pb) << 16);
+			} else generic_row(y);
+			y++; v++; b += PF_PITCH; op += W;
+		}
 		if (txa > 0 && ty > 0 && !(WAY == 0 && zf)) {
 			if (y < yend) {
 				// the row above, carried in registers from here on

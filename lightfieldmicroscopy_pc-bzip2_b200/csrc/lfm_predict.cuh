@@ -173,6 +173,28 @@ __device__ __forceinline__ int predict_interior(Near near, Far far, int T, int u
 	return a ? ((g + up) >> 1) : full;
 }
 
+// The same for the FIRST row of an interior tile (tx > 0, ty > 0, v == 0) of the ways tiles and angle -- one row in Nnum,
+// but through predict0 it cost as much as five interior rows.  near(-1,0) = left, near(0,-1) = the pixel above (last row of
+// the tile above); must agree with predict0 (cases b: u == 0, c: u > 0).
+template <int WAY, int K, class Near, class Far>
+__device__ __forceinline__ int predict_interior_v0(Near near, Far far, int T, int u)
+{
+	int g;                                              // the far-neighbour term (DC rule of way angle, g of way tiles)
+	if (K == 1) g = far(-T, 0);
+	else if (K == 2) g = far(0, -T);
+	else if (K == 3) g = far(-T, -T);
+	else {
+		const int fu = far(0, -T), fl = far(-T, 0), ful = far(-T, -T);
+		if (K == 4 || K == 7) g = fu + fl - ful;
+		else if (K == 5) g = fu + ((fl - ful) >> 1);
+		else g = fl + ((fu - ful) >> 1);
+	}
+	if (WAY == 1) return u == 0 ? g : (K == 2 ? near(0, -1) : near(-1, 0));
+	// WAY 0
+	if (K == 2) return u == 0 ? g : ((near(0, -1) + g) >> 1);
+	return u == 0 ? g : ((near(-1, 0) + g) >> 1);
+}
+
 // zig-zag residual <-> symbol map (lfm_Predictors.cu:16-33), on the int16-truncated residual
 __device__ __forceinline__ uint16_t symbolize16(int residual)
 {
