@@ -284,7 +284,7 @@ constexpr int UP_NT = 512;
 
 __global__ void __launch_bounds__(UP_NT, 2)
 k_unpredict(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T, int way, int k, int video,
-            uint32_t z_start, uint32_t z_step, uint32_t nframes)
+            uint32_t z_start, uint32_t z_step, uint32_t nframes, int rows_b)
 {
 	cg::cluster_group cluster = cg::this_cluster();
 	__shared__ uint32_t pre[512];
@@ -315,7 +315,7 @@ k_unpredict(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T
 
 	if (k == 2 && way != 2) {
 		// ---- schedule B: rows. Leading pixels with left-neighbour chains are walked by one thread.
-		for (int y = 0; y < H; y++) {
+		for (int y = 0; y < min(H, rows_b); y++) {               // rows_b < H: the column kernel below takes the rest
 			const int ty = y / T, v = y - ty * T;
 			const int seq = (y == 0) ? W : min(T, W);
 			if (gtid == 0) for (int x = 0; x < seq; x++) decode_px(x, y, x / T, ty, x % T, v);
@@ -810,6 +810,112 @@ static int launch_unpredict_strips(const uint16_t* sym, uint16_t* out, int W, in
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Predictor 2 of the ways "tiles" and "angle": below the first tile row the rules only look UP -- U = (x, y-1) and
+// Ut = (x, y-T) -- so every image column is an independent chain of H - T steps (lfm_predict.cuh: way tiles
+// (U + Ut) >> 1 / Ut, way angle U / Ut).  One thread per column walks down its column: U in a register, the last T
+// decoded pixels of the column in a shared-memory ring (slot y mod T holds Ut when row y is decoded), symbols prefetched
+// UC_D rows ahead into registers; loads and stores of a warp are 64 contiguous bytes of an image row.  The one
+// horizontal dependency left -- way angle, first tile column, first row of a tile: pred = L -- is a chain of T - 1
+// shuffles in the warp that owns columns 0..31.  In the first tile row the rules of rows 1..T-1 look up as well; only image
+// ROW 0 is a chain along x (pred = L, or Lt for the first pixel of a tile): k_unpredict_row0 walks it, one warp per frame,
+// with the symbols staged in shared memory.
+// Replaces the row-by-row schedule (one cluster barrier per image row: 14.7 ms for a 2048^2 x 32 stack).
+// image row 0 of every frame (predictor 2, ways tiles / angle): t00 pred = L (0 for the first pixel), later tiles Lt for
+// u == 0 and L for u > 0.  One warp per frame: symbols (and the previous frame's row, video) staged in shared memory,
+// lane 0 walks the W pixels with L in a register, the warp writes the row back.
+template <int WAY>
+__global__ void __launch_bounds__(32)
+k_unpredict_row0(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T, int video, uint32_t z_start, uint32_t z_step)
+{
+	extern __shared__ __align__(16) uint8_t r0_smem[];
+	uint16_t* srow = reinterpret_cast<uint16_t*>(r0_smem);        // symbols -> pixels, in place
+	uint16_t* prow = srow + W;                                     // previous frame (odd video frames)
+	const int lane = (int)threadIdx.x;
+	const uint32_t z = z_start + blockIdx.x * z_step;
+	const uint64_t fpx = (uint64_t)W * H;
+	const bool zflag = (video & (int)z & 1) != 0;
+	const uint16_t* s = sym + (uint64_t)z * fpx;
+	uint16_t* o = out + (uint64_t)z * fpx;
+	for (int x = lane; x < W; x += 32) { srow[x] = __ldg(s + x); if (zflag) prow[x] = __ldcg(o + x - fpx); }
+	__syncwarp();
+	if (lane == 0) {
+		int left = 0, tx = 0, u = 0;
+		for (int x = 0; x < W; x++) {
+			auto px = [&](int dx, int dy) -> int { return dy != 0 ? 0 : (dx == -1 ? left : (int)srow[x + dx]); };   // (-T,0): already decoded
+			int p = predict0(px, T, WAY, 2, tx, 0, u, 0);
+			if (WAY == 0 && zflag) p = x == 0 ? (int)prow[0] : ((p + (int)prow[x]) >> 1);
+			left = (unsymbolize16(srow[x]) + p) & 0xffff;
+			srow[x] = (uint16_t)left;
+			if (++u == T) { u = 0; tx++; }
+		}
+	}
+	__syncwarp();
+	for (int x = lane; x < W; x += 32) o[x] = srow[x];
+}
+
+constexpr int UC_NT = 128;
+constexpr int UC_D = 8;
+
+template <int WAY>
+__global__ void __launch_bounds__(UC_NT)
+k_unpredict_cols2(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T, int video,
+                  uint32_t z_start, uint32_t z_step)
+{
+	extern __shared__ __align__(16) uint8_t uc_smem[];
+	uint16_t* ring = reinterpret_cast<uint16_t*>(uc_smem);          // [T][UC_NT]
+	const int tid = (int)threadIdx.x;
+	const int x = (int)blockIdx.x * UC_NT + tid;
+	const bool live = x < W;
+	const int xc = live ? x : W - 1;                                // dead lanes shadow the last column and never store
+	const uint32_t z = z_start + blockIdx.y * z_step;
+	const uint64_t fpx = (uint64_t)W * H;
+	const bool zflag = (video & (int)z & 1) != 0;
+	const uint16_t* s = sym + (uint64_t)z * fpx + xc;
+	uint16_t* o = out + (uint64_t)z * fpx + xc;
+	const int tx = xc / T, u = xc - tx * T;
+	const bool chain_warp = WAY == 1 && blockIdx.x == 0 && tid < 32;  // columns 0..31 hold the first tile (T <= 32)
+	ring[tid] = __ldcg(o);                                          // row 0: decoded by k_unpredict_row0 before
+	int up = (int)ring[tid];
+	uint32_t q[UC_D];                                               // symbol | previous-frame pixel << 16
+	auto fetch = [&](int y) -> uint32_t {
+		if (y >= H) return 0u;
+		uint32_t v2 = (uint32_t)__ldg(s + (size_t)y * W);
+		if (zflag) v2 |= (uint32_t)__ldcg(o + (size_t)y * W - fpx) << 16;
+		return v2;
+	};
+	#pragma unroll
+	for (int d = 0; d < UC_D; d++) q[d] = fetch(1 + d);
+	int v = T > 1 ? 1 : 0, slot = v, tyc = T > 1 ? 0 : 1;           // row y: v = y mod T = ring slot, tyc = (y >= T)
+	for (int y0 = 1; y0 < H; y0 += UC_D) {
+		#pragma unroll
+		for (int d = 0; d < UC_D; d++) {
+			const int y = y0 + d;
+			if (y < H) {                                              // uniform
+				const uint32_t qq = q[d];
+				q[d] = fetch(y + UC_D);
+				const int ut = (int)ring[slot * UC_NT + tid];
+				auto px = [&](int dx, int dy) -> int { return dx != 0 ? 0 : (dy == -1 ? up : ut); };    // (-1,0) is patched below
+				int p = predict0(px, T, WAY, 2, tx, tyc, u, v);
+				if (WAY == 0 && zflag) p = (p + (int)(qq >> 16)) >> 1;  // (x, y) != (0, 0) here
+				const int res = unsymbolize16((uint16_t)qq);
+				int val = (res + p) & 0xffff;
+				if (chain_warp && v == 0 && tyc) {                      // way angle, tile column 0, first row of a tile below the first: pred = L
+					for (int uu = 1; uu < T; uu++) {
+						const int l = __shfl_sync(0xffffffffu, val, uu - 1);
+						if (tid == uu) val = (res + l) & 0xffff;
+					}
+				}
+				if (live) o[(size_t)y * W] = (uint16_t)val;
+				ring[slot * UC_NT + tid] = (uint16_t)val;
+				up = val;
+				if (++v == T) { v = 0; tyc = 1; }
+				slot = v;
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Band-pipelined inverse (way "tiles" incl. video; any way whose rule only looks at the operands listed below; not
 // predictor 2 of the ways tiles / angle, whose U crosses the tile border).
 //
@@ -1170,8 +1276,11 @@ int launch_unpredict(const uint16_t* sym, uint16_t* out, int W, int H, int T, in
 	}
 	// remaining cases (way tiles, video, predictor 2 of tiles/angle): many frames -> one CTA per frame in shared memory;
 	// few frames -> the cluster wavefront below (all SMs on one frame)
+	// predictor 2 of the ways tiles / angle: below the first tile row every image column is an independent chain
+	static const int cols_on = getenv("LFM_B200_COLS") ? atoi(getenv("LFM_B200_COLS")) : 1;
+	const bool cols = cols_on && k == 2 && way != 2 && T <= 32 && H > 1 && (size_t)W * 4 <= (size_t)UG_MAX_SMEM;
 	static const int strips_min = getenv("LFM_B200_STRIPS_MIN") ? atoi(getenv("LFM_B200_STRIPS_MIN")) : 128;
-	if ((int)count >= strips_min) {
+	if ((int)count >= strips_min && !cols) {
 		const int rcs = way == 0 ? launch_unpredict_strips<0>(sym, out, W, H, T, k, video, z_start, z_step, count, st)
 		              : way == 1 ? launch_unpredict_strips<1>(sym, out, W, H, T, k, video, z_start, z_step, count, st)
 		                         : launch_unpredict_strips<2>(sym, out, W, H, T, k, video, z_start, z_step, count, st);
@@ -1187,7 +1296,22 @@ int launch_unpredict(const uint16_t* sym, uint16_t* out, int W, int H, int T, in
 	attr[0].id = cudaLaunchAttributeClusterDimension;
 	attr[0].val.clusterDim.x = csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr; cfg.numAttrs = 1;
-	return cudaLaunchKernelEx(&cfg, k_unpredict, sym, out, W, H, T, way, k, video, z_start, z_step, count) == cudaSuccess ? 0 : 1;
+	if (cols) {
+		const size_t smem0 = (size_t)W * 2 * 2;
+		const dim3 grid((unsigned)((W + UC_NT - 1) / UC_NT), count);
+		const size_t smem = (size_t)T * UC_NT * 2;
+		if (way == 0) {
+			cudaFuncSetAttribute(k_unpredict_row0<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0);
+			k_unpredict_row0<0><<<count, 32, smem0, st>>>(sym, out, W, H, T, video, z_start, z_step);
+			k_unpredict_cols2<0><<<grid, UC_NT, smem, st>>>(sym, out, W, H, T, video, z_start, z_step);
+		} else {
+			cudaFuncSetAttribute(k_unpredict_row0<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0);
+			k_unpredict_row0<1><<<count, 32, smem0, st>>>(sym, out, W, H, T, video, z_start, z_step);
+			k_unpredict_cols2<1><<<grid, UC_NT, smem, st>>>(sym, out, W, H, T, video, z_start, z_step);
+		}
+		return cudaGetLastError() == cudaSuccess ? 0 : 1;
+	}
+	return cudaLaunchKernelEx(&cfg, k_unpredict, sym, out, W, H, T, way, k, video, z_start, z_step, count, H) == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace lfm
