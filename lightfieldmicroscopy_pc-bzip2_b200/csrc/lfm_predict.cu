@@ -841,8 +841,9 @@ k_unpredict_row0(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, 
 	if (lane == 0) {
 		int left = 0, tx = 0, u = 0;
 		for (int x = 0; x < W; x++) {
-			auto px = [&](int dx, int dy) -> int { return dy != 0 ? 0 : (dx == -1 ? left : (int)srow[x + dx]); };   // (-T,0): already decoded
-			int p = predict0(px, T, WAY, 2, tx, 0, u, 0);
+			// predict0 for k = 2, ty == 0, v == 0 written out (both ways): L inside a tile, Lt (already decoded, in place) for the
+			// first pixel of a tile, 0 for the first pixel of the row
+			int p = u ? left : (tx ? (int)srow[x - T] : 0);
 			if (WAY == 0 && zflag) p = x == 0 ? (int)prow[0] : ((p + (int)prow[x]) >> 1);
 			left = (unsymbolize16(srow[x]) + p) & 0xffff;
 			srow[x] = (uint16_t)left;
@@ -894,8 +895,13 @@ k_unpredict_cols2(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H,
 				const uint32_t qq = q[d];
 				q[d] = fetch(y + UC_D);
 				const int ut = (int)ring[slot * UC_NT + tid];
-				auto px = [&](int dx, int dy) -> int { return dx != 0 ? 0 : (dy == -1 ? up : ut); };    // (-1,0) is patched below
-				int p = predict0(px, T, WAY, 2, tx, tyc, u, v);
+				// predict0 for k = 2 written out (lfm_predict.cuh): first tile row: U.  Below it -- way tiles: Ut where the rule
+				// has no near neighbour (u == 0; in the first tile column v == 0), else (U + Ut) >> 1; way angle: Ut for the tile
+				// DC, else U (the L of the first tile column is patched below).
+				int p;
+				if (!tyc) p = up;
+				else if (WAY == 0) p = (tx == 0 ? v == 0 : u == 0) ? ut : ((up + ut) >> 1);
+				else p = (u == 0 && v == 0) ? ut : up;
 				if (WAY == 0 && zflag) p = (p + (int)(qq >> 16)) >> 1;  // (x, y) != (0, 0) here
 				const int res = unsymbolize16((uint16_t)qq);
 				int val = (res + p) & 0xffff;
