@@ -17,7 +17,7 @@ G = json.load(open(os.path.join(GOLDEN, "golden.json")))
 @pytest.fixture(scope="module")
 def L():
     os.environ["LFM_B200_DEBUG_POISON"] = "1"      # poison decode buffers so ordering bugs cannot hide behind stale data
-    os.environ["LFM_B200_STRIPS_MIN"] = "8"        # stacks of >= 8 frames take the one-CTA-per-frame inverse, smaller ones the cluster kernel
+    os.environ["LFM_B200_STRIPS_MIN"] = "8"        # fall-back inverse kernels (Nnum > 32, predictor 2 with Nnum > 32): strips from 8 frames on, cluster below
     import lfm_b200
     import torch
     assert torch.cuda.is_available(), "gpu tests need a CUDA device"
@@ -360,3 +360,33 @@ def test_pageable_stacks_take_the_staged_copy_path(L, tmp_path):
     back = np.empty_like(a)
     L.decompress_into(blob.numpy(), n, back, way=0)                  # pinned source, pageable destination
     assert np.array_equal(back, a)
+
+
+@pytest.mark.parametrize("frames", [3, 9])
+def test_inverse_fallback_kernels_large_nnum(L, oracle, frames):
+    """Nnum = 33: a tile no longer fits the band pipeline (Nnum^2 threads) nor the column kernel's shuffle chain (Nnum <= 32), so
+    the way tiles / angle inverses fall back to the strips kernel (>= 8 frames here) and the cluster wavefront / row schedule.
+    Every predictor, image and video mode: forward symbols of frame 0 equal the oracle's, inverse(forward) restores the stack."""
+    import ctypes as C
+    import torch
+    T, H, W = 33, 100, 136
+    rng = np.random.default_rng(frames)
+    a = (lf_synth((frames, H, W), T, seed=2).astype(np.int64) + rng.integers(0, 300, (frames, H, W))).astype(np.uint16)
+    d = torch.from_numpy(a.view(np.int16)).cuda()
+    sym = torch.empty_like(d); back = torch.empty_like(d)
+    xyz = L._u32x5(W, H, frames, 1, 1)
+    ms = C.c_float()
+    prev = L.set_way(0)
+    try:
+        for way in (0, 1, 2):
+            L.set_way(way)
+            for k in range(1, 8):
+                for video in ((0, 1) if way == 0 else (0,)):
+                    back.fill_(-21555)
+                    assert L.lib.lfmDebugPredictDevice(d.data_ptr(), sym.data_ptr(), xyz, T, k, video, 0, 1, C.byref(ms)) == 0
+                    want0 = oracle.predict_frame(a[0], None, T, way, k, 0)
+                    assert np.array_equal(sym[0].cpu().numpy().view(np.uint16), want0), (way, k, video)
+                    assert L.lib.lfmDebugPredictDevice(sym.data_ptr(), back.data_ptr(), xyz, T, k, video, 1, 1, C.byref(ms)) == 0
+                    assert torch.equal(back, d), (way, k, video)
+    finally:
+        L.set_way(prev if prev is not None and prev >= 0 else 0)
