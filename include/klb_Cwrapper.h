@@ -7,8 +7,8 @@
  *
  * Return codes (src/klb_Cwrapper.cpp:33-46, src/klb_imageIO.cpp:220-221,531-532,2267-2268,2619-2631):
  *   0 ok; 2 block codec failure / no blocks; 3 cannot open for read / API misuse; 5 cannot create output or unknown codec;
- *   new: 6 CUDA failure (the reference ignores CUDA errors); 7 unsupported (non-uint16 data, ZLIB/NONE codec,
- *   block sizes that need multi-block bzip2 streams).
+ *   new: 6 CUDA failure (the reference ignores CUDA errors); 7 unsupported (non-16-bit data, ZLIB codec, video stacks with
+ *   predictor way angle/space, KLB blocks that need more than 32 bzip2 blocks per stream).
  */
 #ifndef __KLB_IMAGE_C_WRAPPER_H__
 #define __KLB_IMAGE_C_WRAPPER_H__

@@ -64,6 +64,7 @@ public:
 	               const std::uint8_t Nnum_ = 13);
 
 	// serialise / parse the 320-byte fixed part (helpers of this implementation)
+	bool numBlocksBounded(size_t limit, size_t* nb) const;    // calculateNumBlocks() with an overflow / size guard
 	void packFixed(std::uint8_t out[320]) const;
 	void unpackFixed(const std::uint8_t in[320]);
 

@@ -56,10 +56,29 @@ int lfmDecompressDevice(const void* d_payload, const uint64_t* blockOffset, uint
                         const uint32_t xyzct[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS],
                         uint8_t storedHeaderVersion, uint8_t Nnum, void* d_out);
 
+/* ---- one process per GPU: KLB blocks are independent streams and a range of z-slabs is a contiguous block-id and
+   payload range (block ids are x fastest, src/klb_imageIO.cpp:133-140), so every rank compresses the slabs it owns as a stack of
+   its own and the only exchange is the host-side prefix sum of the block sizes (blockWriter, src/klb_imageIO.cpp:1145-1225):
+     1. lfmShardCompress   this rank's frames (host) -> streams left on its GPU; blockSizes[numBlocks] = size of each local block.
+                           Ranks other than the owner of frame 0 pass a forced headerVersion (8 + k | video bit); a video shard
+                           must start on an even frame of the whole stack.
+     2. the caller all-gathers the sizes, prefix-sums them into blockOffset[] and calls lfmWriteHeader once (creates the file,
+        writes the 320 bytes + table, sizes the file);
+     3. lfmShardWritePayload  streams the rank's payload from its GPU to its byte offset of the file (pinned ring + pwrite),
+        or lfmShardFetchPayload copies it into a host buffer.
+   The read side needs nothing new: readKLBroiInPlace with the rank's z range only fetches and decodes its slabs. */
+int lfmShardCompress(const void* im_local, const uint32_t xyzct_local[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS],
+                     uint8_t headerVersion, uint8_t Nnum, uint8_t* storedHeaderVersion, uint32_t* blockSizes, uint64_t numBlocks,
+                     uint64_t* payload_bytes);
+int lfmShardWritePayload(const char* filename, uint64_t file_offset);
+int lfmShardFetchPayload(void* dst, uint64_t capacity);
+int lfmWriteHeader(const char* filename, const uint32_t xyzct[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS],
+                   uint8_t storedHeaderVersion, uint8_t Nnum, const uint64_t* blockOffset, uint64_t numBlocks);
+
 /* number of KLB blocks for a stack (klb_imageHeader.cpp:77-85, after clamping blockSize to xyzct; NULL = default) */
 uint64_t lfmNumBlocks(const uint32_t xyzct[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS]);
 
-/* statistics of the last compress / decompress call on this thread's engine(s) */
+/* statistics of the last compress / decompress call made by the calling thread */
 typedef struct {
 	int    predictor;         /* stored predictor 0..7 */
 	int    selected;          /* 1 if chosen by the 2-D entropy rule */
@@ -74,7 +93,7 @@ typedef struct {
 } lfm_stats;
 int lfmGetLastStats(lfm_stats* out);
 
-/* last error text of the library (thread-unsafe, diagnostic only) */
+/* error text of the last failed call made by the calling thread (valid until its next call) */
 const char* lfmLastError(void);
 
 /* test hook: per-stage intermediates of the block encoder for ONE host buffer treated as one KLB block of

@@ -76,6 +76,11 @@ lib.lfmCompressDevice.argtypes = [C.c_void_p, _u32x5, C.c_void_p, C.c_uint8, C.c
 lib.lfmCompressDevice.restype = C.c_int
 lib.lfmDecompressDevice.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, _u32x5, C.c_void_p, C.c_uint8, C.c_uint8, C.c_void_p]
 lib.lfmDecompressDevice.restype = C.c_int
+lib.lfmShardCompress.argtypes = [C.c_void_p, _u32x5, C.c_void_p, C.c_uint8, C.c_uint8, C.POINTER(C.c_uint8), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+lib.lfmShardCompress.restype = C.c_int
+lib.lfmShardWritePayload.argtypes = [C.c_char_p, C.c_uint64]; lib.lfmShardWritePayload.restype = C.c_int
+lib.lfmShardFetchPayload.argtypes = [C.c_void_p, C.c_uint64]; lib.lfmShardFetchPayload.restype = C.c_int
+lib.lfmWriteHeader.argtypes = [C.c_char_p, _u32x5, C.c_void_p, C.c_uint8, C.c_uint8, C.c_void_p, C.c_uint64]; lib.lfmWriteHeader.restype = C.c_int
 lib.lfmNumBlocks.argtypes = [_u32x5, C.c_void_p]; lib.lfmNumBlocks.restype = C.c_uint64
 lib.lfmGetLastStats.argtypes = [C.POINTER(LfmStats)]; lib.lfmGetLastStats.restype = C.c_int
 lib.lfmLastError.restype = C.c_char_p
@@ -90,7 +95,8 @@ _libc.free.argtypes = [C.c_void_p]
 EXPORTS = ["writeKLBstack", "writeKLBstackSlices", "readKLBheader", "readKLBstack", "readKLBstackInPlace", "readKLBroiInPlace",
            "lfmSetPredictorWay", "lfmGetPredictorWay", "lfmSetDevices", "writeLFMstackEx", "readLFMheaderEx",
            "lfmCompressToMemory", "lfmCompressToBuffer", "lfmDecompressFromMemory", "lfmCompressDevice", "lfmDecompressDevice", "lfmNumBlocks",
-           "lfmGetLastStats", "lfmLastError", "lfmDebugEncodeBlock", "lfmDebugPredictDevice"]
+           "lfmGetLastStats", "lfmLastError", "lfmDebugEncodeBlock", "lfmDebugPredictDevice",
+           "lfmShardCompress", "lfmShardWritePayload", "lfmShardFetchPayload", "lfmWriteHeader"]
 
 
 class LfmError(RuntimeError):
@@ -129,14 +135,14 @@ def stats():
     return s
 
 
-def write_stack(img, filename, header_version=0, nnum=13, block_size=None, way=None):
+def write_stack(img, filename, header_version=0, nnum=13, block_size=None, way=None, codec=BZIP2):
     """img: uint16 array [..., z, y, x]. Mirrors writeKLBstack + the header knobs (writeLFMstackEx)."""
     img = np.ascontiguousarray(img, dtype=np.uint16)
     if way is not None:
         set_way(way)
     bs = _bs(block_size)
     rc = lib.writeLFMstackEx(img.ctypes.data, os.fsencode(filename), _xyzct(img.shape), UINT16_TYPE, -1, None,
-                             C.cast(bs, C.c_void_p) if bs is not None else None, BZIP2, None, header_version, nnum)
+                             C.cast(bs, C.c_void_p) if bs is not None else None, codec, None, header_version, nnum)
     if rc:
         raise LfmError(rc, "writeLFMstackEx")
     return rc
@@ -176,6 +182,38 @@ def read_roi(filename, lb, ub, way=None):
     if rc:
         raise LfmError(rc, "readKLBroiInPlace")
     return out
+
+
+def shard_compress(frames, header_version, nnum=13, block_size=None, way=None):
+    """one rank's frames (uint16 [z, y, x], host) -> (stored headerVersion, uint32 size of every local block, payload bytes);
+    the streams stay on the rank's GPU until shard_write_payload / shard_fetch_payload (include/lfm_b200.h)"""
+    assert frames.dtype == np.uint16 and frames.flags.c_contiguous
+    if way is not None:
+        set_way(way)
+    xyzct = _xyzct(frames.shape)
+    bs = _bs(block_size)
+    bsp = C.cast(bs, C.c_void_p) if bs is not None else None
+    nb = lib.lfmNumBlocks(xyzct, bsp)
+    sizes = np.zeros(nb, np.uint32); shv = C.c_uint8(); pb = C.c_uint64()
+    rc = lib.lfmShardCompress(frames.ctypes.data, xyzct, bsp, header_version, nnum, C.byref(shv), sizes.ctypes.data, nb, C.byref(pb))
+    if rc:
+        raise LfmError(rc, "lfmShardCompress")
+    return shv.value, sizes, pb.value
+
+
+def shard_write_payload(filename, file_offset):
+    rc = lib.lfmShardWritePayload(os.fsencode(filename), int(file_offset))
+    if rc:
+        raise LfmError(rc, "lfmShardWritePayload")
+
+
+def write_header(filename, xyzct, block_size, stored_header_version, nnum, block_offset):
+    bo = np.ascontiguousarray(block_offset, dtype=np.uint64)
+    bs = _bs(block_size)
+    rc = lib.lfmWriteHeader(os.fsencode(filename), _u32x5(*xyzct), C.cast(bs, C.c_void_p) if bs is not None else None,
+                            stored_header_version, nnum, bo.ctypes.data, bo.size)
+    if rc:
+        raise LfmError(rc, "lfmWriteHeader")
 
 
 def compress_to_bytes(img, header_version=0, nnum=13, block_size=None, way=None):

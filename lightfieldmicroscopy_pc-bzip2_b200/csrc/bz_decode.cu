@@ -407,6 +407,7 @@ k_imtf(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, DecJob* __restrict_
 				}
 				if (bad) break;
 				outc += run;
+				if (outc > max_block) { bad = true; break; }       // keeps the CTA-wide sum below 128 * max_block: no uint32 wrap
 				continue;
 			}
 			if (sym >= EOB) { bad = true; break; }
@@ -430,6 +431,7 @@ k_imtf(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, DecJob* __restrict_
 			outc++;
 			i++;
 		}
+		if (outc > max_block) bad = true;
 	}
 	uint32_t total; const uint32_t inc = block_scan_add<IM_NT>(outc, red, &total);
 	if (__syncthreads_or(bad || total > max_block || total > cap)) { if (tid == 0) J.status = 2; return; }

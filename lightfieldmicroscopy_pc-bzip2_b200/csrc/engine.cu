@@ -110,6 +110,43 @@ __global__ void k_dec_status(const DecJob* __restrict__ jobs, uint32_t njobs, ui
 	if (j < njobs && jobs[j].status) atomicOr(flag, 1u << min(jobs[j].status, 31u));
 }
 
+// KLB_COMPRESSION_TYPE::NONE: a block's payload is its rows, x fastest, copied verbatim (src/klb_imageIO.cpp:146-183 gather,
+// :207-210 "codec", :673-746 scatter).  One CTA per KLB block, one warp per row.  Payload positions come from the file on
+// the read side and may be odd: bytes are moved one by one there.
+__global__ void k_none_gather(const uint16_t* __restrict__ sym, Geom g, uint64_t first_block, const uint64_t* __restrict__ starts,
+                              uint8_t* __restrict__ payload)
+{
+	uint32_t c0[5], ext[5];
+	block_box(g, first_block + blockIdx.x, c0, ext);
+	const uint32_t rows = ext[1] * ext[2] * ext[3] * ext[4], rowpx = ext[0];
+	uint16_t* dst = reinterpret_cast<uint16_t*>(payload + starts[blockIdx.x]);       // starts are sums of even byte counts
+	for (uint32_t r = warp_id(); r < rows; r += blockDim.x >> 5) {
+		uint32_t y = r % ext[1], q = r / ext[1];
+		uint32_t z = q % ext[2]; q /= ext[2];
+		uint32_t c = q % ext[3], t = q / ext[3];
+		const uint16_t* row = sym + (c0[0] + (uint64_t)(c0[1] + y) * g.stride[1] + (uint64_t)(c0[2] + z) * g.stride[2]
+		                             + (uint64_t)(c0[3] + c) * g.stride[3] + (uint64_t)(c0[4] + t) * g.stride[4]);
+		for (uint32_t x = lane_id(); x < rowpx; x += 32) dst[(size_t)r * rowpx + x] = row[x];
+	}
+}
+__global__ void k_none_scatter(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ begin, const uint64_t* __restrict__ block_ids,
+                               uint16_t* __restrict__ sym, Geom g)
+{
+	uint32_t c0[5], ext[5];
+	block_box(g, block_ids[blockIdx.x], c0, ext);
+	const uint32_t rows = ext[1] * ext[2] * ext[3] * ext[4], rowpx = ext[0];
+	const uint8_t* src = payload + begin[blockIdx.x];
+	for (uint32_t r = warp_id(); r < rows; r += blockDim.x >> 5) {
+		uint32_t y = r % ext[1], q = r / ext[1];
+		uint32_t z = q % ext[2]; q /= ext[2];
+		uint32_t c = q % ext[3], t = q / ext[3];
+		uint16_t* row = sym + (c0[0] + (uint64_t)(c0[1] + y) * g.stride[1] + (uint64_t)(c0[2] + z) * g.stride[2]
+		                       + (uint64_t)(c0[3] + c) * g.stride[3] + (uint64_t)(c0[4] + t) * g.stride[4]);
+		const uint8_t* s2 = src + ((size_t)r * rowpx) * 2;
+		for (uint32_t x = lane_id(); x < rowpx; x += 32) row[x] = (uint16_t)(s2[2 * x] | ((uint32_t)s2[2 * x + 1] << 8));
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 static std::mutex g_mu;
 static std::map<int, std::unique_ptr<Engine>> g_engines;
@@ -314,11 +351,73 @@ int Engine::unpredict(const uint16_t* d_sym, uint16_t* d_out, const StackDesc& s
 	return check("unpredict");
 }
 
+// ------------------------------------------------------------------------------------------------ codec NONE
+static uint64_t host_block_bytes(const Geom& g, uint64_t id)
+{
+	uint64_t n = 2;
+	for (int i = 0; i < 5; i++) {
+		const uint64_t c = id % g.nb[i]; id /= g.nb[i];
+		n *= std::min<uint64_t>(g.bs[i], g.xyzct[i] - c * g.bs[i]);
+	}
+	return n;
+}
+
+int Engine::compress_blocks_none(const uint16_t* d_sym, const StackDesc& s, uint64_t first, uint64_t count,
+                                 uint32_t* sizes_out, const uint8_t** d_payload, uint64_t* payload_bytes, CompressStats* stt)
+{
+	cudaStream_t st = (cudaStream_t)stream_;
+	const Geom g = make_geom(s);
+	if (count == 0) { *d_payload = nullptr; *payload_bytes = 0; return LFM_OK; }
+	std::vector<uint64_t> starts(count);
+	uint64_t acc = 0;
+	for (uint64_t i = 0; i < count; i++) {
+		const uint64_t n = host_block_bytes(g, first + i);
+		if (n > 0xffffffffull) { err_ = "KLB block larger than 4 GB"; return LFM_ERR_UNSUPPORTED; }
+		starts[i] = acc; sizes_out[i] = (uint32_t)n; acc += n;
+	}
+	int rc;
+	if ((rc = reserve(payload_, acc + 16))) return rc;
+	if ((rc = reserve(offs_, count * 8))) return rc;
+	cudaMemcpyAsync(offs_.p, starts.data(), count * 8, cudaMemcpyHostToDevice, st);
+	for (uint64_t b0 = 0; b0 < count; b0 += 0x40000000ull) {
+		const uint32_t nj = (uint32_t)std::min<uint64_t>(0x40000000ull, count - b0);
+		k_none_gather<<<nj, 256, 0, st>>>(d_sym, g, first + b0, (const uint64_t*)offs_.p + b0, (uint8_t*)payload_.p);
+		if (stt) stt->launches++;
+	}
+	cudaStreamSynchronize(st);                                  // `starts` is pageable host memory
+	if ((rc = check("compress_blocks_none"))) return rc;
+	*d_payload = (const uint8_t*)payload_.p; *payload_bytes = acc;
+	return LFM_OK;
+}
+
+int Engine::decompress_blocks_none(const uint8_t* d_payload, const uint64_t* begin, const uint64_t* end, const uint64_t* block_ids,
+                                   uint64_t count, uint16_t* d_sym, const StackDesc& s, DecompressStats* stt)
+{
+	cudaStream_t st = (cudaStream_t)stream_;
+	const Geom g = make_geom(s);
+	if (count == 0) return LFM_OK;
+	for (uint64_t i = 0; i < count; i++)
+		if (end[i] - begin[i] != host_block_bytes(g, block_ids[i])) { err_ = "uncompressed block has the wrong size"; return LFM_ERR_BZIP; }
+	int rc;
+	if ((rc = reserve(dbegin_, count * 8))) return rc;
+	if ((rc = reserve(dids_, count * 8))) return rc;
+	cudaMemcpyAsync(dbegin_.p, begin, count * 8, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(dids_.p, block_ids, count * 8, cudaMemcpyHostToDevice, st);
+	for (uint64_t b0 = 0; b0 < count; b0 += 0x40000000ull) {
+		const uint32_t nj = (uint32_t)std::min<uint64_t>(0x40000000ull, count - b0);
+		k_none_scatter<<<nj, 256, 0, st>>>(d_payload, (const uint64_t*)dbegin_.p + b0, (const uint64_t*)dids_.p + b0, d_sym, g);
+		if (stt) stt->launches++;
+	}
+	cudaStreamSynchronize(st);
+	return check("decompress_blocks_none");
+}
+
 // ------------------------------------------------------------------------------------------------ compress
 int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t first, uint64_t count,
                             uint32_t* sizes_out, const uint8_t** d_payload, uint64_t* payload_bytes, CompressStats* stt)
 {
 	cudaSetDevice(device_);
+	if (s.codec == 0) return compress_blocks_none(d_sym, s, first, count, sizes_out, d_payload, payload_bytes, stt);
 	cudaStream_t st = (cudaStream_t)stream_;
 	const Geom g = make_geom(s);
 	EncSizes z;
@@ -428,6 +527,7 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
                               uint64_t count, uint16_t* d_sym, const StackDesc& s, DecompressStats* stt)
 {
 	cudaSetDevice(device_);
+	if (s.codec == 0) return decompress_blocks_none(d_payload, begin, end, block_ids, count, d_sym, s, stt);
 	cudaStream_t st = (cudaStream_t)stream_;
 	if (count == 0) return LFM_OK;
 	const Geom g = make_geom(s);

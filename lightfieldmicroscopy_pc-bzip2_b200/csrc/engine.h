@@ -27,6 +27,7 @@ struct StackDesc {
 	uint32_t blockSize[5];     // already clamped to xyzct
 	int      Nnum;
 	int      way;              // 0 tiles(both), 1 angle, 2 space  (compile-time LFM_PREDICTOR_WAY in the reference)
+	int      codec = 1;        // KLB_COMPRESSION_TYPE of the block payloads: 1 bzip2, 0 none (rows copied verbatim)
 };
 
 struct CompressStats {
@@ -95,6 +96,11 @@ public:
 private:
 	explicit Engine(int device);
 	int check(const char* what);
+	// KLB_COMPRESSION_TYPE::NONE (src/klb_imageIO.cpp:207-210, :620-623): gather / scatter only
+	int compress_blocks_none(const uint16_t* d_sym, const StackDesc& s, uint64_t first, uint64_t count,
+	                         uint32_t* sizes_out, const uint8_t** d_payload, uint64_t* payload_bytes, CompressStats* st);
+	int decompress_blocks_none(const uint8_t* d_payload, const uint64_t* begin, const uint64_t* end, const uint64_t* block_ids,
+	                           uint64_t count, uint16_t* d_sym, const StackDesc& s, DecompressStats* st);
 
 	int device_ = 0, sm_count_ = 148;
 	void* stream_ = nullptr;

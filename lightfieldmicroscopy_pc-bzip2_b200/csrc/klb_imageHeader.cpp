@@ -100,15 +100,46 @@ void klb_image_header::writeHeader(std::ostream& fid)
 	fid.write((const char*)blockOffset, sizeof(std::uint64_t) * Nb);
 }
 
+// number of blocks of the current xyzct / blockSize if it does not exceed `limit` (the header of an untrusted file: the
+// product of five 32-bit ratios must not overflow or drive an allocation); false otherwise
+bool klb_image_header::numBlocksBounded(size_t limit, size_t* nb) const
+{
+	size_t n = 1;
+	for (int d = 0; d < KLB_DATA_DIMS; d++) {
+		if (blockSize[d] == 0) return false;
+		const size_t r = (size_t)std::ceil((float)xyzct[d] / (float)blockSize[d]);
+		if (r != 0 && n > limit / r) return false;
+		n *= r;
+	}
+	if (nb) *nb = n;
+	return n <= limit;
+}
+
+// The stream must hold the 320 fixed bytes and the whole blockOffset table; a short or inconsistent header leaves Nb == 0
+// (callers report "no blocks", code 2) instead of parsing uninitialised bytes or allocating a table the file cannot hold.
 void klb_image_header::readHeader(std::istream& fid)
 {
 	std::uint8_t fixed[320];
+	resizeBlockOffset(0);
+	const std::istream::pos_type here = fid.tellg();
+	std::uint64_t avail = ~0ull;
+	if (here != std::istream::pos_type(-1)) {
+		fid.seekg(0, std::ios::end);
+		const std::istream::pos_type endp = fid.tellg();
+		fid.seekg(here);
+		if (endp != std::istream::pos_type(-1) && endp >= here) avail = (std::uint64_t)(endp - here);
+	}
 	fid.read((char*)fixed, sizeof(fixed));
+	if ((size_t)fid.gcount() != sizeof(fixed)) return;
 	unpackFixed(fixed);
-	bool sane = true;
-	for (int d = 0; d < KLB_DATA_DIMS; d++) if (blockSize[d] == 0) sane = false;
-	resizeBlockOffset(sane ? calculateNumBlocks() : 0);
-	if (Nb) fid.read((char*)blockOffset, sizeof(std::uint64_t) * Nb);
+	size_t nb = 0;
+	const std::uint64_t room = avail >= sizeof(fixed) ? (avail - sizeof(fixed)) / sizeof(std::uint64_t) : 0;
+	if (!numBlocksBounded((size_t)std::min<std::uint64_t>(room, (std::uint64_t)1 << 40), &nb)) return;
+	resizeBlockOffset(nb);
+	if (Nb) {
+		fid.read((char*)blockOffset, sizeof(std::uint64_t) * Nb);
+		if ((size_t)fid.gcount() != sizeof(std::uint64_t) * Nb) resizeBlockOffset(0);
+	}
 }
 
 int klb_image_header::readHeader(const char* filename)
@@ -118,7 +149,11 @@ int klb_image_header::readHeader(const char* filename)
 		std::cout << "ERROR: klb_image_header::readHeader : file " << filename << " could not be opened to read header" << std::endl;
 		return 2;
 	}
-	readHeader(fid);
+	try { readHeader(fid); } catch (const std::bad_alloc&) { resizeBlockOffset(0); }
+	if (Nb == 0) {
+		std::cout << "ERROR: klb_image_header::readHeader : file " << filename << " holds no complete header / blockOffset table" << std::endl;
+		return 2;
+	}
 	return 0;
 }
 

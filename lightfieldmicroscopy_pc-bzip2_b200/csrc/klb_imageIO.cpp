@@ -19,6 +19,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 #include <cuda_runtime.h>
@@ -35,8 +37,22 @@ struct Settings {
 	int first_device = 0;
 	int ndev = -1;
 } g_set;
-lfm_stats g_stats;
-std::string g_err;
+// statistics / error text of the last call are per calling thread; the shard worker threads of a call report through their
+// ShardOut / per-shard slots and the calling thread merges them after the join.
+thread_local lfm_stats g_stats;
+thread_local std::string g_err;
+// The engines (one per GPU: stream, workspace, pinned staging) are shared by every klb_imageIO object of the process, so the
+// compute entry points of the library are serialised; calls stay synchronous as in the reference (SURVEY 8b "Threading").
+std::recursive_mutex g_api_mu;
+#define LFM_API_LOCK() std::lock_guard<std::recursive_mutex> lfm_api_lock_(g_api_mu); DeviceGuard lfm_device_guard_
+// the caller's current CUDA device is restored when a call returns (a framework above us keeps its own notion of it)
+#define LFM_CATCH catch (const std::bad_alloc&) { g_err = "out of host memory"; return LFM_ERR_CREATE; } \
+                  catch (const std::exception& ex_) { g_err = ex_.what(); return LFM_ERR_BZIP; }
+struct DeviceGuard {
+	int prev = -1;
+	DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+	~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 int current_way() { if (g_set.way < 0) { int w = env_int("LFM_PREDICTOR_WAY", LFM_PREDICTOR_WAY_DEFAULT); g_set.way = (w >= 0 && w <= 2) ? w : 0; } return g_set.way; }
@@ -83,18 +99,36 @@ void slab_frames(const klb_image_header& h, const Layout& L, uint64_t s0, uint64
 		f1 = std::max(f1, z1 + h.xyzct[2] * (c1 + (uint64_t)h.xyzct[3] * t1));
 	}
 }
+// Slab boundaries of D shards: shard d owns slabs [cut[d], cut[d+1]) -- a contiguous block-id and payload range.  With
+// pair_frames (video stack + predictor: an odd frame is predicted from the even frame before it, `video_bit & z`) a shard
+// never starts on an odd frame, so the writer and the reader of a shard have everything they need inside it.
+std::vector<uint64_t> shard_cuts(const klb_image_header& h, const Layout& L, int D, bool pair_frames)
+{
+	std::vector<uint64_t> cut(D + 1);
+	for (int d = 0; d <= D; d++) {
+		uint64_t s = L.nSlabs * (uint64_t)d / (uint64_t)D;
+		if (d > 0) s = std::max(s, cut[d - 1]);
+		if (pair_frames && d < D) {
+			for (; s < L.nSlabs; s++) { uint64_t f0, f1; slab_frames(h, L, s, s + 1, f0, f1); if (!(f0 & 1)) break; }
+		}
+		cut[d] = d == D ? L.nSlabs : s;
+	}
+	return cut;
+}
 StackDesc make_desc(const klb_image_header& h, int way)
 {
 	StackDesc s;
 	for (int d = 0; d < 5; d++) { s.xyzct[d] = h.xyzct[d]; s.blockSize[d] = h.blockSize[d]; }
 	s.Nnum = h.Nnum ? h.Nnum : 1; s.way = way;
+	s.codec = h.compressionType == KLB_COMPRESSION_TYPE::NONE ? 0 : 1;
 	return s;
 }
 int validate(const klb_image_header& h, bool writing)
 {
-	if (h.compressionType != KLB_COMPRESSION_TYPE::BZIP2) {
-		if (h.compressionType == KLB_COMPRESSION_TYPE::NONE || h.compressionType == KLB_COMPRESSION_TYPE::ZLIB) {
-			std::cout << "ERROR: lfm_b200: only BZIP2 block compression is implemented by the GPU engine" << std::endl;
+	if (h.compressionType != KLB_COMPRESSION_TYPE::BZIP2 && h.compressionType != KLB_COMPRESSION_TYPE::NONE) {
+		if (h.compressionType == KLB_COMPRESSION_TYPE::ZLIB) {
+			std::cout << "ERROR: lfm_b200: ZLIB block payloads (src/klb_imageIO.cpp:222-252) are not " << (writing ? "written" : "decoded")
+			          << " by the GPU engine; supported KLB_COMPRESSION_TYPE values: BZIP2 (1) and NONE (0)" << std::endl;
 			return LFM_ERR_UNSUPPORTED;
 		}
 		std::cout << "ERROR: workerfunc: compression type not implemented" << std::endl;
@@ -184,7 +218,7 @@ void d2h_staged(Engine& e, void* dst, const void* src, size_t bytes, cudaStream_
 
 // ------------------------------------------------------------------------------------------------ compress core
 struct ShardOut {
-	std::vector<uint32_t> sizes; int rc = 0; CompressStats st; double ms_h2d = 0, ms_d2h = 0;
+	std::vector<uint32_t> sizes; int rc = 0; CompressStats st; double ms_h2d = 0, ms_d2h = 0; std::string err;
 	const uint8_t* d_payload = nullptr; uint64_t payload_bytes = 0; int device = 0;      // streams stay on the GPU until fetched
 };
 enum { UB_IMG = 0, UB_SYM = 1, UB_PAY = 2, UB_F0 = 3 };
@@ -231,11 +265,14 @@ int compress_core(const FrameSource& src, klb_image_header& h, std::vector<Shard
 	g_stats.predictor = k;
 
 	const int D = (int)std::min<uint64_t>((uint64_t)ndev, L.nSlabs);
+	const std::vector<uint64_t> cut = shard_cuts(h, L, D, k != 0 && video);
 	shards.assign(D, ShardOut());
 	shardFirstBlock.assign(D, 0);
 	auto work = [&](int d) {
 		ShardOut& out = shards[d];
-		const uint64_t s0 = L.nSlabs * d / D, s1 = L.nSlabs * (d + 1) / D;
+		const uint64_t s0 = cut[d], s1 = cut[d + 1];
+		shardFirstBlock[d] = s0 * L.blocksPerSlab;
+		if (s0 == s1) return;                               // fewer indivisible slab groups than GPUs
 		uint64_t f0, f1; slab_frames(h, L, s0, s1, f0, f1);
 		if (k != 0 && video && (f0 & 1)) f0--;              // an odd first frame is predicted from the even one before it
 		const uint64_t nf = f1 - f0 + 1;
@@ -262,7 +299,7 @@ int compress_core(const FrameSource& src, klb_image_header& h, std::vector<Shard
 		out.rc = e.compress_blocks(sym_base, desc, first, count, out.sizes.data(), &out.d_payload, &out.payload_bytes, &out.st);
 		if (k != 0 && out.rc == 0) out.st.ms_predict = e.last_predict_ms();
 		out.ms_h2d = now_ms() - t0;                         // H2D + kernels (the copy is asynchronous and overlaps nothing yet)
-		if (out.rc) { g_err = e.last_error(); return; }
+		if (out.rc) { out.err = e.last_error(); return; }
 	};
 	if (D == 1) work(0);
 	else {
@@ -270,7 +307,7 @@ int compress_core(const FrameSource& src, klb_image_header& h, std::vector<Shard
 		for (int d = 0; d < D; d++) th.emplace_back(work, d);
 		for (auto& t : th) t.join();
 	}
-	for (auto& s : shards) if (s.rc) return s.rc;
+	for (auto& s : shards) if (s.rc) { g_err = s.err; return s.rc; }
 	// host-side inclusive prefix sum of the block sizes -> blockOffset[] (END offsets)
 	uint64_t acc = 0;
 	for (int d = 0; d < D; d++) {
@@ -369,6 +406,10 @@ int decompress_core(const klb_image_header& h, const PayloadSource& psrc, uint16
 	const Layout L = make_layout(h);
 	if (L.Nb != h.Nb) return LFM_ERR_BZIP;
 	if (h.blockOffset[L.Nb - 1] > payload_size) { std::cerr << "ERROR: lfm_b200: file is truncated" << std::endl; return LFM_ERR_BZIP; }
+	// the table comes from an untrusted file: END offsets must not decrease and none may point past the payload (an ROI read
+	// skips blocks, so checking only the last one is not enough)
+	for (uint64_t i = 1; i < L.Nb; i++)
+		if (h.blockOffset[i] < h.blockOffset[i - 1]) { std::cerr << "ERROR: lfm_b200: corrupt blockOffset table" << std::endl; return LFM_ERR_BZIP; }
 	const StackDesc desc = make_desc(h, way);
 	const int k = h.headerVersion & 0x7F, video = (h.headerVersion & 0x80) ? 1 : 0;
 	if (k > 7) return LFM_ERR_UNSUPPORTED;
@@ -400,14 +441,19 @@ int decompress_core(const klb_image_header& h, const PayloadSource& psrc, uint16
 		if ((f0 & 1) && slabs.front() > 0) slabs.insert(slabs.begin(), slabs.front() - 1);
 	}
 	const bool contiguous = !slabs.empty() && (slabs.back() - slabs.front() + 1 == slabs.size());
-	const int D = (full && contiguous) ? (int)std::min<uint64_t>((uint64_t)ndev, slabs.size()) : 1;
+	// Full reads are sharded over the GPUs by slab ranges whose frame ranges are disjoint: with c or t blocked (blockSize[3] or
+	// blockSize[4] > 1) the frames of neighbouring slabs interleave, and one GPU decodes the stack.
+	const bool disjoint = h.blockSize[3] == 1 && h.blockSize[4] == 1;
+	const int D = (full && contiguous && disjoint && slabs.size() == L.nSlabs) ? (int)std::min<uint64_t>((uint64_t)ndev, slabs.size()) : 1;
+	const std::vector<uint64_t> cut = shard_cuts(h, L, D, k != 0 && video);
 
 	std::vector<int> rcs(D, 0);
 	std::vector<DecompressStats> sts(D);
 	std::vector<double> h2d(D, 0), d2h(D, 0);
+	std::vector<std::string> errs(D);
 	auto work = [&](int d) {
 		// this shard's slabs
-		std::vector<uint64_t> my(slabs.begin() + slabs.size() * d / D, slabs.begin() + slabs.size() * (d + 1) / D);
+		std::vector<uint64_t> my = D == 1 ? slabs : std::vector<uint64_t>(slabs.begin() + cut[d], slabs.begin() + cut[d + 1]);
 		if (my.empty()) return;
 		uint64_t f0 = ~0ull, f1 = 0;
 		for (uint64_t s : my) { uint64_t a, b; slab_frames(h, L, s, s + 1, a, b); f0 = std::min(f0, a); f1 = std::max(f1, b); }
@@ -451,7 +497,7 @@ int decompress_core(const klb_image_header& h, const PayloadSource& psrc, uint16
 		h2d[d] = now_ms() - t0;
 		uint16_t* sym_base = (uint16_t*)dsym.p - f0 * L.fpx;
 		rcs[d] = e.decompress_blocks((const uint8_t*)dpay.p, beg.data(), end.data(), ids.data(), ids.size(), sym_base, desc, &sts[d]);
-		if (rcs[d]) { g_err = e.last_error(); return; }
+		if (rcs[d]) { errs[d] = e.last_error(); return; }
 		const uint16_t* res_base = sym_base;
 		if (k != 0) {
 			rcs[d] = e.unpredict(sym_base, (uint16_t*)dimg.p - f0 * L.fpx, desc, k, video, (uint32_t)f0, (uint32_t)nf);
@@ -487,7 +533,7 @@ int decompress_core(const klb_image_header& h, const PayloadSource& psrc, uint16
 		for (auto& t : th) t.join();
 	}
 	for (int d = 0; d < D; d++) {
-		if (rcs[d]) return rcs[d];
+		if (rcs[d]) { g_err = errs[d]; return rcs[d]; }
 		g_stats.ms_decode = std::max(g_stats.ms_decode, sts[d].ms_decode); g_stats.ms_imtf = std::max(g_stats.ms_imtf, sts[d].ms_imtf); g_stats.ms_ibwt = std::max(g_stats.ms_ibwt, sts[d].ms_ibwt);
 		g_stats.ms_unrle = std::max(g_stats.ms_unrle, sts[d].ms_unrle); g_stats.ms_unpredict = std::max(g_stats.ms_unpredict, sts[d].ms_unpredict);
 		g_stats.ms_h2d = std::max(g_stats.ms_h2d, h2d[d]); g_stats.ms_d2h = std::max(g_stats.ms_d2h, d2h[d]);
@@ -503,30 +549,101 @@ int decompress_core(const klb_image_header& h, const PayloadSource& psrc, uint16
 klb_imageIO::klb_imageIO() { numThreads = (int)std::thread::hardware_concurrency(); }
 klb_imageIO::klb_imageIO(const std::string& filename_) : filename(filename_) { numThreads = (int)std::thread::hardware_concurrency(); }
 
-static int write_file(FILE* fout, klb_image_header& h, std::vector<ShardOut>& shards)
+// Payload -> file.  Every shard streams its compacted streams from its GPU through a ring of pinned staging buffers of its
+// engine (D2H of chunk i+1 in flight while chunk i is pwrite()n at its final file position), one host thread per shard; no
+// payload-sized host allocation (the counterpart of blockWriter's staging queue, src/klb_imageIO.cpp:1152-1217).
+static int stream_payload_to_fd(std::vector<ShardOut>& shards, int fd, uint64_t file_off)
 {
-	h.writeHeader(fout);
-	uint64_t total = 0;
-	for (const auto& s : shards) total += s.payload_bytes;
-	if (total == 0) return LFM_OK;
-	// D2H into the first engine's pinned staging buffer, then one fwrite
-	uint8_t* stage = (uint8_t*)Engine::for_device(shards[0].device).pinned(total);
-	if (!stage) return LFM_ERR_CUDA;
-	int rc = fetch_payload(shards, stage);
+	const double t0 = now_ms();
+	std::vector<uint64_t> off(shards.size(), 0);
+	uint64_t acc = 0;
+	for (size_t d = 0; d < shards.size(); d++) { off[d] = acc; acc += shards[d].payload_bytes; }
+	std::vector<int> rcs(shards.size(), LFM_OK);
+	auto work = [&](size_t d) {
+		ShardOut& s = shards[d];
+		if (!s.payload_bytes) return;
+		cudaSetDevice(s.device);
+		Engine& e = Engine::for_device(s.device);
+		cudaStream_t st = (cudaStream_t)e.stream();
+		uint8_t* pin = (uint8_t*)e.pinned(kStageBufs * kStageChunk);
+		if (!pin) { rcs[d] = LFM_ERR_CUDA; return; }
+		cudaEvent_t ev[kStageBufs];
+		for (auto& x : ev) cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+		const uint64_t bytes = s.payload_bytes;
+		const size_t nch = (size_t)((bytes + kStageChunk - 1) / kStageChunk);
+		auto issue = [&](size_t i) {
+			const uint64_t o = (uint64_t)i * kStageChunk; const size_t len = (size_t)std::min<uint64_t>(kStageChunk, bytes - o);
+			cudaMemcpyAsync(pin + (i % kStageBufs) * kStageChunk, s.d_payload + o, len, cudaMemcpyDeviceToHost, st);
+			cudaEventRecord(ev[i % kStageBufs], st);
+		};
+		for (size_t i = 0; i < std::min<size_t>(nch, kStageBufs - 1); i++) issue(i);
+		for (size_t i = 0; i < nch && rcs[d] == LFM_OK; i++) {
+			if (i + kStageBufs - 1 < nch) issue(i + kStageBufs - 1);       // its buffer was written out in the previous iteration
+			if (cudaEventSynchronize(ev[i % kStageBufs]) != cudaSuccess) { cudaGetLastError(); rcs[d] = LFM_ERR_CUDA; break; }
+			const uint64_t o = (uint64_t)i * kStageChunk; const size_t len = (size_t)std::min<uint64_t>(kStageChunk, bytes - o);
+			const uint8_t* buf = pin + (i % kStageBufs) * kStageChunk;
+			size_t done = 0;
+			while (done < len) {
+				const ssize_t w = pwrite(fd, buf + done, len - done, (off_t)(file_off + off[d] + o + done));
+				if (w <= 0) { rcs[d] = LFM_ERR_CREATE; break; }
+				done += (size_t)w;
+			}
+		}
+		cudaStreamSynchronize(st);
+		for (auto& x : ev) cudaEventDestroy(x);
+	};
+	if (shards.size() == 1) work(0);
+	else {
+		std::vector<std::thread> th;
+		for (size_t d = 0; d < shards.size(); d++) th.emplace_back(work, d);
+		for (auto& t : th) t.join();
+	}
+	g_stats.ms_d2h = now_ms() - t0;
+	g_stats.ms_total += g_stats.ms_d2h;
+	for (int rc : rcs) if (rc) return rc;
+	return LFM_OK;
+}
+
+static int write_all(int fd, const void* p, size_t n, uint64_t at)
+{
+	size_t done = 0;
+	while (done < n) {
+		const ssize_t w = pwrite(fd, (const uint8_t*)p + done, n - done, (off_t)(at + done));
+		if (w <= 0) return LFM_ERR_CREATE;
+		done += (size_t)w;
+	}
+	return LFM_OK;
+}
+
+// header + blockOffset table + payload (src/klb_imageIO.cpp:1145-1225: header first, blocks appended in id order)
+static int write_file(int fd, klb_image_header& h, std::vector<ShardOut>& shards)
+{
+	uint8_t fixed[320]; h.packFixed(fixed);
+	int rc = write_all(fd, fixed, sizeof(fixed), 0);
+	if (rc == 0 && h.Nb) rc = write_all(fd, h.blockOffset, h.Nb * sizeof(uint64_t), sizeof(fixed));
 	if (rc) return rc;
-	return fwrite(stage, 1, total, fout) == total ? LFM_OK : LFM_ERR_CREATE;
+	return stream_payload_to_fd(shards, fd, sizeof(fixed) + h.Nb * sizeof(uint64_t));
+}
+
+static int write_stack_to_file(const std::string& filename, const FrameSource& src, klb_image_header& header)
+{
+	LFM_API_LOCK();
+	const int fd = open(filename.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+	if (fd < 0) { std::cout << "ERROR: file " << filename << " could not be opened" << std::endl; return LFM_ERR_CREATE; }
+	int rc;
+	try {
+		std::vector<ShardOut> shards; std::vector<uint64_t> first;
+		rc = compress_core(src, header, shards, first);
+		if (rc == 0) rc = write_file(fd, header, shards);
+	} catch (const std::bad_alloc&) { g_err = "out of host memory"; rc = LFM_ERR_CREATE; }
+	if (close(fd) != 0 && rc == 0) rc = LFM_ERR_CREATE;
+	return rc;
 }
 
 int klb_imageIO::writeImage(const char* img, int /*numThreads*/)
 {
-	FILE* fout = fopen(filename.c_str(), "wb");
-	if (fout == NULL) { std::cout << "ERROR: file " << filename << " could not be opened" << std::endl; return LFM_ERR_CREATE; }
 	FrameSource src; src.base = (const uint16_t*)img;
-	std::vector<ShardOut> shards; std::vector<uint64_t> first;
-	int rc = compress_core(src, header, shards, first);
-	if (rc == 0) rc = write_file(fout, header, shards);
-	fclose(fout);
-	return rc;
+	return write_stack_to_file(filename, src, header);
 }
 
 int klb_imageIO::writeImageStackSlices(const char** img, int /*numThreads*/)
@@ -535,18 +652,13 @@ int klb_imageIO::writeImageStackSlices(const char** img, int /*numThreads*/)
 		std::cout << "ERROR: writeImageStackSlices: number of channels or number of time points must be 1 for this API call" << std::endl;
 		return LFM_ERR_OPEN;
 	}
-	FILE* fout = fopen(filename.c_str(), "wb");
-	if (fout == NULL) { std::cout << "ERROR: file " << filename << " could not be opened" << std::endl; return LFM_ERR_CREATE; }
 	FrameSource src; src.slices = (const uint16_t* const*)img;
-	std::vector<ShardOut> shards; std::vector<uint64_t> first;
-	int rc = compress_core(src, header, shards, first);
-	if (rc == 0) rc = write_file(fout, header, shards);
-	fclose(fout);
-	return rc;
+	return write_stack_to_file(filename, src, header);
 }
 
 int klb_imageIO::writeImageToMemory(const char* img, std::string& fileBytes)
-{
+try {
+	LFM_API_LOCK();
 	FrameSource src; src.base = (const uint16_t*)img;
 	std::vector<ShardOut> shards; std::vector<uint64_t> first;
 	int rc = compress_core(src, header, shards, first);
@@ -558,23 +670,25 @@ int klb_imageIO::writeImageToMemory(const char* img, std::string& fileBytes)
 	memcpy(&fileBytes[0], fixed, 320);
 	memcpy(&fileBytes[320], header.blockOffset, header.Nb * 8);
 	return fetch_payload(shards, (uint8_t*)&fileBytes[320 + header.Nb * 8]);
-}
+} LFM_CATCH
 
 int klb_imageIO::readImageFromMemory(const char* fileBytes, size_t fileSize, char* imgOut, const klb_ROI* ROI)
-{
+try {
+	LFM_API_LOCK();
 	if (fileSize < 320) return LFM_ERR_BZIP;
 	header.unpackFixed((const uint8_t*)fileBytes);
-	for (int d = 0; d < 5; d++) if (header.blockSize[d] == 0) return LFM_ERR_BZIP;
-	header.resizeBlockOffset(header.calculateNumBlocks());
-	if (fileSize < 320 + header.Nb * 8) return LFM_ERR_BZIP;
+	size_t nb = 0;
+	if (!header.numBlocksBounded((fileSize - 320) / 8, &nb) || nb == 0) return LFM_ERR_BZIP;    // the table must fit the buffer
+	header.resizeBlockOffset(nb);
 	memcpy(header.blockOffset, fileBytes + 320, header.Nb * 8);
 	PayloadSource ps; ps.base = (const uint8_t*)fileBytes + 320 + header.Nb * 8; ps.size = fileSize - 320 - header.Nb * 8;
 	return decompress_core(header, ps, (uint16_t*)imgOut, ROI);
-}
+} LFM_CATCH
 
 // header (+ blockOffset table) of the file, then decode straight from the open file: only the needed byte ranges are read
 static int read_from_file(const std::string& filename, klb_image_header& header, uint16_t* out, const klb_ROI* roi)
-{
+try {
+	LFM_API_LOCK();
 	if (filename.empty()) { std::cerr << "ERROR: Filename has not been defined. We cannot read image" << std::endl; return LFM_ERR_OPEN; }
 	if (header.Nb == 0) {
 		int err = header.readHeader(filename.c_str());
@@ -589,7 +703,7 @@ static int read_from_file(const std::string& filename, klb_image_header& header,
 	const int rc = decompress_core(header, ps, out, roi);
 	close(fd);
 	return rc;
-}
+} LFM_CATCH
 
 int klb_imageIO::readImageFull(char* imgOut, int /*numThreads*/) { return read_from_file(filename, header, (uint16_t*)imgOut, NULL); }
 
@@ -612,12 +726,12 @@ int lfmSetDevices(int first_device, int count)
 int writeLFMstackEx(const void* im, const char* filename, const uint32_t xyzct[5], enum KLB_DATA_TYPE dataType, int numThreads,
                     const float32_t pixelSize[5], const uint32_t blockSize[5], enum KLB_COMPRESSION_TYPE compressionType,
                     const char metadata[256], uint8_t headerVersion, uint8_t Nnum)
-{
+try {
 	if (!filename || !*filename) return LFM_ERR_OPEN;
 	klb_imageIO io{ std::string(filename) };
 	io.header.setHeader(xyzct, dataType, pixelSize, blockSize, compressionType, metadata, headerVersion, Nnum);
 	return io.writeImage((const char*)im, numThreads);
-}
+} LFM_CATCH
 
 int readLFMheaderEx(const char* filename, uint8_t* headerVersion, uint8_t* Nnum)
 {
@@ -631,7 +745,8 @@ int readLFMheaderEx(const char* filename, uint8_t* headerVersion, uint8_t* Nnum)
 
 int lfmCompressToMemory(const void* im, const uint32_t xyzct[5], const uint32_t blockSize[5], uint8_t headerVersion, uint8_t Nnum,
                         void** file_bytes, uint64_t* file_size)
-{
+try {
+	LFM_API_LOCK();
 	klb_imageIO io;
 	io.header.setHeader(xyzct, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize, KLB_COMPRESSION_TYPE::BZIP2, NULL, headerVersion, Nnum);
 	FrameSource src; src.base = (const uint16_t*)im;
@@ -649,11 +764,12 @@ int lfmCompressToMemory(const void* im, const uint32_t xyzct[5], const uint32_t 
 	if (rc) { free(p); return rc; }
 	*file_bytes = p; *file_size = hdr + total;
 	return 0;
-}
+} LFM_CATCH
 
 int lfmCompressToBuffer(const void* im, const uint32_t xyzct[5], const uint32_t blockSize[5], uint8_t headerVersion, uint8_t Nnum,
                         void* file_bytes, uint64_t capacity, uint64_t* file_size)
-{
+try {
+	LFM_API_LOCK();
 	klb_imageIO io;
 	io.header.setHeader(xyzct, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize, KLB_COMPRESSION_TYPE::BZIP2, NULL, headerVersion, Nnum);
 	FrameSource src; src.base = (const uint16_t*)im;
@@ -669,13 +785,13 @@ int lfmCompressToBuffer(const void* im, const uint32_t xyzct[5], const uint32_t 
 	io.header.packFixed(p);
 	memcpy(p + 320, io.header.blockOffset, io.header.Nb * 8);
 	return fetch_payload(shards, p + hdr);
-}
+} LFM_CATCH
 
 int lfmDecompressFromMemory(const void* file_bytes, uint64_t file_size, void* im)
-{
+try {
 	klb_imageIO io;
 	return io.readImageFromMemory((const char*)file_bytes, (size_t)file_size, (char*)im, NULL);
-}
+} LFM_CATCH
 
 uint64_t lfmNumBlocks(const uint32_t xyzct[5], const uint32_t blockSize[5])
 {
@@ -687,7 +803,8 @@ uint64_t lfmNumBlocks(const uint32_t xyzct[5], const uint32_t blockSize[5])
 
 int lfmCompressDevice(const void* d_im, const uint32_t xyzct[5], const uint32_t blockSize[5], uint8_t headerVersion, uint8_t Nnum,
                       uint8_t* storedHeaderVersion, uint64_t* blockOffset, uint64_t numBlocks, const void** d_payload, uint64_t* payload_bytes)
-{
+try {
+	LFM_API_LOCK();
 	klb_image_header h;
 	h.setHeader(xyzct, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize, KLB_COMPRESSION_TYPE::BZIP2, NULL, headerVersion, Nnum);
 	int rc = validate(h, true);
@@ -735,11 +852,12 @@ int lfmCompressDevice(const void* d_im, const uint32_t xyzct[5], const uint32_t 
 	if (k != 0) g_stats.ms_predict = e.last_predict_ms();
 	g_stats.gpu_launches += st.launches; g_stats.periodic_blocks = st.periodic_blocks; g_stats.payload_bytes = pb;
 	return 0;
-}
+} LFM_CATCH
 
 int lfmDecompressDevice(const void* d_payload, const uint64_t* blockOffset, uint64_t numBlocks, const uint32_t xyzct[5],
                         const uint32_t blockSize[5], uint8_t storedHeaderVersion, uint8_t Nnum, void* d_out)
-{
+try {
+	LFM_API_LOCK();
 	klb_image_header h;
 	h.setHeader(xyzct, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize, KLB_COMPRESSION_TYPE::BZIP2, NULL, storedHeaderVersion, Nnum);
 	int rc = validate(h, false);
@@ -779,14 +897,77 @@ int lfmDecompressDevice(const void* d_payload, const uint64_t* blockOffset, uint
 	g_stats.ms_decode = st.ms_decode; g_stats.ms_imtf = st.ms_imtf; g_stats.ms_ibwt = st.ms_ibwt; g_stats.ms_unrle = st.ms_unrle;
 	g_stats.gpu_launches = st.launches;
 	return 0;
-}
+} LFM_CATCH
+
+// ---- multi-process sharding (one process per GPU): compress now, write once the offsets are known
+namespace { thread_local std::vector<ShardOut> g_pending; }
+
+int lfmShardCompress(const void* im_local, const uint32_t xyzct_local[5], const uint32_t blockSize[5], uint8_t headerVersion, uint8_t Nnum,
+                     uint8_t* storedHeaderVersion, uint32_t* blockSizes, uint64_t numBlocks, uint64_t* payload_bytes)
+try {
+	LFM_API_LOCK();
+	g_pending.clear();
+	klb_imageIO io;
+	io.header.setHeader(xyzct_local, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize, KLB_COMPRESSION_TYPE::BZIP2, NULL, headerVersion, Nnum);
+	FrameSource src; src.base = (const uint16_t*)im_local;
+	std::vector<ShardOut> shards; std::vector<uint64_t> first;
+	int rc = compress_core(src, io.header, shards, first);
+	if (rc) return rc;
+	if (numBlocks != io.header.Nb) return LFM_ERR_OPEN;
+	uint64_t total = 0, prev = 0;
+	for (uint64_t i = 0; i < io.header.Nb; i++) { blockSizes[i] = (uint32_t)(io.header.blockOffset[i] - prev); prev = io.header.blockOffset[i]; }
+	for (const auto& s : shards) total += s.payload_bytes;
+	if (storedHeaderVersion) *storedHeaderVersion = io.header.headerVersion;
+	if (payload_bytes) *payload_bytes = total;
+	g_pending.swap(shards);
+	return LFM_OK;
+} LFM_CATCH
+
+int lfmShardWritePayload(const char* filename, uint64_t file_offset)
+try {
+	LFM_API_LOCK();
+	if (!filename || !*filename) return LFM_ERR_OPEN;
+	const int fd = open(filename, O_WRONLY);
+	if (fd < 0) return LFM_ERR_CREATE;
+	int rc = stream_payload_to_fd(g_pending, fd, file_offset);
+	if (close(fd) != 0 && rc == 0) rc = LFM_ERR_CREATE;
+	return rc;
+} LFM_CATCH
+
+int lfmShardFetchPayload(void* dst, uint64_t capacity)
+try {
+	LFM_API_LOCK();
+	uint64_t total = 0;
+	for (const auto& s : g_pending) total += s.payload_bytes;
+	if (!dst || capacity < total) return LFM_ERR_CREATE;
+	return fetch_payload(g_pending, (uint8_t*)dst);
+} LFM_CATCH
+
+int lfmWriteHeader(const char* filename, const uint32_t xyzct[5], const uint32_t blockSize[5], uint8_t storedHeaderVersion, uint8_t Nnum,
+                   const uint64_t* blockOffset, uint64_t numBlocks)
+try {
+	if (!filename || !*filename) return LFM_ERR_OPEN;
+	klb_image_header h;
+	h.setHeader(xyzct, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize, KLB_COMPRESSION_TYPE::BZIP2, NULL, storedHeaderVersion, Nnum);
+	for (int d = 0; d < 5; d++) { if (h.xyzct[d] == 0 || h.blockSize[d] == 0) return LFM_ERR_BZIP; h.blockSize[d] = std::min(h.blockSize[d], h.xyzct[d]); }
+	if (numBlocks == 0 || numBlocks != h.calculateNumBlocks()) return LFM_ERR_OPEN;
+	const int fd = open(filename, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+	if (fd < 0) return LFM_ERR_CREATE;
+	uint8_t fixed[320]; h.packFixed(fixed);
+	int rc = write_all(fd, fixed, sizeof(fixed), 0);
+	if (rc == 0) rc = write_all(fd, blockOffset, (size_t)numBlocks * 8, sizeof(fixed));
+	if (rc == 0 && ftruncate(fd, (off_t)(sizeof(fixed) + numBlocks * 8 + blockOffset[numBlocks - 1])) != 0) rc = LFM_ERR_CREATE;
+	if (close(fd) != 0 && rc == 0) rc = LFM_ERR_CREATE;
+	return rc;
+} LFM_CATCH
 
 int lfmGetLastStats(lfm_stats* out) { if (!out) return 1; *out = g_stats; return 0; }
 const char* lfmLastError(void) { return g_err.c_str(); }
 
 int lfmDebugPredictDevice(const void* d_in, void* d_out, const uint32_t xyzct[5], uint8_t Nnum, int k, int video, int inverse,
                           int reps, float* ms_per_rep)
-{
+try {
+	LFM_API_LOCK();
 	if (current_ndev() <= 0) return LFM_ERR_CUDA;
 	if (reps < 1 || !ms_per_rep) return LFM_ERR_OPEN;
 	Engine& e = Engine::for_device(g_set.first_device);
@@ -809,10 +990,11 @@ int lfmDebugPredictDevice(const void* d_in, void* d_out, const uint32_t xyzct[5]
 	cudaEventDestroy(a); cudaEventDestroy(b);
 	*ms_per_rep = ms / (float)reps;
 	return rc;
-}
+} LFM_CATCH
 
 int lfmDebugEncodeBlock(const void* bytes, uint32_t n, uint8_t* rle1, uint8_t* bwt, uint16_t* mtfv, uint8_t* stream, uint32_t info[8])
-{
+try {
+	LFM_API_LOCK();
 	if (n == 0 || (n & 1)) return LFM_ERR_OPEN;
 	if (current_ndev() <= 0) return LFM_ERR_CUDA;
 	Engine& e = Engine::for_device(g_set.first_device);
@@ -838,6 +1020,6 @@ int lfmDebugEncodeBlock(const void* bytes, uint32_t n, uint8_t* rle1, uint8_t* b
 	cudaStreamSynchronize((cudaStream_t)e.stream());
 	info[0] = nblock; info[1] = J[2]; info[2] = J[3]; info[3] = J[5]; info[4] = J[4]; info[5] = J[6]; info[6] = J[7]; info[7] = (uint32_t)pb;
 	return 0;
-}
+} LFM_CATCH
 
 }  // extern "C"

@@ -976,14 +976,19 @@ k_unpredict_bands(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H,
                   uint32_t z_start, uint32_t z_step, uint32_t count, int R, int ncomp, uint32_t* flags)
 {
 	extern __shared__ __align__(16) uint8_t ub_smem[];
-	__shared__ uint32_t s_avail, s_step;
+	__shared__ uint32_t s_avail, s_step, s_ticket;
 	__builtin_assume(T >= 2);
 	const int tid = (int)threadIdx.x;
 	const int TT = T * T;
 	const int tilesX = (W + T - 1) / T, tilesY = (H + T - 1) / T;
 	const int nbands = (tilesY + R - 1) / R;
-	const uint32_t fi = blockIdx.x % count;
-	const int band = (int)(blockIdx.x / count);
+	// a band waits for the band above it: the logical (band-major) id is a ticket taken when the CTA starts running, so a
+	// CTA only ever waits for a CTA that is already resident -- whatever order the hardware dispatches blockIdx in
+	if (tid == 0) s_ticket = atomicAdd(flags + (size_t)gridDim.x, 1u);
+	__syncthreads();
+	const uint32_t bid = s_ticket;
+	const uint32_t fi = bid % count;
+	const int band = (int)(bid / count);
 	const uint32_t z = z_start + fi * z_step;
 	const uint64_t fpx = (uint64_t)W * H;
 	const int last_skew = 2 * T - 2 + R;                         // u + v + j + 1 of the band's last thread
@@ -1152,9 +1157,9 @@ static int launch_unpredict_bands(const uint16_t* sym, uint16_t* out, int W, int
 	const int nbands = (tilesY + R - 1) / R;
 	const uint64_t nctas = (uint64_t)nbands * count;
 	if (nctas > 0x7fffffffull) return 2;
-	uint32_t* flags = ub_flags((size_t)nctas);
+	uint32_t* flags = ub_flags((size_t)nctas + 1);              // progress flag per CTA + the ticket counter
 	if (!flags) return 2;
-	cudaMemsetAsync(flags, 0, (size_t)nctas * 4, st);
+	cudaMemsetAsync(flags, 0, ((size_t)nctas + 1) * 4, st);
 	const size_t smem = (size_t)4 * ((R + 1) * TT + T + 2) * 2;
 	#define LFM_UB(KK) do { if (zflag) k_unpredict_bands<WAY, KK, 1><<<(unsigned)nctas, ncomp + UB_HELPERS, smem, st>>>(sym, out, W, H, T, z_start, z_step, count, R, ncomp, flags); \
 		else k_unpredict_bands<WAY, KK, 0><<<(unsigned)nctas, ncomp + UB_HELPERS, smem, st>>>(sym, out, W, H, T, z_start, z_step, count, R, ncomp, flags); } while (0)

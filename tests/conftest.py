@@ -128,6 +128,53 @@ def lf_synth(shape_zyx, nnum, seed=12345):
     return img
 
 
+def lf_synth_int(shape_zyx, nnum, seed=1, device="cpu", z0=0):
+    """Full-size deterministic light-field stacks (torch tensor, int16 view of uint16 pixels): the LF-synth pattern in INTEGER
+    arithmetic only (triangle waves, quadratic microlens vignetting, hashed noise scaled by an integer square root), so that the
+    GPU box generates in a second exactly the bytes the committed md5s of tests/golden/fullsize.json were computed on.
+    Frames z0 .. z0 + Z - 1 of the (unbounded) stack."""
+    import torch
+    Z, Y, X = shape_zyx
+    out = torch.empty((Z, Y, X), dtype=torch.int16, device=device)
+    x = torch.arange(X, dtype=torch.int64, device=device)[None, None, :]
+    y = torch.arange(Y, dtype=torch.int64, device=device)[None, :, None]
+    tri = lambda v, p: ((v % p) - p // 2).abs()
+    u2 = 2 * (x % nnum) - (nnum - 1); v2 = 2 * (y % nnum) - (nnum - 1)
+    V = (256 - (u2 * u2 * 160) // (nnum * nnum)) * (256 - (v2 * v2 * 160) // (nnum * nnum))          # <= 65536
+    M31 = (1 << 31) - 1
+    step = max(1, (1 << 24) // (X * Y))
+    for a in range(0, Z, step):
+        b = min(Z, a + step)
+        z = torch.arange(z0 + a, z0 + b, dtype=torch.int64, device=device)[:, None, None]
+        S = 250 + 3 * tri(x + 5 * z, 194) + 2 * tri(y + z, 262) + tri(x + y, 74) * 4
+        m = 100 + (S * V >> 16)
+        g = torch.zeros((b - a, Y, X), dtype=torch.int64, device=device)
+        h = (x * 73856093 + y * 19349663 + z * 83492791 + seed * 2654435761) & M31
+        for _ in range(4):
+            h = (h * 1103515245 + 12345) & M31
+            h = h ^ (h >> 13)
+            g += (h >> 7) & 255
+        r = torch.sqrt(m.to(torch.float64)).to(torch.int64)                                           # exact: m < 2^52
+        pix = (m + ((g - 510) * r) // 148).clamp_(0, 65535)
+        out[a:b] = (pix - ((pix >> 15) << 16)).to(torch.int16)                                        # uint16 bits in an int16 tensor
+    return out
+
+
+def load_reference_gpu(way):
+    """the UNMODIFIED reference built for the GPU (oracle/_ref/liblfmref_gpu_way<w>.so, oracle/build_ref.py): its CUDA predictor,
+    thrust sort / reduce and threaded CPU bzip2 exactly as shipped.  None when the library (or a CUDA device) is absent."""
+    so = os.path.join(ORACLE_DIR, "_ref", "liblfmref_gpu_way%d.so" % way)
+    if not os.path.exists(so) or not has_cuda():
+        return None
+    try:
+        lib = C.CDLL(so)
+    except OSError:
+        return None
+    lib.ref_write.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.ref_read_full.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+    return lib
+
+
 def golden_img_tif():
     """the reference's only fixture, testData/img.tif (101x151x29 uint16), stored as npz (tests/golden/make_golden.py)"""
     return np.load(os.path.join(GOLDEN, "img_tif_101x151x29_u16.npz"))["img"]

@@ -85,7 +85,38 @@ def test_slab_partition_is_a_partition():
             assert p[2] % 2 == 0 or p[2] == z          # video stacks: every shard starts on an even frame
 
 
-def _worker(rank, world, port, tmpdir):
+class _OracleBackend:
+    """CPU stand-in for the GPU engine (tests only): the oracle writes the slab as a stack of its own, the payload is cut out"""
+
+    def __init__(self, ora, tmpdir, rank, bs):
+        self.ora, self.fn, self.bs, self.payload = ora, os.path.join(tmpdir, "slab_%d.lfm" % rank), bs, b""
+
+    def select_mode(self, f0):
+        return self.ora.select(f0, 13, 0)[0]
+
+    def compress(self, frames, hv):
+        rc, _ = self.ora.write(frames, self.fn, hv, 13, 0, block_size=self.bs)
+        assert rc == 0
+        blob = open(self.fn, "rb").read()
+        nb = int(np.prod([-(-d // b) for d, b in zip((frames.shape[2], frames.shape[1], frames.shape[0]), self.bs[:3])]))
+        ends = np.frombuffer(blob[320:320 + 8 * nb], "<u8")
+        self.payload = blob[320 + 8 * nb:]
+        return np.diff(np.concatenate([[0], ends])).astype(np.uint32), len(self.payload)
+
+    def write_payload(self, filename, off):
+        fd = os.open(filename, os.O_WRONLY)
+        try:
+            os.pwrite(fd, self.payload, off)
+        finally:
+            os.close(fd)
+
+    def read_frames(self, filename, xyzct, z0, z1):
+        rc, out = self.ora.read(filename, (xyzct[2], xyzct[1], xyzct[0]), 0)
+        assert rc == 0
+        return out[z0:z1]
+
+
+def _worker(rank, world, port, tmpdir, gpu):
     import torch.distributed as dist
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "lightfieldmicroscopy_pc-bzip2_b200"))
     import distributed as D
@@ -94,31 +125,39 @@ def _worker(rank, world, port, tmpdir):
     ora = Oracle()
     a = lf_synth((21, 70, 90), 13, seed=5)
     xyzct = (90, 70, 21, 1, 1); bs = (32, 32, 4, 1, 1)
-
-    def compress_slab(frames, hv):          # CPU stand-in for the GPU engine (tests only): the oracle
-        fn = os.path.join(tmpdir, "slab_%d.lfm" % rank)
-        rc, _ = ora.write(frames, fn, hv, 13, 0, block_size=bs)
-        assert rc == 0
-        return open(fn, "rb").read()
-
-    def select_mode(f0):
-        return ora.select(f0, 13, 0)[0]
-
+    backend = None
+    if gpu:                                   # the product path: every rank drives the GPU engine through the C ABI
+        import torch
+        import lfm_b200
+        lfm_b200.set_devices(rank % torch.cuda.device_count(), 1)
+    else:
+        backend = _OracleBackend(ora, tmpdir, rank, bs)
     for hv, name in ((0, "auto"), (0x80 | 12, "video4")):
         z0, z1 = D.slab_partition(xyzct, bs, world)[rank][2:]
         out = os.path.join(tmpdir, "sharded_%s.lfm" % name)
-        D.write_stack_sharded(a[z0:z1], xyzct, out, header_version=hv, nnum=13, block_size=bs, way=0,
-                              compress_slab=compress_slab, select_mode=select_mode, dist=dist)
+        D.write_stack_sharded(a[z0:z1], xyzct, out, header_version=hv, nnum=13, block_size=bs, way=0, backend=backend, dist=dist)
         if rank == 0:
             whole = os.path.join(tmpdir, "whole_%s.lfm" % name)
             rc, _ = ora.write(a, whole, hv, 13, 0, block_size=bs)
             assert rc == 0
             assert open(out, "rb").read() == open(whole, "rb").read(), "sharded file differs from the single-process file (%s)" % name
+        r0, r1, fr = D.read_stack_sharded(out, way=0, backend=backend, dist=dist)
+        assert (r0, r1) == (z0, z1) and np.array_equal(fr, a[z0:z1]), "sharded read back (%s)" % name
     dist.destroy_process_group()
 
 
 def test_two_rank_sharded_writer_on_gloo(tmp_path):
-    """world_size 2 on CPU: per-rank slabs, size exchange + host prefix sum, pwrite at offsets == single-writer file"""
+    """world_size 2 on CPU: per-rank slabs, size exchange + host prefix sum, pwrite at offsets == single-writer file; sharded read"""
     import torch.multiprocessing as mp
     port = 29500 + (os.getpid() % 500)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), False), nprocs=2, join=True)
+
+
+@pytest.mark.gpu
+def test_two_rank_sharded_writer_gpu_engine(tmp_path):
+    """the same protocol with the GPU engine behind every rank (ranks share the GPUs present: world_size 2 also on a 1-GPU box):
+    lfmShardCompress -> size exchange -> lfmWriteHeader / lfmShardWritePayload at offsets -> file == the oracle's single-writer
+    file; read_stack_sharded (readKLBroiInPlace per rank) returns every rank's frames"""
+    import torch.multiprocessing as mp
+    port = 29500 + ((os.getpid() + 17) % 500)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), True), nprocs=2, join=True)

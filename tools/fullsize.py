@@ -1,10 +1,10 @@
 """BASELINE.json configs[2..4] at FULL size on one B200: device-resident compress / decompress throughput, exact round trip,
 compression ratio, and (C3, C4) the host-buffer e2e path.  Frames are synthesised on the GPU from one LF-synth frame
 (pattern x slow z modulation + Poisson noise), so the 6.7 GB stack of C5 never exists on the host.
-  python tools_fullsize.py [c3 c4 c5]      -> one JSON line per config"""
+  python tools/fullsize.py [c3 c4 c5]      -> one JSON line per config"""
 import ctypes as C, importlib, json, os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import lf_synth
 L = importlib.import_module("lightfieldmicroscopy_pc-bzip2_b200")
 L.set_devices(0, 1)

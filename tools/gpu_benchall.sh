@@ -1,6 +1,6 @@
 #!/bin/bash
 # bench lines of every workload (c2 default, c3s, c4s, c5s) + reference arm
-cd "$(dirname "$0")"; mkdir -p gpurun_out
+cd "$(dirname "$0")/.."; mkdir -p gpurun_out
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; tail -2 gpurun_out/bench_c2.err
 for wl in c3s c4s c5s; do python bench.py --steps 4 --warmup 3 --workload $wl > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err; tail -2 gpurun_out/bench_$wl.err; done
 python - <<'PY'

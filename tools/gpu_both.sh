@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")"
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 1700 python -m pytest tests -q -m gpu --timeout 300 -x 2>&1 | tail -25 > gpurun_out/pytest_gpu.log
 tail -25 gpurun_out/pytest_gpu.log

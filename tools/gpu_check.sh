@@ -1,6 +1,6 @@
 #!/bin/bash
 # first contact with the GPU: the gpu test-suite without -x so one call shows every failing stage
-cd "$(dirname "$0")"
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt; lscpu | grep "Model name" >> gpurun_out/gpu.txt

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round check: gpu tests, smoke, bench (c2, c3s, reference arm), then the ncu launch list of the default bench command
-cd "$(dirname "$0")"
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu --timeout 300 2>&1 | tail -25 > gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log

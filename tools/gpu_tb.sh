@@ -1,6 +1,6 @@
 #!/bin/bash
 # tests, then bench of the workloads named on the command line
-cd "$(dirname "$0")"; mkdir -p gpurun_out
+cd "$(dirname "$0")/.."; mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu --timeout 600 2>&1 | tail -5 > gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
 for wl in "$@"; do st=4; [ $wl == c2 ] && st=10; python bench.py --steps $st --warmup 3 --workload $wl > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err; tail -2 gpurun_out/bench_$wl.err; done
 python - "$@" <<'PY'

@@ -1,5 +1,5 @@
 """hot source lines of one kernel from an .ncu-rep (needs -lineinfo + --import-source on):
-   python tools_ncu_lines.py report.ncu-rep [top_n]"""
+   python tools/ncu_lines.py report.ncu-rep [top_n]"""
 import csv, subprocess, sys, io, collections
 
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40

@@ -1,5 +1,5 @@
 """Summarise every kernel of an .ncu-rep into one small markdown file (run on the GPU box; the report itself is too big to bring back):
-   python tools_ncu_report.py report.ncu-rep out.md [lines_per_kernel]"""
+   python tools/ncu_report.py report.ncu-rep out.md [lines_per_kernel]"""
 import csv, subprocess, sys, io, collections
 
 rep, out = sys.argv[1], sys.argv[2]

@@ -1,7 +1,7 @@
 """predictor-only timings (lfmDebugPredictDevice): ways x predictors x stack shapes; prints GB/s at 4 B/px and checks the round trip"""
 import ctypes as C, importlib, os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import lf_synth
 L = importlib.import_module("lightfieldmicroscopy_pc-bzip2_b200")
 L.set_devices(0, 1)

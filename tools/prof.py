@@ -1,7 +1,7 @@
 """small driver for ncu captures: a few device-resident round trips of one workload"""
 import ctypes as C, importlib, sys, os
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import lf_synth
 L = importlib.import_module("lightfieldmicroscopy_pc-bzip2_b200")
 wl = sys.argv[1] if len(sys.argv) > 1 else "c2"

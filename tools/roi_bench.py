@@ -3,7 +3,7 @@ full read, one XY plane, one 512x512x16 box -- with the selected predictor (whol
 cropped) and with the predictor off (only the KLB blocks that intersect the ROI are read from the file and decoded)."""
 import json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import importlib
 from conftest import lf_synth
 L = importlib.import_module("lightfieldmicroscopy_pc-bzip2_b200")

@@ -1,7 +1,7 @@
 """stage times of one device-resident round trip of a workload (c2 / c3s / c5s), a few repetitions: quick A/B of kernel switches"""
 import ctypes as C, importlib, sys, os, json
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import lf_synth
 L = importlib.import_module("lightfieldmicroscopy_pc-bzip2_b200")
 wl = sys.argv[1] if len(sys.argv) > 1 else "c3s"
