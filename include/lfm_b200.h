@@ -52,6 +52,10 @@ int lfmDecompressFromMemory(const void* file_bytes, uint64_t file_size, void* im
 int lfmCompressDevice(const void* d_im, const uint32_t xyzct[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS],
                       uint8_t headerVersion, uint8_t Nnum, uint8_t* storedHeaderVersion, uint64_t* blockOffset,
                       uint64_t numBlocks, const void** d_payload, uint64_t* payload_bytes);
+/* mode selection alone (predict_and_2DEntropy x 8 + the min-entropy pick, src/klb_imageIO.cpp:2197-2225, :2300-2305) on a
+   device-resident frame of xy[0] x xy[1] pixels: *predictor = winner 0..7, entropy[8] (may be NULL) the candidates' estimates.
+   With one process per GPU the owner of frame 0 calls this and broadcasts the 3 bits. */
+int lfmSelectDevice(const void* d_frame0, const uint32_t xy[2], uint8_t Nnum, int* predictor, float entropy[8]);
 int lfmDecompressDevice(const void* d_payload, const uint64_t* blockOffset, uint64_t numBlocks,
                         const uint32_t xyzct[KLB_DATA_DIMS], const uint32_t blockSize[KLB_DATA_DIMS],
                         uint8_t storedHeaderVersion, uint8_t Nnum, void* d_out);

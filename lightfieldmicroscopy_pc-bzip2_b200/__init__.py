@@ -81,6 +81,7 @@ lib.lfmShardCompress.restype = C.c_int
 lib.lfmShardWritePayload.argtypes = [C.c_char_p, C.c_uint64]; lib.lfmShardWritePayload.restype = C.c_int
 lib.lfmShardFetchPayload.argtypes = [C.c_void_p, C.c_uint64]; lib.lfmShardFetchPayload.restype = C.c_int
 lib.lfmWriteHeader.argtypes = [C.c_char_p, _u32x5, C.c_void_p, C.c_uint8, C.c_uint8, C.c_void_p, C.c_uint64]; lib.lfmWriteHeader.restype = C.c_int
+lib.lfmSelectDevice.argtypes = [C.c_void_p, C.c_uint32 * 2, C.c_uint8, C.POINTER(C.c_int), C.c_void_p]; lib.lfmSelectDevice.restype = C.c_int
 lib.lfmNumBlocks.argtypes = [_u32x5, C.c_void_p]; lib.lfmNumBlocks.restype = C.c_uint64
 lib.lfmGetLastStats.argtypes = [C.POINTER(LfmStats)]; lib.lfmGetLastStats.restype = C.c_int
 lib.lfmLastError.restype = C.c_char_p
@@ -96,7 +97,7 @@ EXPORTS = ["writeKLBstack", "writeKLBstackSlices", "readKLBheader", "readKLBstac
            "lfmSetPredictorWay", "lfmGetPredictorWay", "lfmSetDevices", "writeLFMstackEx", "readLFMheaderEx",
            "lfmCompressToMemory", "lfmCompressToBuffer", "lfmDecompressFromMemory", "lfmCompressDevice", "lfmDecompressDevice", "lfmNumBlocks",
            "lfmGetLastStats", "lfmLastError", "lfmDebugEncodeBlock", "lfmDebugPredictDevice",
-           "lfmShardCompress", "lfmShardWritePayload", "lfmShardFetchPayload", "lfmWriteHeader"]
+           "lfmShardCompress", "lfmShardWritePayload", "lfmShardFetchPayload", "lfmWriteHeader", "lfmSelectDevice"]
 
 
 class LfmError(RuntimeError):

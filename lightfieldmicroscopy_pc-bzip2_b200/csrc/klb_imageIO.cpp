@@ -854,6 +854,30 @@ try {
 	return 0;
 } LFM_CATCH
 
+int lfmSelectDevice(const void* d_frame0, const uint32_t xy[2], uint8_t Nnum, int* predictor, float entropy[8])
+try {
+	LFM_API_LOCK();
+	if (!d_frame0 || !xy || !predictor || xy[0] == 0 || xy[1] == 0) return LFM_ERR_OPEN;
+	if (current_ndev() <= 0) return LFM_ERR_CUDA;
+	StackDesc s;
+	const uint32_t xyzct[5] = { xy[0], xy[1], 1, 1, 1 };
+	for (int d = 0; d < 5; d++) { s.xyzct[d] = xyzct[d]; s.blockSize[d] = xyzct[d]; }
+	s.Nnum = Nnum ? Nnum : 1; s.way = current_way();
+	Engine& e = Engine::for_device(g_set.first_device);
+	cudaSetDevice(e.device());
+	memset(&g_stats, 0, sizeof(g_stats));
+	float ent[8];
+	int k = 0;
+	const double t0 = now_ms();
+	int rc = e.select_mode((const uint16_t*)d_frame0, s, ent, &k);
+	if (rc) { g_err = e.last_error(); return rc; }
+	g_stats.ms_select = now_ms() - t0; g_stats.selected = 1; g_stats.predictor = k; g_stats.gpu_launches = 12;
+	memcpy(g_stats.entropy, ent, sizeof(ent));
+	if (entropy) memcpy(entropy, ent, sizeof(ent));
+	*predictor = k;
+	return LFM_OK;
+} LFM_CATCH
+
 int lfmDecompressDevice(const void* d_payload, const uint64_t* blockOffset, uint64_t numBlocks, const uint32_t xyzct[5],
                         const uint32_t blockSize[5], uint8_t storedHeaderVersion, uint8_t Nnum, void* d_out)
 try {
