@@ -342,7 +342,6 @@ def main():
             block_offset = exchange_sizes(np.cumsum(sizes.astype(np.int64)))
             if rank == 0:
                 L.write_header(fname, (W, H, nfr * world, 1, 1), (96, 96, bdepth, 1, 1), stored, nnum, block_offset)
-            dist.barrier()                             # the file exists and has its final size
             L.shard_write_payload(fname, hdr_bytes + (int(block_offset[rank * nb - 1]) if rank else 0))
             dist.barrier()                             # the file is complete
             torch.cuda.synchronize()

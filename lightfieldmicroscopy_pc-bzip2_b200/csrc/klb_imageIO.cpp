@@ -19,6 +19,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -159,32 +161,76 @@ bool is_pageable(const void* p)
 	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
 	return a.type == cudaMemoryTypeUnregistered;
 }
+// a few persistent host threads for the staging copies (thread start-up per call would cost more than a small copy)
+class CopyPool {
+public:
+	// never destroyed: the workers wait on the condition variables for the life of the process (destroying a condition
+	// variable with waiters blocks in pthread_cond_destroy at exit)
+	static CopyPool& get() { static CopyPool* p = new CopyPool; return *p; }
+	static constexpr int kWorkers = 3;
+	// run f(0..parts-1): part 0 on the calling thread, the others on the workers; returns when all are done
+	template <class F> void run(int parts, F f)
+	{
+		std::unique_lock<std::mutex> lk(mu_);
+		caller_.wait(lk, [&] { return pending_ == 0 && next_ >= nparts_; });     // one batch at a time
+		task_ = [&f](int i) { f(i); };
+		nparts_ = parts; next_ = 1; pending_ = parts - 1;
+		lk.unlock();
+		work_.notify_all();
+		f(0);
+		lk.lock();
+		caller_.wait(lk, [&] { return pending_ == 0; });
+		nparts_ = 0; next_ = 0;
+		lk.unlock();
+		caller_.notify_all();
+	}
+private:
+	CopyPool() { for (int i = 0; i < kWorkers; i++) std::thread([this] { loop(); }).detach(); }
+	void loop()
+	{
+		std::unique_lock<std::mutex> lk(mu_);
+		for (;;) {
+			work_.wait(lk, [&] { return next_ < nparts_; });
+			const int i = next_++;
+			lk.unlock();
+			task_(i);
+			lk.lock();
+			if (--pending_ == 0) caller_.notify_all();
+		}
+	}
+	std::mutex mu_;
+	std::condition_variable work_, caller_;
+	std::function<void(int)> task_;
+	int nparts_ = 0, next_ = 0, pending_ = 0;
+};
 void par_memcpy(void* dst, const void* src, size_t n)
 {
-	const int nt = 4;
-	if (n < ((size_t)4 << 20)) { memcpy(dst, src, n); return; }
-	std::thread th[nt - 1];
+	const int nt = CopyPool::kWorkers + 1;
+	if (n < ((size_t)512 << 10)) { memcpy(dst, src, n); return; }
 	const size_t part = (n / nt + 63) & ~(size_t)63;
-	for (int i = 1; i < nt; i++) {
-		const size_t o = std::min(n, part * i), len = std::min(n, part * (i + 1)) - o;
-		th[i - 1] = std::thread([=]() { if (len) memcpy((uint8_t*)dst + o, (const uint8_t*)src + o, len); });
-	}
-	memcpy(dst, src, std::min(n, part));
-	for (int i = 1; i < nt; i++) th[i - 1].join();
+	CopyPool::get().run(nt, [=](int i) {
+		const size_t o = std::min(n, part * (size_t)i), len = std::min(n, part * (size_t)(i + 1)) - o;
+		if (len) memcpy((uint8_t*)dst + o, (const uint8_t*)src + o, len);
+	});
 }
 constexpr size_t kStageChunk = (size_t)8 << 20;
 constexpr int kStageBufs = 4;
+// pageable <-> device copies of at least 2 MB are staged: big ones in 8 MB chunks, a single frame in 2 MB chunks so that the
+// host copy of chunk i+1 overlaps the DMA of chunk i
+constexpr size_t kStageMin = (size_t)2 << 20;
+inline size_t stage_chunk(size_t bytes) { return bytes >= ((size_t)64 << 20) ? kStageChunk : ((size_t)2 << 20); }
 
 void h2d_staged(Engine& e, void* dst, const void* src, size_t bytes, cudaStream_t st)
 {
-	uint8_t* pin = (bytes >= 2 * kStageChunk && is_pageable(src)) ? (uint8_t*)e.pinned(kStageBufs * kStageChunk) : nullptr;
+	uint8_t* pin = (bytes >= kStageMin && is_pageable(src)) ? (uint8_t*)e.pinned(kStageBufs * kStageChunk) : nullptr;
 	if (!pin) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st); return; }
+	const size_t CH = stage_chunk(bytes);
 	cudaEvent_t ev[kStageBufs];
 	for (auto& x : ev) cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
 	size_t i = 0;
-	for (size_t off = 0; off < bytes; off += kStageChunk, i++) {
-		const size_t len = std::min(kStageChunk, bytes - off);
-		uint8_t* buf = pin + (i % kStageBufs) * kStageChunk;
+	for (size_t off = 0; off < bytes; off += CH, i++) {
+		const size_t len = std::min(CH, bytes - off);
+		uint8_t* buf = pin + (i % kStageBufs) * CH;
 		if (i >= (size_t)kStageBufs) cudaEventSynchronize(ev[i % kStageBufs]);
 		par_memcpy(buf, (const uint8_t*)src + off, len);
 		cudaMemcpyAsync((uint8_t*)dst + off, buf, len, cudaMemcpyHostToDevice, st);
@@ -196,22 +242,23 @@ void h2d_staged(Engine& e, void* dst, const void* src, size_t bytes, cudaStream_
 
 void d2h_staged(Engine& e, void* dst, const void* src, size_t bytes, cudaStream_t st)
 {
-	uint8_t* pin = (bytes >= 2 * kStageChunk && is_pageable(dst)) ? (uint8_t*)e.pinned(kStageBufs * kStageChunk) : nullptr;
+	uint8_t* pin = (bytes >= kStageMin && is_pageable(dst)) ? (uint8_t*)e.pinned(kStageBufs * kStageChunk) : nullptr;
 	if (!pin) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st); return; }
+	const size_t CH = stage_chunk(bytes);
 	cudaEvent_t ev[kStageBufs];
 	for (auto& x : ev) cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
-	const size_t nch = (bytes + kStageChunk - 1) / kStageChunk;
+	const size_t nch = (bytes + CH - 1) / CH;
 	auto issue = [&](size_t i) {
-		const size_t off = i * kStageChunk, len = std::min(kStageChunk, bytes - off);
-		cudaMemcpyAsync(pin + (i % kStageBufs) * kStageChunk, (const uint8_t*)src + off, len, cudaMemcpyDeviceToHost, st);
+		const size_t off = i * CH, len = std::min(CH, bytes - off);
+		cudaMemcpyAsync(pin + (i % kStageBufs) * CH, (const uint8_t*)src + off, len, cudaMemcpyDeviceToHost, st);
 		cudaEventRecord(ev[i % kStageBufs], st);
 	};
 	for (size_t i = 0; i < std::min<size_t>(nch, kStageBufs - 1); i++) issue(i);
 	for (size_t i = 0; i < nch; i++) {
 		if (i + kStageBufs - 1 < nch) issue(i + kStageBufs - 1);   // its buffer was drained in the previous iteration
 		cudaEventSynchronize(ev[i % kStageBufs]);
-		const size_t off = i * kStageChunk, len = std::min(kStageChunk, bytes - off);
-		par_memcpy((uint8_t*)dst + off, pin + (i % kStageBufs) * kStageChunk, len);
+		const size_t off = i * CH, len = std::min(CH, bytes - off);
+		par_memcpy((uint8_t*)dst + off, pin + (i % kStageBufs) * CH, len);
 	}
 	for (auto& x : ev) cudaEventDestroy(x);
 }
@@ -628,13 +675,17 @@ static int write_file(int fd, klb_image_header& h, std::vector<ShardOut>& shards
 static int write_stack_to_file(const std::string& filename, const FrameSource& src, klb_image_header& header)
 {
 	LFM_API_LOCK();
-	const int fd = open(filename.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+	// the file is overwritten in place and cut to its final size at the end (same result as "wb", but an existing file of about
+	// the same size keeps its pages: rewriting a stack does not pay for page allocation again)
+	const int fd = open(filename.c_str(), O_WRONLY | O_CREAT, 0666);
 	if (fd < 0) { std::cout << "ERROR: file " << filename << " could not be opened" << std::endl; return LFM_ERR_CREATE; }
 	int rc;
 	try {
 		std::vector<ShardOut> shards; std::vector<uint64_t> first;
 		rc = compress_core(src, header, shards, first);
 		if (rc == 0) rc = write_file(fd, header, shards);
+		if (rc == 0 && ftruncate(fd, (off_t)header.getCompressedFileSizeInBytes()) != 0) rc = LFM_ERR_CREATE;
+		if (rc != 0 && ftruncate(fd, 0) != 0) { /* nothing more to do */ }
 	} catch (const std::bad_alloc&) { g_err = "out of host memory"; rc = LFM_ERR_CREATE; }
 	if (close(fd) != 0 && rc == 0) rc = LFM_ERR_CREATE;
 	return rc;
@@ -951,7 +1002,7 @@ int lfmShardWritePayload(const char* filename, uint64_t file_offset)
 try {
 	LFM_API_LOCK();
 	if (!filename || !*filename) return LFM_ERR_OPEN;
-	const int fd = open(filename, O_WRONLY);
+	const int fd = open(filename, O_WRONLY | O_CREAT, 0666);      // no truncation: ranks write their ranges in any order
 	if (fd < 0) return LFM_ERR_CREATE;
 	int rc = stream_payload_to_fd(g_pending, fd, file_offset);
 	if (close(fd) != 0 && rc == 0) rc = LFM_ERR_CREATE;
@@ -975,7 +1026,7 @@ try {
 	h.setHeader(xyzct, KLB_DATA_TYPE::UINT16_TYPE, NULL, blockSize, KLB_COMPRESSION_TYPE::BZIP2, NULL, storedHeaderVersion, Nnum);
 	for (int d = 0; d < 5; d++) { if (h.xyzct[d] == 0 || h.blockSize[d] == 0) return LFM_ERR_BZIP; h.blockSize[d] = std::min(h.blockSize[d], h.xyzct[d]); }
 	if (numBlocks == 0 || numBlocks != h.calculateNumBlocks()) return LFM_ERR_OPEN;
-	const int fd = open(filename, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+	const int fd = open(filename, O_WRONLY | O_CREAT, 0666);      // no truncation to 0: other ranks may already be writing their payload
 	if (fd < 0) return LFM_ERR_CREATE;
 	uint8_t fixed[320]; h.packFixed(fixed);
 	int rc = write_all(fd, fixed, sizeof(fixed), 0);
