@@ -11,6 +11,7 @@
 // unresolved set, with the same tile pass.  Exactly periodic blocks keep their ties; rotation 0 is placed last in
 // its group (what bzip2 does for the periods met in practice).
 #include "lfm_radix.cuh"
+#include <cstdlib>
 
 namespace lfm {
 
@@ -19,12 +20,17 @@ enum { S_SA0 = 0, S_SA1, S_ISA, S_G0, S_G1, S_R0, S_R1, S_V0, S_V1, S_U0, S_U1, 
 
 extern __shared__ __align__(16) uint8_t bwt_smem[];
 
-__global__ void __launch_bounds__(BWT_NT, 1)
+// NT = 1024: one CTA per SM (text of up to 184 KB in shared memory); NT = 256: four CTAs per SM for small blocks (a 96x96x1
+// uint16 KLB block is 18 KB: six whole 3072-element tiles per pass, and all 484 blocks of a 2048^2 frame resident at once
+// instead of four waves of 148 CTAs with half-empty 12288-element tiles)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 4)
 k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jobs, uint32_t njobs,
       uint8_t* __restrict__ bwt_all, uint32_t* __restrict__ scratch_all, int text_in_smem)
 {
+	constexpr int BWT_NT = NT;                       // shadows the namespace constant inside this kernel
 	uint32_t* wcnt = reinterpret_cast<uint32_t*>(bwt_smem);
-	uint32_t* base = reinterpret_cast<uint32_t*>(bwt_smem + BWT_NW * BWT_WS * 4);
+	uint32_t* base = reinterpret_cast<uint32_t*>(bwt_smem + (NT / 32) * BWT_WS * 4);
 	uint32_t* run  = base + 256;
 	uint32_t* red  = run + 256;          // 64
 	uint32_t* misc = red + 64;           // 16
@@ -53,7 +59,7 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 			text = gtext;    // the slot keeps 8 wrap bytes after n (written by k_rle1)
 		}
 		__syncthreads();
-		digit_starts(n, base, wcnt, red, [&](uint32_t e) { return (uint32_t)text[e]; });
+		digit_starts<NT>(n, base, wcnt, red, [&](uint32_t e) { return (uint32_t)text[e]; });
 		if (tid < 256) {                                  // inUse map = byte values that occur (bzlib.c:226, :243-258)
 			const uint32_t c = (tid == 255 ? n : base[tid + 1]) - base[tid];
 			const uint32_t bal = __ballot_sync(0xffffffffu, c != 0);
@@ -66,7 +72,7 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 			if (tid < 256) run[tid] = base[tid];
 			__syncthreads();
 			const uint32_t* s = src; uint32_t* d = dst;
-			radix_scatter<BWT_R, uint32_t>(n, run, wcnt,
+			radix_scatter<BWT_R, uint32_t, NT>(n, run, wcnt,
 				[&](uint32_t e) { return s ? s[e] : e; },
 				[&](uint32_t idx) { return (uint32_t)text[idx + p]; },
 				[&](uint32_t pos, uint32_t idx) { d[pos] = idx; });
@@ -81,7 +87,7 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 		uint32_t* Rk[2] = { scr + (size_t)S_R0 * cap, scr + (size_t)S_R1 * cap };
 		uint32_t* V[2] = { scr + (size_t)S_V0 * cap, scr + (size_t)S_V1 * cap };
 		uint32_t* U[2] = { scr + (size_t)S_U0 * cap, scr + (size_t)S_U1 * cap };
-		uint32_t m = split_groups(n, red,
+		uint32_t m = split_groups<NT>(n, red,
 			[&](uint32_t j) -> uint64_t {                 // the 8-byte prefix of rotation sa[j]: three aligned words, shifted
 				const uint32_t idx = sa[j], sh = (idx & 3u) * 8u;
 				const uint32_t* tw = reinterpret_cast<const uint32_t*>(text + (idx & ~3u));
@@ -112,8 +118,8 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 					const uint32_t* kg = G[cur]; const uint32_t* kr = Rk[cur]; const uint32_t* kv = V[cur];
 					uint32_t* og = G[cur ^ 1]; uint32_t* orr = Rk[cur ^ 1]; uint32_t* ov = V[cur ^ 1];
 					const int sh = ps * 8;
-					digit_starts(m, run, wcnt, red, [&](uint32_t e) { return ((key ? kg[e] : kr[e]) >> sh) & 255u; });
-					radix_scatter<4, Trip>(m, run, wcnt,
+					digit_starts<NT>(m, run, wcnt, red, [&](uint32_t e) { return ((key ? kg[e] : kr[e]) >> sh) & 255u; });
+					radix_scatter<4, Trip, NT>(m, run, wcnt,
 						[&](uint32_t e) { Trip t; t.g = kg[e]; t.r = kr[e]; t.v = kv[e]; return t; },
 						[&](const Trip& t) { return ((key ? t.g : t.r) >> sh) & 255u; },
 						[&](uint32_t pos, const Trip& t) { og[pos] = t.g; orr[pos] = t.r; ov[pos] = t.v; });
@@ -127,7 +133,7 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 				const uint32_t* up = U[ucur];
 				uint32_t* ng = G[cur ^ 1]; uint32_t* nv = V[cur ^ 1]; uint32_t* nu = U[ucur ^ 1];
 				const uint32_t mm = m;
-				m = split_groups(mm, red,
+				m = split_groups<NT>(mm, red,
 					[&](uint32_t s) -> uint64_t { return ((uint64_t)kg[s] << 32) | kr[s]; },
 					[&](uint32_t s) { return up[s]; },
 					[&](uint32_t s, uint32_t head, bool un, uint32_t slot) {
@@ -169,19 +175,33 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 	}
 }
 
-size_t bwt_smem_bytes(uint32_t cap, int text_in_smem)
+static size_t bwt_smem_bytes_nt(uint32_t cap, int text_in_smem, int nt)
 {
-	size_t fixed = (size_t)BWT_NW * BWT_WS * 4 + (256 + 256 + 64 + 16) * 4;
+	size_t fixed = (size_t)(nt / 32) * BWT_WS * 4 + (256 + 256 + 64 + 16) * 4;
 	return fixed + (text_in_smem ? (size_t)cap + 16 : 0);
 }
+size_t bwt_smem_bytes(uint32_t cap, int text_in_smem) { return bwt_smem_bytes_nt(cap, text_in_smem, BWT_NT); }
 size_t bwt_scratch_elems_per_cta(uint32_t cap) { return (size_t)S_COUNT * cap; }
+// resident CTAs per SM of the variant launch_bwt picks for this slot size: 4 (256 threads) when four texts fit shared memory
+int bwt_ctas_per_sm(uint32_t cap, int text_in_smem)
+{
+	static const int forced = getenv("LFM_B200_BWT_NT") ? atoi(getenv("LFM_B200_BWT_NT")) : 0;
+	if (forced == 1024) return 1;
+	return (text_in_smem && bwt_smem_bytes_nt(cap, 1, 256) + 1024 <= (size_t)227 * 1024 / 4) ? 4 : 1;
+}
 
 void launch_bwt(const uint8_t* txt, uint32_t cap, EncJob* jobs, uint32_t njobs, uint8_t* bwt, uint32_t* scratch,
                 int grid, int text_in_smem, cudaStream_t st)
 {
-	size_t smem = bwt_smem_bytes(cap, text_in_smem);
-	cudaFuncSetAttribute(k_bwt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	k_bwt<<<grid, BWT_NT, smem, st>>>(txt, cap, jobs, njobs, bwt, scratch, text_in_smem);
+	if (bwt_ctas_per_sm(cap, text_in_smem) == 4) {
+		const size_t smem = bwt_smem_bytes_nt(cap, text_in_smem, 256);
+		cudaFuncSetAttribute(k_bwt<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		k_bwt<256><<<grid, 256, smem, st>>>(txt, cap, jobs, njobs, bwt, scratch, text_in_smem);
+		return;
+	}
+	const size_t smem = bwt_smem_bytes_nt(cap, text_in_smem, 1024);
+	cudaFuncSetAttribute(k_bwt<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	k_bwt<1024><<<grid, 1024, smem, st>>>(txt, cap, jobs, njobs, bwt, scratch, text_in_smem);
 }
 
 }  // namespace lfm

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include "lfm_device.cuh"
 
+#include <cstdlib>
 namespace lfm {
 
 // =====================================================================================================
@@ -555,13 +556,23 @@ __device__ __forceinline__ void hp_build_tree(uint64_t* heap, uint16_t* parent, 
 {
 	for (int i = 0; i < 2 * alpha + 6; i++) heap[i] = (uint64_t)HP_INF << 32;
 	heap[0] = 0;
+	// up-heap: the ancestors of a slot are known before anything is compared, so all of them are fetched at once (independent
+	// shared-memory loads in flight together) and the walk itself is register arithmetic; heap[0] (weight 0) stops it
+	auto up_heap = [&](int z, uint32_t wt, uint32_t node) {
+		uint64_t anc[9];                                              // the heap never holds more than 2^9 - 1 entries
+		#pragma unroll
+		for (int k = 0; k < 9; k++) anc[k] = heap[z >> (k + 1)];
+		#pragma unroll
+		for (int k = 0; k < 9; k++) {
+			if (!(wt < (uint32_t)(anc[k] >> 32))) break;
+			heap[z] = anc[k]; z >>= 1;
+		}
+		heap[z] = ((uint64_t)wt << 32) | node;
+	};
 	int n_heap = 0;
 	for (int i = 1; i <= alpha; i++) {
 		parent[i] = HP_NOPARENT;
-		const uint32_t wt = lw[i];
-		int z = ++n_heap;
-		for (;;) { const uint64_t up = heap[z >> 1]; if (!(wt < (uint32_t)(up >> 32))) break; heap[z] = up; z >>= 1; }
-		heap[z] = ((uint64_t)wt << 32) | (uint32_t)i;
+		up_heap(++n_heap, lw[i], (uint32_t)i);
 	}
 	int n_nodes = alpha;
 	while (n_heap > 1) {
@@ -575,20 +586,28 @@ __device__ __forceinline__ void hp_build_tree(uint64_t* heap, uint16_t* parent, 
 			const uint32_t tw = (uint32_t)(tmp >> 32);
 			int z = 1;
 			if (n_heap >= 1) {
-				// the children of BOTH possible next positions are fetched while this level is being decided, so the
-				// level-to-level chain is two compares and a select instead of a shared-memory round trip
+				// down-heap, TWO levels per shared-memory round trip: the four grandchildren and the eight great-grandchildren of
+				// the current slot are fetched while its children (already in registers) are being compared; slots below the heap
+				// hold HP_INF, so the walk always stops there (clamped addresses are never used: their parents are HP_INF)
 				ulonglong2 ch = *reinterpret_cast<const ulonglong2*>(heap + 2);               // children of the root
 				for (;;) {
-					const int y = z << 1;
-					const int gy = min(2 * y, HP_HEAP - 4);                                   // grandchildren 4z .. 4z+3 (clamped: unused past the heap)
-					const ulonglong2 g0 = *reinterpret_cast<const ulonglong2*>(heap + gy);
-					const ulonglong2 g1 = *reinterpret_cast<const ulonglong2*>(heap + gy + 2);
-					const uint32_t w0 = (uint32_t)(ch.x >> 32), w1 = (uint32_t)(ch.y >> 32);
-					const bool right = w1 < w0;
-					const uint64_t c = right ? ch.y : ch.x;
-					if (tw < (right ? w1 : w0)) break;                                         // HP_INF below the heap: always stops
-					heap[z] = c; z = y + (right ? 1 : 0);
-					ch = right ? g1 : g0;
+					const int g = min(4 * z, HP_HEAP - 4), q8 = 8 * z;
+					const ulonglong2 ga = *reinterpret_cast<const ulonglong2*>(heap + g);
+					const ulonglong2 gb = *reinterpret_cast<const ulonglong2*>(heap + g + 2);
+					const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(heap + min(q8, HP_HEAP - 2));
+					const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(heap + min(q8 + 2, HP_HEAP - 2));
+					const ulonglong2 q2 = *reinterpret_cast<const ulonglong2*>(heap + min(q8 + 4, HP_HEAP - 2));
+					const ulonglong2 q3 = *reinterpret_cast<const ulonglong2*>(heap + min(q8 + 6, HP_HEAP - 2));
+					const bool r1 = (uint32_t)(ch.y >> 32) < (uint32_t)(ch.x >> 32);
+					const uint64_t c1 = r1 ? ch.y : ch.x;
+					if (tw < (uint32_t)(c1 >> 32)) break;
+					heap[z] = c1; z = 2 * z + (r1 ? 1 : 0);
+					const ulonglong2 ch2 = r1 ? gb : ga;
+					const bool r2 = (uint32_t)(ch2.y >> 32) < (uint32_t)(ch2.x >> 32);
+					const uint64_t c2 = r2 ? ch2.y : ch2.x;
+					if (tw < (uint32_t)(c2 >> 32)) break;
+					heap[z] = c2; z = 2 * z + (r2 ? 1 : 0);
+					ch = r1 ? (r2 ? q3 : q2) : (r2 ? q1 : q0);
 				}
 				heap[z] = tmp;
 			}
@@ -599,10 +618,80 @@ __device__ __forceinline__ void hp_build_tree(uint64_t* heap, uint16_t* parent, 
 		const uint32_t d1 = w1 & 0xffu, d2 = w2 & 0xffu;
 		const uint32_t nwt = ((w1 & 0xffffff00u) + (w2 & 0xffffff00u)) | (1u + (d1 > d2 ? d1 : d2));
 		parent[n_nodes] = HP_NOPARENT;
-		int z = ++n_heap;
-		for (;;) { const uint64_t up = heap[z >> 1]; if (!(nwt < (uint32_t)(up >> 32))) break; heap[z] = up; z >>= 1; }
-		heap[z] = ((uint64_t)nwt << 32) | (uint32_t)n_nodes;
+		up_heap(++n_heap, nwt, (uint32_t)n_nodes);
 	}
+}
+
+// The same construction with 32-bit heap entries, for blocks of fewer than 2^17 symbols (every 96x96x1 block; the tree build is
+// bound by the instructions its single lane issues, and 64-bit entries cost two registers per move / select):
+//   entry = frequency sum << 15 | depth << 10 | node      (bzip2's weight is frequency << 8 | depth: the same order, huffman.c:70-71)
+// compared on entry >> 10.  Depths above 31 do not fit: the function then returns false and the caller runs the 64-bit version.
+__device__ __forceinline__ bool hp_build_tree32(uint32_t* heap, uint16_t* parent, const uint32_t* lw, int alpha)
+{
+	constexpr uint32_t INF = 0xFFFFFFFFu;
+	constexpr int SLOTS = 2 * HP_HEAP;                                  // uint32 slots in the table's heap row
+	for (int i = 0; i < 2 * alpha + 6; i++) heap[i] = INF;
+	heap[0] = 0;
+	auto up_heap = [&](int z, uint32_t e) {
+		uint32_t anc[9];
+		#pragma unroll
+		for (int k = 0; k < 9; k++) anc[k] = heap[z >> (k + 1)];
+		const uint32_t wt = e >> 10;
+		#pragma unroll
+		for (int k = 0; k < 9; k++) {
+			if (!(wt < (anc[k] >> 10))) break;
+			heap[z] = anc[k]; z >>= 1;
+		}
+		heap[z] = e;
+	};
+	int n_heap = 0;
+	for (int i = 1; i <= alpha; i++) {
+		parent[i] = HP_NOPARENT;
+		up_heap(++n_heap, ((lw[i] >> 8) << 15) | (uint32_t)i);          // leaf weights are frequency << 8, depth 0
+	}
+	int n_nodes = alpha;
+	bool ok = true;
+	while (n_heap > 1) {
+		uint32_t pick[2];
+		#pragma unroll
+		for (int q = 0; q < 2; q++) {
+			pick[q] = heap[1];
+			const uint32_t tmp = heap[n_heap];
+			heap[n_heap] = INF;
+			n_heap--;
+			const uint32_t tw = tmp >> 10;
+			int z = 1;
+			if (n_heap >= 1) {
+				uint2 ch = *reinterpret_cast<const uint2*>(heap + 2);                        // children of the root
+				for (;;) {
+					// two levels per shared-memory round trip: grandchildren (one 16-byte load) and great-grandchildren (two)
+					const uint4 g = *reinterpret_cast<const uint4*>(heap + min(4 * z, SLOTS - 4));
+					const uint4 qa = *reinterpret_cast<const uint4*>(heap + min(8 * z, SLOTS - 4));
+					const uint4 qb = *reinterpret_cast<const uint4*>(heap + min(8 * z + 4, SLOTS - 4));
+					const bool r1 = (ch.y >> 10) < (ch.x >> 10);
+					const uint32_t c1 = r1 ? ch.y : ch.x;
+					if (tw < (c1 >> 10)) break;
+					heap[z] = c1; z = 2 * z + (r1 ? 1 : 0);
+					const uint32_t a0 = r1 ? g.z : g.x, a1 = r1 ? g.w : g.y;
+					const bool r2 = (a1 >> 10) < (a0 >> 10);
+					const uint32_t c2 = r2 ? a1 : a0;
+					if (tw < (c2 >> 10)) break;
+					heap[z] = c2; z = 2 * z + (r2 ? 1 : 0);
+					const uint4 qq = r1 ? qb : qa;
+					ch.x = r2 ? qq.z : qq.x; ch.y = r2 ? qq.w : qq.y;
+				}
+				heap[z] = tmp;
+			}
+		}
+		n_nodes++;
+		parent[pick[0] & 1023u] = (uint16_t)n_nodes; parent[pick[1] & 1023u] = (uint16_t)n_nodes;
+		const uint32_t d1 = (pick[0] >> 10) & 31u, d2 = (pick[1] >> 10) & 31u;
+		const uint32_t nd = 1u + (d1 > d2 ? d1 : d2);
+		if (nd > 31u) { ok = false; break; }
+		parent[n_nodes] = HP_NOPARENT;
+		up_heap(++n_heap, (((pick[0] >> 15) + (pick[1] >> 15)) << 15) | (nd << 10) | (uint32_t)n_nodes);
+	}
+	return ok;
 }
 
 // sequential MSB-first bit writer used by thread 0 for the fixed part of the block header (whole big-endian words)
@@ -760,8 +849,14 @@ k_huff_pack(const uint16_t* __restrict__ mtfv_all, uint32_t mcap, EncJob* __rest
 			if (tid == 0) s_redo = 0;
 			// small grids (latency matters, issue slots are plentiful): one warp per table, no divergence between the tables;
 			// large grids (throughput matters): the tables side by side in the lanes of one warp
-			if (spread) { if ((int)wid < ng && lane == 0 && ((redo >> wid) & 1u)) hp_build_tree(hheap[wid], hparent[wid], hlw[wid], alpha); }
-			else if (wid == 0 && (int)lane < ng && ((redo >> lane) & 1u)) hp_build_tree(hheap[lane], hparent[lane], hlw[lane], alpha);
+			{
+				const int tb = spread ? (int)wid : (int)lane;                        // the table this lane builds
+				const bool mine = spread ? ((int)wid < ng && lane == 0) : (wid == 0 && (int)lane < ng);
+				if (mine && ((redo >> tb) & 1u)) {
+					if (!(n_mtf < (1u << 17) - 1024u) || !hp_build_tree32(reinterpret_cast<uint32_t*>(hheap[tb]), hparent[tb], hlw[tb], alpha))
+						hp_build_tree(hheap[tb], hparent[tb], hlw[tb], alpha);
+				}
+			}
 			__syncthreads();
 			if ((int)wid < ng && ((redo >> wid) & 1u)) {
 				const uint16_t* parent = hparent[wid];
@@ -1036,7 +1131,10 @@ void launch_huff_pack(const uint16_t* mtfv, uint32_t mcap, EncJob* jobs, uint32_
 {
 	const size_t smem = sizeof(uint64_t) * kGroups * HP_HEAP;
 	cudaFuncSetAttribute(k_huff_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	k_huff_pack<<<njobs, HP_NT, smem, st>>>(mtfv, mcap, jobs, njobs, sel, selcap, out, ocap, level, 0);
+	// small grids (latency matters, issue slots are plentiful): one warp per table; large grids: the tables in the lanes of one warp
+	static const int forced = getenv("LFM_B200_HP_SPREAD") ? atoi(getenv("LFM_B200_HP_SPREAD")) : -1;
+	const int spread = forced >= 0 ? forced : 0;       // measured on B200: one-lane warps make the SM issue bound (c2: 2.2 ms against 1.0 ms)
+	k_huff_pack<<<njobs, HP_NT, smem, st>>>(mtfv, mcap, jobs, njobs, sel, selcap, out, ocap, level, spread);
 }
 
 }  // namespace lfm

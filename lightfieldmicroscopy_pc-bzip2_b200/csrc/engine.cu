@@ -428,7 +428,7 @@ int Engine::compress_blocks(const uint16_t* d_sym, const StackDesc& s, uint64_t 
 	uint64_t B = std::min<uint64_t>(count, std::max<uint64_t>(1, ((size_t)6 << 30) / per_job));
 	B = std::min<uint64_t>(B, 16384);
 	const uint64_t BS = B * z.nsub;                                            // job records per batch
-	const int grid = (int)std::min<uint64_t>(BS, (uint64_t)sm_count_);
+	const int grid = (int)std::min<uint64_t>(BS, (uint64_t)sm_count_ * bwt_ctas_per_sm(z.cap, z.text_in_smem));   // resident k_bwt CTAs
 	uint64_t blockBytes = 2; for (int i = 0; i < 5; i++) blockBytes *= s.blockSize[i];
 	uint64_t pcap = std::min<uint64_t>(count * (uint64_t)z.ocap * z.nsub, count * blockBytes + count * blockBytes / 3 + count * 1024 * z.nsub + (1 << 20));
 	int rc;

@@ -22,6 +22,7 @@ void launch_huff_pack(const uint16_t* mtfv, uint32_t mcap, EncJob* jobs, uint32_
 // bz_bwt.cu
 size_t bwt_smem_bytes(uint32_t cap, int text_in_smem);
 size_t bwt_scratch_elems_per_cta(uint32_t cap);
+int bwt_ctas_per_sm(uint32_t cap, int text_in_smem);
 void launch_bwt(const uint8_t* txt, uint32_t cap, EncJob* jobs, uint32_t njobs, uint8_t* bwt, uint32_t* scratch,
                 int grid, int text_in_smem, cudaStream_t st);
 // bz_decode.cu

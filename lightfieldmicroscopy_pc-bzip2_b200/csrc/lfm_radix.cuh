@@ -25,13 +25,15 @@ struct Trip { uint32_t g, r, v; };
 //      R serialised load/modify/store rounds;
 //   3. the per-warp digit counts are scanned ACROSS warps by warp shuffles (warp w owns digits 8w..8w+7);
 //   4. scatter; the warp clears its own counter row for the next tile (two CTA barriers per tile in all).
-template <int R, class P, class LoadFn, class DigitFn, class StoreFn>
+// NT = threads of the CTA: 1024 (one CTA per SM, blocks of 100 KB and more) or 256 (four CTAs per SM: small blocks, where whole
+// 12288-element tiles and 148-CTA waves would leave a third of the machine idle).
+template <int R, class P, int NT = BWT_NT, class LoadFn, class DigitFn, class StoreFn>
 __device__ __forceinline__ void radix_scatter(uint32_t m, uint32_t* run, uint32_t* wcnt,
                                               LoadFn load, DigitFn digit, StoreFn store)
 {
 	const uint32_t lane = lane_id(), w = warp_id();
 	const uint32_t lt = (1u << lane) - 1u;
-	constexpr uint32_t TILE = BWT_NT * R;
+	constexpr uint32_t TILE = NT * R;
 	uint32_t* myc = wcnt + w * BWT_WS;
 	__syncthreads();                                      // earlier users of wcnt / run are done
 	for (uint32_t i = lane; i < BWT_WS; i += 32) myc[i] = 0;
@@ -62,10 +64,21 @@ __device__ __forceinline__ void radix_scatter(uint32_t m, uint32_t* run, uint32_
 			}
 		}
 		__syncthreads();
-		{
+		if constexpr (NT == 256) {
+			// 8 warps: thread d owns the counters of digit d in all of them (bank = (i + d) mod 32: conflict free)
+			const uint32_t d = threadIdx.x;
+			uint32_t* col = wcnt + d;
+			uint32_t c[8];
+			#pragma unroll
+			for (int i = 0; i < 8; i++) c[i] = col[i * BWT_WS];
+			uint32_t acc = run[d];
+			#pragma unroll
+			for (int i = 0; i < 8; i++) { col[i * BWT_WS] = acc; acc += c[i]; }
+			run[d] = acc;
+		} else {
 			// exclusive scan over the warps, digit by digit: thread (d, part) owns the counters of digit d in warps
 			// 8*part .. 8*part+7 (bank = (8*part + i + d) mod 32: conflict free), the 4 parts are adjacent lanes
-			static_assert(BWT_NT == 1024 && BWT_NW == 32, "scan layout assumes 1024 threads");
+			static_assert(NT == 1024, "scan layouts exist for 1024 and 256 threads");
 			const uint32_t d = threadIdx.x >> 2, part = threadIdx.x & 3u;
 			uint32_t* col = wcnt + (part * 8) * BWT_WS + d;
 			uint32_t c[8], tot = 0;
@@ -93,7 +106,7 @@ __device__ __forceinline__ void radix_scatter(uint32_t m, uint32_t* run, uint32_
 // per-warp private histograms (match.any aggregated) of an 8-bit digit over m elements,
 // reduced and exclusive-scanned into run[256]
 // (SCAN = false: run[] receives the plain digit counts)
-template <bool SCAN, class DigitOfIndex>
+template <bool SCAN, int NT = BWT_NT, class DigitOfIndex>
 __device__ __forceinline__ void digit_hist(uint32_t m, uint32_t* run, uint32_t* wcnt, uint32_t* red, DigitOfIndex dig)
 {
 	const uint32_t lane = lane_id(), w = warp_id();
@@ -103,7 +116,7 @@ __device__ __forceinline__ void digit_hist(uint32_t m, uint32_t* run, uint32_t* 
 	__syncthreads();
 	for (uint32_t i = lane; i < BWT_WS; i += 32) myc[i] = 0;
 	__syncwarp();
-	for (uint32_t e0 = w * (32 * U); e0 < m; e0 += BWT_NT * U) {        // warp-uniform trip count
+	for (uint32_t e0 = w * (32 * U); e0 < m; e0 += NT * U) {        // warp-uniform trip count
 		uint32_t d[U], peers[U];
 		#pragma unroll
 		for (int u = 0; u < U; u++) { const uint32_t e = e0 + u * 32 + lane; d[u] = e < m ? dig(e) : 256u; }
@@ -116,27 +129,27 @@ __device__ __forceinline__ void digit_hist(uint32_t m, uint32_t* run, uint32_t* 
 	if (threadIdx.x < 256) {
 		uint32_t s = 0;
 		#pragma unroll 8
-		for (int ww = 0; ww < BWT_NW; ww++) s += LFM_WC(ww, threadIdx.x);
+		for (int ww = 0; ww < NT / 32; ww++) s += LFM_WC(ww, threadIdx.x);
 		run[threadIdx.x] = s;
 	}
 	__syncthreads();
-	if (SCAN) scan256_excl<BWT_NT>(run, red);
+	if (SCAN) scan256_excl<NT>(run, red);
 }
-template <class DigitOfIndex>
+template <int NT = BWT_NT, class DigitOfIndex>
 __device__ __forceinline__ void digit_starts(uint32_t m, uint32_t* run, uint32_t* wcnt, uint32_t* red, DigitOfIndex dig)
 {
-	digit_hist<true>(m, run, wcnt, red, dig);
+	digit_hist<true, NT>(m, run, wcnt, red, dig);
 }
 
 // Walk cnt sorted entries; entry j is a group head when its 64-bit key differs from the key of entry j-1.
 // group head value pos_of(j) is propagated to the members (max-scan, heads ascend), singleton groups are resolved,
 // the others are appended (compacted, order kept) to the next unresolved set.
 // emit(j, head, unresolved, slot) is called once per entry. Returns the number of unresolved entries.
-template <class KeyFn, class PosFn, class EmitFn>
+template <int NT = BWT_NT, class KeyFn, class PosFn, class EmitFn>
 __device__ __forceinline__ uint32_t split_groups(uint32_t cnt, uint32_t* red, KeyFn key_of, PosFn pos_of, EmitFn emit)
 {
 	uint32_t carry_head = 0, carry_cnt = 0;
-	for (uint32_t t0 = 0; t0 < cnt; t0 += BWT_NT * SPLIT_R) {
+	for (uint32_t t0 = 0; t0 < cnt; t0 += NT * SPLIT_R) {
 		uint32_t i0 = t0 + threadIdx.x * SPLIT_R;
 		bool hd[SPLIT_R + 1]; uint32_t gh[SPLIT_R];
 		{
@@ -149,8 +162,8 @@ __device__ __forceinline__ uint32_t split_groups(uint32_t cnt, uint32_t* red, Ke
 		uint32_t local = 0;
 		#pragma unroll
 		for (int r = 0; r < SPLIT_R; r++) { if (i0 + r < cnt && hd[r]) local = pos_of(i0 + r); gh[r] = local; }
-		uint32_t incl = block_scan_max<BWT_NT>(local, red);
-		uint32_t tile_max = red[BWT_NW - 1];
+		uint32_t incl = block_scan_max<NT>(local, red);
+		uint32_t tile_max = red[NT / 32 - 1];
 		uint32_t before = __shfl_up_sync(0xffffffffu, incl, 1);
 		if (lane_id() == 0) before = warp_id() ? red[warp_id() - 1] : 0;
 		before = max(before, carry_head);
@@ -161,7 +174,7 @@ __device__ __forceinline__ uint32_t split_groups(uint32_t cnt, uint32_t* red, Ke
 			un[r] = (i0 + r < cnt) && !(hd[r] && hd[r + 1]);
 			c += un[r];
 		}
-		uint32_t tot; uint32_t inc = block_scan_add<BWT_NT>(c, red, &tot);
+		uint32_t tot; uint32_t inc = block_scan_add<NT>(c, red, &tot);
 		uint32_t o = carry_cnt + inc - c;
 		#pragma unroll
 		for (int r = 0; r < SPLIT_R; r++) if (i0 + r < cnt) { emit(i0 + r, gh[r], un[r], o); o += un[r]; }
