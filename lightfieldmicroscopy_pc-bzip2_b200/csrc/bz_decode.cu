@@ -10,9 +10,13 @@
 //   k_unrle       inverse of the initial run-length coding + CRC check (bzlib.c:561-728) fused with the scatter
 //                 of the block into the symbol image
 #include "lfm_radix.cuh"
+#include "bz_randtable.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace lfm {
+
+__device__ const uint16_t kRNums[512] = BZ_RNUMS_INIT;
 
 // =====================================================================================================
 // k_huff_decode : one warp per KLB block stream -- ONLY the inherently sequential part.
@@ -118,7 +122,7 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	DecJob& J = jobs[(size_t)job * nsub + kb];
 	uint16_t* mtfv = mtfv_all + ((size_t)job * nsub + kb) * mcap;
 	const uint32_t stored_crc = get(32);
-	if (get(1)) FAIL(4);                                   // randomised blocks are never produced (compress.c:629)
+	const uint32_t randomised = get(1);                    // never produced since bzip2 0.9.5 (compress.c:629), still legal to read
 	const uint32_t orig_ptr = get(24);
 	uint32_t iu[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 	uint32_t n_in_use = 0;
@@ -277,7 +281,7 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	if (wi > wi_limit) FAIL(2);
 	if (lane == 0) {
 		J.n_mtf = nsym; J.n_in_use = n_in_use; J.orig_ptr = orig_ptr; J.stored_crc = stored_crc; J.level = (uint32_t)level; J.status = 0;
-		J.max_block = max_block; J.flags = kb == 0 ? kSubFirst : 0u;
+		J.max_block = max_block; J.flags = (kb == 0 ? kSubFirst : 0u) | (randomised ? kSubRand : 0u);
 		for (int k = 0; k < 8; k++) J.in_use[k] = iu[k];
 	}
 	combined = ((combined << 1) | (combined >> 31)) ^ stored_crc;         // bzlib.c / decompress.c: calculatedCombinedCRC
@@ -497,16 +501,20 @@ constexpr uint32_t IB_NIL = 0xFFFFu;
 
 extern __shared__ __align__(16) uint8_t ib_smem[];
 
-__global__ void __launch_bounds__(BWT_NT, 1)
+// NT = 1024: one CTA per SM; NT = 256 (fewer, longer sublists: maxs <= 3072): four CTAs per SM for small blocks, so that the 484
+// blocks of a 2048^2 frame are all resident at once instead of four waves of 148 CTAs (the same split as k_bwt)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 4)
 k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict__ jobs, uint32_t njobs,
-          uint32_t* __restrict__ tt_all, uint8_t* __restrict__ txt_all)
+          uint32_t* __restrict__ tt_all, uint8_t* __restrict__ txt_all, uint32_t maxs)
 {
-	__shared__ uint32_t wcnt[BWT_NW * BWT_WS];
+	constexpr int BWT_NT = NT;                       // shadows the namespace constant inside this kernel
+	__shared__ uint32_t wcnt[(NT / 32) * BWT_WS];
 	__shared__ uint32_t run[256];
 	__shared__ uint32_t red[64];
 	__shared__ uint32_t s_nvis;
-	uint32_t* s_dist = reinterpret_cast<uint32_t*>(ib_smem);                         // [2][IB_MAXS + 2]
-	uint16_t* s_nxt = reinterpret_cast<uint16_t*>(s_dist + 2 * (IB_MAXS + 2));      // [2][IB_MAXS + 2]
+	uint32_t* s_dist = reinterpret_cast<uint32_t*>(ib_smem);                         // [2][maxs + 2]
+	uint16_t* s_nxt = reinterpret_cast<uint16_t*>(s_dist + 2 * (maxs + 2));         // [2][maxs + 2]
 	const uint32_t tid = threadIdx.x;
 	uint32_t* tt = tt_all + (size_t)blockIdx.x * cap;          // per-CTA scratch
 	uint32_t* vis = tt_all + (size_t)gridDim.x * cap + (size_t)blockIdx.x * 2 * IB_VIS;   // visit list (id, offset)
@@ -519,8 +527,8 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 		uint8_t* txt = txt_all + (size_t)job * cap;
 
 		// ---- LF mapping: T[pos] = i for the i-th occurrence ... stable counting sort of positions by byte
-		digit_starts(n, run, wcnt, red, [&](uint32_t e) { return (uint32_t)L[e]; });     // cftab (decompress.c:494-510)
-		radix_scatter<BWT_R, uint32_t>(n, run, wcnt,
+		digit_starts<NT>(n, run, wcnt, red, [&](uint32_t e) { return (uint32_t)L[e]; });     // cftab (decompress.c:494-510)
+		radix_scatter<BWT_R, uint32_t, NT>(n, run, wcnt,
 			[&](uint32_t e) { return (e << 8) | (uint32_t)L[e]; },
 			[&](uint32_t p) { return p & 255u; },
 			[&](uint32_t pos, uint32_t p) { tt[pos] = p >> 8; });
@@ -530,7 +538,7 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 
 		// ---- splitters: every K-th position, plus the start of the walk
 		uint32_t kshift = 2;                               // sublists of ~4 .. 32 steps: as many as the ranking arrays hold
-		while (((n + (1u << kshift) - 1) >> kshift) > (uint32_t)IB_MAXS) kshift++;
+		while (((n + (1u << kshift) - 1) >> kshift) > maxs) kshift++;
 		const uint32_t K = 1u << kshift, S = (n + K - 1) >> kshift;
 		const uint32_t p0 = tt[J.orig_ptr] >> 8;
 		const bool p0_regular = (p0 & (K - 1)) == 0;
@@ -568,8 +576,8 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 		// ---- rank the sublists: distance to the end of the path by pointer jumping (double buffered)
 		uint32_t cur = 0;
 		for (uint32_t span = 1; span < nspl; span <<= 1) {
-			const uint32_t* di = s_dist + cur * (IB_MAXS + 2); const uint16_t* ni = s_nxt + cur * (IB_MAXS + 2);
-			uint32_t* dq = s_dist + (cur ^ 1) * (IB_MAXS + 2); uint16_t* nq = s_nxt + (cur ^ 1) * (IB_MAXS + 2);
+			const uint32_t* di = s_dist + cur * (maxs + 2); const uint16_t* ni = s_nxt + cur * (maxs + 2);
+			uint32_t* dq = s_dist + (cur ^ 1) * (maxs + 2); uint16_t* nq = s_nxt + (cur ^ 1) * (maxs + 2);
 			for (uint32_t q = tid; q < nspl; q += BWT_NT) {
 				const uint32_t nx = ni[q];
 				uint32_t d = di[q], n2 = nx;
@@ -579,8 +587,8 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 			cur ^= 1;
 			__syncthreads();
 		}
-		const uint32_t* dfin = s_dist + cur * (IB_MAXS + 2);
-		const uint16_t* nfin = s_nxt + cur * (IB_MAXS + 2);
+		const uint32_t* dfin = s_dist + cur * (maxs + 2);
+		const uint16_t* nfin = s_nxt + cur * (maxs + 2);
 		const bool ranked = (dfin[start_id] == n) && (nfin[start_id] == IB_NIL);     // the path from the start covers the block
 		__syncthreads();
 		if (ranked) {
@@ -624,6 +632,18 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 				uint32_t q = vis[2 * i], off = vis[2 * i + 1];
 				uint32_t p = q < S ? (q << kshift) : p0, len = s_len[q];
 				for (uint32_t k = 0; k < len && off + k < n; k++) { uint32_t e = tt[p]; txt[off + k] = (uint8_t)e; p = e >> 8; }
+			}
+		}
+		__syncthreads();
+		// de-randomisation (decompress.c BZ_RAND_INIT_MASK / BZ_RAND_UPD_MASK / BZ_RAND_MASK, bzlib.c:577-640): byte j of the block is
+		// XORed with 1 when j + 2 is a partial sum of the cyclic BZ2_rNums sequence -- a few hundred bytes per block, walked by one
+		// thread (only streams of bzip2 <= 0.9.0 carry the bit)
+		if ((J.flags & kSubRand) && tid == 0) {
+			uint32_t sum = 0;
+			for (uint32_t k = 0;; k++) {
+				sum += kRNums[k & 511u];
+				if (sum - 2u >= n) break;
+				txt[sum - 2u] ^= 1u;
 			}
 		}
 		__syncthreads();
@@ -849,12 +869,26 @@ int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t*
 	return 0;
 }
 size_t inv_bwt_scratch_elems(int grid, uint32_t cap) { return (size_t)grid * cap + (size_t)grid * 2 * IB_VIS; }
+constexpr uint32_t IB_MAXS_SMALL = 3072;
+// resident CTAs per SM of the variant launch_inv_bwt picks: 4 (256 threads) for slots of up to 48 KB
+int inv_bwt_ctas_per_sm(uint32_t cap)
+{
+	static const int forced = getenv("LFM_B200_IBWT_NT") ? atoi(getenv("LFM_B200_IBWT_NT")) : 0;
+	if (forced == 1024) return 1;
+	return cap <= 48 * 1024 ? 4 : 1;
+}
 void launch_inv_bwt(const uint8_t* bwt, uint32_t cap, DecJob* jobs, uint32_t njobs, uint32_t* tt_scratch, uint8_t* txt,
                     int grid, cudaStream_t st)
 {
+	if (inv_bwt_ctas_per_sm(cap) == 4) {
+		const size_t smem = (size_t)2 * (IB_MAXS_SMALL + 2) * (4 + 2);
+		cudaFuncSetAttribute(k_inv_bwt<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		k_inv_bwt<256><<<grid, 256, smem, st>>>(bwt, cap, jobs, njobs, tt_scratch, txt, IB_MAXS_SMALL);
+		return;
+	}
 	const size_t smem = (size_t)2 * (IB_MAXS + 2) * (4 + 2);
-	cudaFuncSetAttribute(k_inv_bwt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	k_inv_bwt<<<grid, BWT_NT, smem, st>>>(bwt, cap, jobs, njobs, tt_scratch, txt);
+	cudaFuncSetAttribute(k_inv_bwt<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	k_inv_bwt<1024><<<grid, 1024, smem, st>>>(bwt, cap, jobs, njobs, tt_scratch, txt, (uint32_t)IB_MAXS);
 }
 void launch_unrle(const uint8_t* txt, uint8_t* stage_scratch, uint32_t cap, uint32_t nsub, uint32_t max_raw_bytes, DecJob* jobs, uint32_t njobs,
                   uint16_t* sym, const Geom& g, const uint64_t* block_ids, cudaStream_t st)

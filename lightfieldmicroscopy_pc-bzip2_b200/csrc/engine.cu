@@ -538,7 +538,7 @@ int Engine::decompress_blocks(const uint8_t* d_payload, const uint64_t* begin, c
 	uint64_t B = std::min<uint64_t>(count, std::max<uint64_t>(1, ((size_t)6 << 30) / per_job));
 	B = std::min<uint64_t>(B, 32768);
 	const uint64_t BS = B * z.nsub;                                            // job records per batch
-	const int grid = (int)std::min<uint64_t>(BS, (uint64_t)sm_count_);
+	const int grid = (int)std::min<uint64_t>(BS, (uint64_t)sm_count_ * inv_bwt_ctas_per_sm(z.cap));   // resident k_inv_bwt CTAs
 	int rc;
 	if ((rc = reserve(djobs_, BS * sizeof(DecJob) + 16))) return rc;
 	if ((rc = reserve(bwt_, BS * z.cap))) return rc;

@@ -30,6 +30,7 @@ int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t*
                   uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap, cudaStream_t st,
                   cudaEvent_t between = nullptr);
 size_t inv_bwt_scratch_elems(int grid, uint32_t cap);
+int inv_bwt_ctas_per_sm(uint32_t cap);
 void launch_inv_bwt(const uint8_t* bwt, uint32_t cap, DecJob* jobs, uint32_t njobs, uint32_t* tt_scratch, uint8_t* txt,
                     int grid, cudaStream_t st);
 void launch_unrle(const uint8_t* txt, uint8_t* stage_scratch, uint32_t cap, uint32_t nsub, uint32_t max_raw_bytes, DecJob* jobs, uint32_t njobs,

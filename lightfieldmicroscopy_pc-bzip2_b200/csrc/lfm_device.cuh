@@ -28,6 +28,7 @@ struct Geom {
 constexpr uint32_t kSubUnused = 1u;    // EncJob/DecJob.flags: this record holds no bzip2 block
 constexpr uint32_t kSubFirst  = 2u;    // first bzip2 block of its stream (the stream header precedes it)
 constexpr uint32_t kSubLast   = 4u;    // last bzip2 block of its stream (the stream trailer follows it)
+constexpr uint32_t kSubRand   = 8u;    // decoder: the block carries bzip2's "randomised" bit (streams of bzip2 <= 0.9.0)
 constexpr int kMaxSub = 32;            // bzip2 blocks per KLB block this engine handles
 
 struct EncJob {
@@ -56,7 +57,7 @@ struct DecJob {
 	uint32_t orig_ptr;
 	uint32_t stored_crc;
 	uint32_t out_bytes;    // bytes produced by un-RLE1
-	uint32_t status;       // 0 ok, 1 bad magic, 2 corrupt, 3 crc mismatch, 4 unsupported (randomised / too many blocks)
+	uint32_t status;       // 0 ok, 1 bad magic, 2 corrupt, 3 crc mismatch, 4 unsupported (more bzip2 blocks than the geometry allows)
 	uint32_t level;
 	uint32_t max_block;
 	uint32_t flags;        // kSub*

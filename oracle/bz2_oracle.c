@@ -206,9 +206,36 @@ static void assign_codes(int32_t* code, const uint8_t* len, int min_len, int max
 }
 
 /* ------------------------------------------------------------------ one block: BWT .. bits (compress.c:603-676) */
-static void compress_block(bitw* w, const uint8_t* blk, int32_t nblock, const uint8_t* in_use, uint32_t block_crc,
+#include "bz2_randtable.h"
+static const int32_t bz2o_rnums[512] = BZ_RNUMS_INIT;
+/* decompress.c BZ_RAND_INIT_MASK / BZ_RAND_UPD_MASK / BZ_RAND_MASK applied to a whole block: byte j ^= 1 where the mask is set */
+static void randomise_block(uint8_t* blk, int32_t nblock)
+{
+	int32_t n_to_go = 0, t_pos = 0;
+	for (int32_t j = 0; j < nblock; j++) {
+		if (n_to_go == 0) { n_to_go = bz2o_rnums[t_pos]; t_pos++; if (t_pos == 512) t_pos = 0; }
+		n_to_go--;
+		if (n_to_go == 1) blk[j] ^= 1;
+	}
+}
+
+static int g_force_randomised = 0;      /* test hook: write blocks the way bzip2 <= 0.9.0 did after a failed sort (randomised bit set) */
+void bz2o_set_randomised(int on) { g_force_randomised = on; }
+
+static void compress_block(bitw* w, const uint8_t* blk_in, int32_t nblock, const uint8_t* in_use_in, uint32_t block_crc,
                            bz2o_block_trace* tr)
 {
+	const int randomised = g_force_randomised;
+	uint8_t* blk_r = NULL; uint8_t in_use_r[256];
+	const uint8_t* blk = blk_in; const uint8_t* in_use = in_use_in;
+	if (randomised) {                   /* the block is XORed with the mask, then sorted and coded; the CRC stays that of the input */
+		blk_r = (uint8_t*)malloc((size_t)nblock);
+		memcpy(blk_r, blk_in, (size_t)nblock);
+		randomise_block(blk_r, nblock);
+		memset(in_use_r, 0, 256);
+		for (int32_t i = 0; i < nblock; i++) in_use_r[blk_r[i]] = 1;
+		blk = blk_r; in_use = in_use_r;
+	}
 	int32_t* sa = (int32_t*)malloc(sizeof(int32_t) * (size_t)nblock);
 	int32_t periodic = 0;
 	rot_sort(blk, nblock, sa, &periodic);
@@ -305,7 +332,7 @@ static void compress_block(bitw* w, const uint8_t* blk, int32_t nblock, const ui
 	int64_t bit_start = (int64_t)w->pos * 8 + w->live;
 	bw_put(w, 8, 0x31); bw_put(w, 8, 0x41); bw_put(w, 8, 0x59); bw_put(w, 8, 0x26); bw_put(w, 8, 0x53); bw_put(w, 8, 0x59);
 	bw_put(w, 32, block_crc);
-	bw_put(w, 1, 0);
+	bw_put(w, 1, (uint32_t)randomised);
 	bw_put(w, 24, (uint32_t)orig_ptr);
 	{
 		int in_use16[16];
@@ -343,7 +370,7 @@ static void compress_block(bitw* w, const uint8_t* blk, int32_t nblock, const ui
 		memcpy(tr->len, len, sizeof(len));
 		tr->bit_start = bit_start; tr->bit_end = (int64_t)w->pos * 8 + w->live;
 	}
-	free(sa); free(mtfv); free(sel_buf); free(sel_mtf);
+	free(sa); free(mtfv); free(sel_buf); free(sel_mtf); free(blk_r);
 }
 
 /* ------------------------------------------------------------------ whole stream
@@ -565,13 +592,18 @@ int bz2o_decompress(const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_
 			for (int i = 0; i < 256; i++) cf[i + 1] = cf[i] + unzftab[i];
 			for (int32_t i = 0; i < nblock; i++) { uint8_t uc = (uint8_t)(tt[i] & 0xff); tt[cf[uc]++] |= ((uint32_t)i << 8); }
 		}
-		/* un-RLE1 + CRC (bzlib.c:561-728); de-randomisation omitted: randomised==1 is never produced (compress.c:629) */
-		if (randomised) { rc = -2; break; }
+		/* un-RLE1 + CRC (bzlib.c:561-728), with the de-randomisation of bzip2 <= 0.9.0 blocks (decompress.c BZ_RAND_*, bzlib.c:577-640) */
 		{
 			uint32_t crc = 0xFFFFFFFFu, pos = tt[orig_ptr] >> 8;
 			int prev = -1, cnt = 0;
+			int32_t n_to_go = 0, t_pos = 0;
 			for (int32_t i = 0; i < nblock; i++) {
 				pos = tt[pos]; uint8_t ch = (uint8_t)(pos & 0xff); pos >>= 8;
+				if (randomised) {
+					if (n_to_go == 0) { n_to_go = bz2o_rnums[t_pos]; t_pos++; if (t_pos == 512) t_pos = 0; }
+					n_to_go--;
+					if (n_to_go == 1) ch ^= 1;
+				}
 				if (cnt == 4) {                          /* ch is a repeat count */
 					for (int k = 0; k < ch; k++) { if (op >= cap) { rc = -4; break; } out[op++] = (uint8_t)prev; crc = (crc << 8) ^ crc_tab[(crc >> 24) ^ (uint32_t)prev]; }
 					if (rc) break;

@@ -22,7 +22,8 @@ def build_oracle():
     """compile oracle/*.c into oracle/liblfm_oracle.so (gcc, a second or two)"""
     so = os.path.join(ORACLE_DIR, "liblfm_oracle.so")
     srcs = [os.path.join(ORACLE_DIR, f) for f in ("lfm_oracle.c", "bz2_oracle.c")]
-    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+    deps = srcs + [os.path.join(ORACLE_DIR, "bz2_randtable.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in deps):
         subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so] + srcs + ["-lm"])
     return so
 
@@ -71,6 +72,11 @@ class Oracle:
                                mtfv=arr(2, n_mtf, C.c_uint16), selector=arr(3, n_sel, C.c_uint8)))
         self.lib.bz2o_trace_delete(tr)
         return out, blocks
+
+    def set_randomised(self, on):
+        """test hook: blocks are written the way bzip2 <= 0.9.0 did after a failed sort (randomised bit set, bytes XORed with the
+        BZ2_rNums mask before the sort); libbz2 decodes such streams, nothing written since 0.9.5 produces them"""
+        self.lib.bz2o_set_randomised(1 if on else 0)
 
     def bz2_decompress(self, data, cap):
         buf = C.create_string_buffer(max(cap, 1))

@@ -241,6 +241,24 @@ def test_corrupt_file_is_rejected(L, tmp_path):
     assert ei.value.code == 2
 
 
+def test_randomised_bzip2_blocks_decode(L, oracle, tmp_path):
+    """files whose block streams carry bzip2's "randomised" bit (only bzip2 <= 0.9.0 wrote them; decompress.c BZ_RAND_*): the oracle's
+    test hook writes them (pinned to libbz2 in test_oracle_bz2.py), the GPU decoder reads them -- single- and multi-block streams"""
+    a = (lf_synth((9, 100, 130), 13, seed=12)).astype(np.uint16)
+    fn = str(tmp_path / "r.lfm")
+    for hv, bs in ((8, (64, 48, 4, 1, 1)), (8 + 4, (130, 100, 9, 1, 1)), (8, (130, 100, 9, 1, 1))):
+        oracle.set_randomised(True)
+        try:
+            rc, _ = oracle.write(a, fn, hv, 13, 0, block_size=bs)
+        finally:
+            oracle.set_randomised(False)
+        assert rc == 0
+        plain = str(tmp_path / "p.lfm")
+        rc, _ = oracle.write(a, plain, hv, 13, 0, block_size=bs)
+        assert rc == 0 and open(plain, "rb").read() != open(fn, "rb").read()
+        assert np.array_equal(L.read_stack(fn, way=0), a), (hv, bs)
+
+
 def test_memory_and_device_entry_points(L):
     import ctypes as C
     import torch

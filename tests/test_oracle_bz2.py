@@ -120,3 +120,22 @@ def test_oracle_multi_block_streams(oracle, name):
     assert bz2.decompress(got) == data
     rc, back = oracle.bz2_decompress(got, len(data))
     assert rc == 0 and back == data
+
+
+def test_randomised_blocks_are_pinned_to_libbz2(oracle):
+    """bzip2 <= 0.9.0 could set the "randomised" bit of a block (BZ_RAND_*, randtable.c); the oracle's test hook writes such
+    streams: libbz2 itself must decode them back to the input (that pins the mask positions), and so must the oracle's decoder"""
+    rng = np.random.default_rng(3)
+    cases = [rng.poisson(5, 20000).astype(np.uint16).tobytes(), bytes(5000), rng.integers(0, 256, 300000, dtype=np.uint8).tobytes(),
+             b"ab" * 700, rng.poisson(30, 400000).astype(np.uint16).tobytes()]
+    for data in cases:
+        level = min(9, (len(data) + 99999) // 100000)
+        oracle.set_randomised(True)
+        try:
+            s = oracle.bz2_compress(data, level)
+        finally:
+            oracle.set_randomised(False)
+        assert s != oracle.bz2_compress(data, level)
+        assert bz2.decompress(s) == data
+        rc, back = oracle.bz2_decompress(s, len(data) + 16)
+        assert rc == 0 and back == data
