@@ -628,21 +628,28 @@ __device__ __forceinline__ void hp_build_tree(uint64_t* heap, uint16_t* parent, 
 // compared on entry >> 10.  Depths above 31 do not fit: the function then returns false and the caller runs the 64-bit version.
 __device__ __forceinline__ bool hp_build_tree32(uint32_t* heap, uint16_t* parent, const uint32_t* lw, int alpha)
 {
+	// A lone lane pays ~4 cycles per instruction and ~25 per branch it has to resolve, so both heap walks are written WITHOUT
+	// data-dependent branches: a walk that has found its place keeps going as a no-op (predicated stores, selects) for the
+	// fixed number of levels the heap has.
 	constexpr uint32_t INF = 0xFFFFFFFFu;
 	constexpr int SLOTS = 2 * HP_HEAP;                                  // uint32 slots in the table's heap row
 	for (int i = 0; i < 2 * alpha + 6; i++) heap[i] = INF;
 	heap[0] = 0;
+	// up-heap: all ancestors are fetched at once; their keys do not increase towards the root, so "wt < key" holds for the first
+	// m of them and m is a sum of independent compares; ancestor k moves down to the slot of ancestor k - 1, the entry lands above
 	auto up_heap = [&](int z, uint32_t e) {
 		uint32_t anc[9];
 		#pragma unroll
 		for (int k = 0; k < 9; k++) anc[k] = heap[z >> (k + 1)];
 		const uint32_t wt = e >> 10;
+		int m = 0;
 		#pragma unroll
 		for (int k = 0; k < 9; k++) {
-			if (!(wt < (anc[k] >> 10))) break;
-			heap[z] = anc[k]; z >>= 1;
+			const bool mv = wt < (anc[k] >> 10);
+			if (mv) heap[z >> k] = anc[k];
+			m += mv ? 1 : 0;
 		}
-		heap[z] = e;
+		heap[z >> m] = e;
 	};
 	int n_heap = 0;
 	for (int i = 1; i <= alpha; i++) {
@@ -661,35 +668,39 @@ __device__ __forceinline__ bool hp_build_tree32(uint32_t* heap, uint16_t* parent
 			n_heap--;
 			const uint32_t tw = tmp >> 10;
 			int z = 1;
-			if (n_heap >= 1) {
-				uint2 ch = *reinterpret_cast<const uint2*>(heap + 2);                        // children of the root
-				for (;;) {
-					// two levels per shared-memory round trip: grandchildren (one 16-byte load) and great-grandchildren (two)
-					const uint4 g = *reinterpret_cast<const uint4*>(heap + min(4 * z, SLOTS - 4));
-					const uint4 qa = *reinterpret_cast<const uint4*>(heap + min(8 * z, SLOTS - 4));
-					const uint4 qb = *reinterpret_cast<const uint4*>(heap + min(8 * z + 4, SLOTS - 4));
-					const bool r1 = (ch.y >> 10) < (ch.x >> 10);
-					const uint32_t c1 = r1 ? ch.y : ch.x;
-					if (tw < (c1 >> 10)) break;
-					heap[z] = c1; z = 2 * z + (r1 ? 1 : 0);
-					const uint32_t a0 = r1 ? g.z : g.x, a1 = r1 ? g.w : g.y;
-					const bool r2 = (a1 >> 10) < (a0 >> 10);
-					const uint32_t c2 = r2 ? a1 : a0;
-					if (tw < (c2 >> 10)) break;
-					heap[z] = c2; z = 2 * z + (r2 ? 1 : 0);
-					const uint4 qq = r1 ? qb : qa;
-					ch.x = r2 ? qq.z : qq.x; ch.y = r2 ? qq.w : qq.y;
-				}
-				heap[z] = tmp;
+			// down-heap, two levels per shared-memory round trip (grandchildren: one 16-byte load, great-grandchildren: two); slots
+			// below the heap hold INF, so the walk stops there by itself (clamped addresses are never used: their parents are INF)
+			const int levels = 31 - __clz(n_heap | 1);                            // deepest level that holds an entry (root = 0)
+			uint2 ch = *reinterpret_cast<const uint2*>(heap + 2);                 // children of the root
+			bool going = n_heap >= 1;
+			#pragma unroll 1
+			for (int it = 0; it < levels; it += 2) {
+				const uint4 g = *reinterpret_cast<const uint4*>(heap + min(4 * z, SLOTS - 4));
+				const uint4 qa = *reinterpret_cast<const uint4*>(heap + min(8 * z, SLOTS - 4));
+				const uint4 qb = *reinterpret_cast<const uint4*>(heap + min(8 * z + 4, SLOTS - 4));
+				const bool r1 = (ch.y >> 10) < (ch.x >> 10);
+				const uint32_t c1 = r1 ? ch.y : ch.x;
+				going = going & !(tw < (c1 >> 10));
+				if (going) heap[z] = c1;
+				z = going ? 2 * z + (r1 ? 1 : 0) : z;
+				const uint32_t a0 = r1 ? g.z : g.x, a1 = r1 ? g.w : g.y;
+				const bool r2 = (a1 >> 10) < (a0 >> 10);
+				const uint32_t c2 = r2 ? a1 : a0;
+				going = going & !(tw < (c2 >> 10));
+				if (going) heap[z] = c2;
+				z = going ? 2 * z + (r2 ? 1 : 0) : z;
+				const uint4 qq = r1 ? qb : qa;
+				ch.x = r2 ? qq.z : qq.x; ch.y = r2 ? qq.w : qq.y;
 			}
+			if (n_heap >= 1) heap[z] = tmp;
 		}
 		n_nodes++;
 		parent[pick[0] & 1023u] = (uint16_t)n_nodes; parent[pick[1] & 1023u] = (uint16_t)n_nodes;
 		const uint32_t d1 = (pick[0] >> 10) & 31u, d2 = (pick[1] >> 10) & 31u;
 		const uint32_t nd = 1u + (d1 > d2 ? d1 : d2);
-		if (nd > 31u) { ok = false; break; }
+		ok = ok & (nd <= 31u);
 		parent[n_nodes] = HP_NOPARENT;
-		up_heap(++n_heap, (((pick[0] >> 15) + (pick[1] >> 15)) << 15) | (nd << 10) | (uint32_t)n_nodes);
+		up_heap(++n_heap, (((pick[0] >> 15) + (pick[1] >> 15)) << 15) | ((nd & 31u) << 10) | (uint32_t)n_nodes);
 	}
 	return ok;
 }
