@@ -79,10 +79,16 @@ public:
 	// growable device scratch, kept across calls
 	struct Buf { void* p = nullptr; size_t cap = 0; };
 	int reserve(Buf& b, size_t bytes);
-	// buffers the orchestrator (klb_imageIO.cpp) keeps on this GPU between calls: image, symbol image, payload, frame 0
-	Buf user[4];
-	// growable pinned host staging buffer (one per engine)
-	void* pinned(size_t bytes);
+	// buffers the orchestrator (klb_imageIO.cpp) keeps on this GPU between calls: image, symbol image, payload, frame 0, and
+	// the second image / payload buffer of the slab pipeline
+	Buf user[6];
+	// growable pinned host staging buffers: slot 0 = towards the GPU, slot 1 = from the GPU (the two directions of the slab
+	// pipeline run on different host threads at the same time)
+	void* pinned(size_t bytes, int slot = 0);
+	// copy streams of the slab pipeline (0: host -> device, 1: device -> host), beside the compute stream
+	void* copy_stream(int i) { return aux_stream(kMaxGroups + i); }
+	// which of the two payload buffers compress_blocks fills next (the other one may still be on its way to the host)
+	void use_payload_buffer(int i) { pay_sel_ = i & 1; }
 
 	// debugging / stage-parity hook: copies of the intermediate arrays of the LAST compress_blocks batch
 	struct EncodeTrace {
@@ -106,11 +112,12 @@ private:
 	void* stream_ = nullptr;
 	std::string err_;
 	// workspace
-	Buf jobs_, txt_, bwt_, rank_, mtfv_, sel_, out_, scratch_, payload_, sizes_, offs_;
+	Buf jobs_, txt_, bwt_, rank_, mtfv_, sel_, out_, scratch_, payload2_[2], sizes_, offs_;
+	int pay_sel_ = 0;
 	Buf djobs_, dbegin_, dend_, dids_, tt_;
 	Buf sel_sorted_, sel_hist_, sel_e_, sel_cand_;
 	uint32_t last_cap_ = 0, last_mcap_ = 0, last_njobs_ = 0;
-	void* pin_ = nullptr; size_t pin_cap_ = 0;
+	void* pin_[2] = { nullptr, nullptr }; size_t pin_cap_[2] = { 0, 0 };
 	static constexpr int kMaxGroups = 4;   // forked streams a small batch is spread over
 	void* ev_[16] = { nullptr };          // 0-3 predictor timing, 4 fork, 5.. join of every group
 	std::vector<void*> aux_;               // forked streams

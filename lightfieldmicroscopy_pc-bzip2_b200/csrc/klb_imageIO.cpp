@@ -222,7 +222,7 @@ inline size_t stage_chunk(size_t bytes) { return bytes >= ((size_t)64 << 20) ? k
 
 void h2d_staged(Engine& e, void* dst, const void* src, size_t bytes, cudaStream_t st)
 {
-	uint8_t* pin = (bytes >= kStageMin && is_pageable(src)) ? (uint8_t*)e.pinned(kStageBufs * kStageChunk) : nullptr;
+	uint8_t* pin = (bytes >= kStageMin && is_pageable(src)) ? (uint8_t*)e.pinned(kStageBufs * kStageChunk, 0) : nullptr;
 	if (!pin) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st); return; }
 	const size_t CH = stage_chunk(bytes);
 	cudaEvent_t ev[kStageBufs];
@@ -242,7 +242,7 @@ void h2d_staged(Engine& e, void* dst, const void* src, size_t bytes, cudaStream_
 
 void d2h_staged(Engine& e, void* dst, const void* src, size_t bytes, cudaStream_t st)
 {
-	uint8_t* pin = (bytes >= kStageMin && is_pageable(dst)) ? (uint8_t*)e.pinned(kStageBufs * kStageChunk) : nullptr;
+	uint8_t* pin = (bytes >= kStageMin && is_pageable(dst)) ? (uint8_t*)e.pinned(kStageBufs * kStageChunk, 1) : nullptr;
 	if (!pin) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st); return; }
 	const size_t CH = stage_chunk(bytes);
 	cudaEvent_t ev[kStageBufs];
@@ -268,10 +268,146 @@ struct ShardOut {
 	std::vector<uint32_t> sizes; int rc = 0; CompressStats st; double ms_h2d = 0, ms_d2h = 0; std::string err;
 	const uint8_t* d_payload = nullptr; uint64_t payload_bytes = 0; int device = 0;      // streams stay on the GPU until fetched
 };
-enum { UB_IMG = 0, UB_SYM = 1, UB_PAY = 2, UB_F0 = 3 };
+enum { UB_IMG = 0, UB_SYM = 1, UB_PAY = 2, UB_F0 = 3, UB_IMG2 = 4, UB_PAY2 = 5 };
+
+// ------------------------------------------------------------------------------------------------ slab pipeline (one GPU)
+// Large stacks written to a file go through the GPU in batches of whole z-slabs: while batch b is predicted and compressed, batch
+// b + 1 is on its way to the GPU (pinned staging + copy stream 0, own host thread) and the streams of batch b - 1 are on their
+// way to the file (copy stream 1 + pwrite at the final offset, own host thread) -- the counterpart of the reference's block
+// threads feeding blockWriter through a staging queue (src/klb_imageIO.cpp:1152-1217, :2446).  Two image and two payload buffers.
+struct FileSink { int fd = -1; uint64_t base = 0; };               // payload byte 0 lives at file offset `base`
+constexpr uint64_t kBatchBytes = (uint64_t)96 << 20;               // raw bytes per batch (at least one slab)
+constexpr uint64_t kBatchBlocks = 2048;                            // ... and at least this many KLB blocks
+
+static int payload_to_fd(Engine& e, const uint8_t* d_payload, uint64_t bytes, int fd, uint64_t file_off, cudaStream_t st)
+{
+	uint8_t* pin = (uint8_t*)e.pinned(kStageBufs * kStageChunk, 1);
+	if (!pin) return LFM_ERR_CUDA;
+	cudaEvent_t ev[kStageBufs];
+	for (auto& x : ev) cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+	const size_t nch = (size_t)((bytes + kStageChunk - 1) / kStageChunk);
+	auto issue = [&](size_t i) {
+		const uint64_t o = (uint64_t)i * kStageChunk; const size_t len = (size_t)std::min<uint64_t>(kStageChunk, bytes - o);
+		cudaMemcpyAsync(pin + (i % kStageBufs) * kStageChunk, d_payload + o, len, cudaMemcpyDeviceToHost, st);
+		cudaEventRecord(ev[i % kStageBufs], st);
+	};
+	int rc = LFM_OK;
+	for (size_t i = 0; i < std::min<size_t>(nch, kStageBufs - 1); i++) issue(i);
+	for (size_t i = 0; i < nch && rc == LFM_OK; i++) {
+		if (i + kStageBufs - 1 < nch) issue(i + kStageBufs - 1);           // its buffer was written out in the previous iteration
+		if (cudaEventSynchronize(ev[i % kStageBufs]) != cudaSuccess) { cudaGetLastError(); rc = LFM_ERR_CUDA; break; }
+		const uint64_t o = (uint64_t)i * kStageChunk; const size_t len = (size_t)std::min<uint64_t>(kStageChunk, bytes - o);
+		const uint8_t* buf = pin + (i % kStageBufs) * kStageChunk;
+		size_t done = 0;
+		while (done < len) {
+			const ssize_t w = pwrite(fd, buf + done, len - done, (off_t)(file_off + o + done));
+			if (w <= 0) { rc = LFM_ERR_CREATE; break; }
+			done += (size_t)w;
+		}
+	}
+	cudaStreamSynchronize(st);
+	for (auto& x : ev) cudaEventDestroy(x);
+	return rc;
+}
+
+// slabs per batch; 0 when the stack is not worth / not fit for batching (few slabs, c or t blocked)
+static uint64_t slabs_per_batch(const klb_image_header& h, const Layout& L, bool pair_frames)
+{
+	if (env_int("LFM_B200_NO_PIPELINE", 0) || h.blockSize[3] != 1 || h.blockSize[4] != 1) return 0;
+	const uint64_t batch_bytes = env_int("LFM_B200_BATCH_KB", 0) > 0 ? (uint64_t)env_int("LFM_B200_BATCH_KB", 0) << 10 : kBatchBytes;   // test knob
+	const uint64_t slab_bytes = (uint64_t)h.blockSize[2] * L.fpx * 2;
+	uint64_t n = std::max<uint64_t>(1, batch_bytes / std::max<uint64_t>(1, slab_bytes));
+	// the block codec kernels are latency bound: a batch needs a few thousand KLB blocks to fill the GPU (k_huff_decode alone keeps
+	// ~1500 streams in flight), or the overlap won is lost again in half-empty kernels
+	if (env_int("LFM_B200_BATCH_KB", 0) <= 0) n = std::max<uint64_t>(n, (kBatchBlocks + L.blocksPerSlab - 1) / L.blocksPerSlab);
+	if (pair_frames && (h.blockSize[2] & 1)) n = (n + 1) & ~(uint64_t)1;         // batches start on even frames
+	return L.nSlabs >= 2 * n ? n : 0;
+}
+
+static int compress_pipelined(const FrameSource& src, klb_image_header& h, const Layout& L, const StackDesc& desc, int k, int video,
+                              const FileSink& sink, uint64_t per)
+{
+	Engine& e = Engine::for_device(g_set.first_device);
+	cudaSetDevice(e.device());
+	const int dev = e.device();
+	cudaStream_t up_st = (cudaStream_t)e.copy_stream(0), down_st = (cudaStream_t)e.copy_stream(1);   // created on this thread
+	const uint64_t nbatch = (L.nSlabs + per - 1) / per;
+	struct Batch { uint64_t s0, s1, f0, nf; };
+	std::vector<Batch> B(nbatch);
+	uint64_t max_nf = 0;
+	for (uint64_t b = 0; b < nbatch; b++) {
+		B[b].s0 = b * per; B[b].s1 = std::min(L.nSlabs, (b + 1) * per);
+		uint64_t f0, f1; slab_frames(h, L, B[b].s0, B[b].s1, f0, f1);
+		B[b].f0 = f0; B[b].nf = f1 - f0 + 1;
+		max_nf = std::max(max_nf, B[b].nf);
+	}
+	const size_t img_bytes = (size_t)max_nf * L.fpx * 2;
+	if (e.reserve(e.user[UB_IMG], img_bytes) || e.reserve(e.user[UB_IMG2], img_bytes) || (k != 0 && e.reserve(e.user[UB_SYM], img_bytes))) return LFM_ERR_CUDA;
+	if (!e.pinned(kStageBufs * kStageChunk, 0) || !e.pinned(kStageBufs * kStageChunk, 1)) return LFM_ERR_CUDA;
+	uint16_t* dimg[2] = { (uint16_t*)e.user[UB_IMG].p, (uint16_t*)e.user[UB_IMG2].p };
+	uint16_t* dsym = (uint16_t*)e.user[UB_SYM].p;
+	std::thread up_th[2], wr_th[2];
+	int up_rc[2] = { 0, 0 }, wr_rc[2] = { 0, 0 };
+	auto upload = [&](uint64_t b, int slot) {
+		cudaSetDevice(dev);
+		const Batch& bt = B[b];
+		if (src.base) h2d_staged(e, dimg[slot], src.frame(bt.f0, L.fpx), (size_t)bt.nf * L.fpx * 2, up_st);
+		else for (uint64_t f = 0; f < bt.nf; f++) h2d_staged(e, dimg[slot] + f * L.fpx, src.frame(bt.f0 + f, L.fpx), (size_t)L.fpx * 2, up_st);
+		if (cudaStreamSynchronize(up_st) != cudaSuccess) { cudaGetLastError(); up_rc[slot] = LFM_ERR_CUDA; }
+	};
+	auto join_all = [&]() { for (auto& t : up_th) if (t.joinable()) t.join(); for (auto& t : wr_th) if (t.joinable()) t.join(); };
+	int rc = LFM_OK;
+	uint64_t pay_off = 0, blk = 0;
+	std::vector<uint32_t> sizes;
+	const double t0 = now_ms();
+	up_th[0] = std::thread(upload, 0, 0);
+	for (uint64_t b = 0; b < nbatch && rc == LFM_OK; b++) {
+		const int slot = (int)(b & 1);
+		up_th[slot].join();                                            // batch b is resident
+		if ((rc = up_rc[slot])) break;
+		if (b + 1 < nbatch) up_th[slot ^ 1] = std::thread(upload, b + 1, slot ^ 1);   // its image buffer was last read by batch b - 1 (done)
+		if (wr_th[slot].joinable()) { wr_th[slot].join(); if ((rc = wr_rc[slot])) break; }   // payload buffer `slot` (batch b - 2) is on disk
+		const Batch& bt = B[b];
+		const uint16_t* img_base = dimg[slot] - bt.f0 * L.fpx;         // virtual base: absolute frame indexing
+		const uint16_t* sym_base = img_base;
+		CompressStats st;
+		if (k != 0) {
+			rc = e.predict(img_base, dsym - bt.f0 * L.fpx, desc, k, video, (uint32_t)bt.f0, (uint32_t)bt.nf);
+			st.launches++;
+			if (rc) break;
+			sym_base = dsym - bt.f0 * L.fpx;
+		}
+		const uint64_t first = bt.s0 * L.blocksPerSlab, count = (bt.s1 - bt.s0) * L.blocksPerSlab;
+		sizes.resize(count);
+		const uint8_t* dpay = nullptr; uint64_t pbytes = 0;
+		e.use_payload_buffer(slot);
+		rc = e.compress_blocks(sym_base, desc, first, count, sizes.data(), &dpay, &pbytes, &st);
+		if (rc) { g_err = e.last_error(); break; }
+		if (k != 0) g_stats.ms_predict += e.last_predict_ms();
+		uint64_t acc = blk ? h.blockOffset[blk - 1] : 0;
+		for (uint64_t i = 0; i < count; i++) { acc += sizes[i]; h.blockOffset[blk + i] = acc; }
+		blk += count;
+		g_stats.ms_rle += st.ms_rle; g_stats.ms_bwt += st.ms_bwt; g_stats.ms_mtf += st.ms_mtf; g_stats.ms_huff += st.ms_huff;
+		g_stats.gpu_launches += st.launches; g_stats.periodic_blocks += st.periodic_blocks;
+		const uint64_t at = sink.base + pay_off;
+		// one writer at a time (they share the pinned ring and copy stream 1): batch b - 1 had all of this batch's kernels to finish
+		if (wr_th[slot ^ 1].joinable()) { wr_th[slot ^ 1].join(); if ((rc = wr_rc[slot ^ 1])) break; }
+		wr_th[slot] = std::thread([&, slot, dpay, pbytes, at]() { cudaSetDevice(dev); wr_rc[slot] = pbytes ? payload_to_fd(e, dpay, pbytes, sink.fd, at, down_st) : LFM_OK; });
+		pay_off += pbytes;
+	}
+	join_all();
+	e.use_payload_buffer(0);
+	for (int i = 0; i < 2; i++) { if (!rc && up_rc[i]) rc = up_rc[i]; if (!rc && wr_rc[i]) rc = wr_rc[i]; }
+	g_stats.payload_bytes = pay_off;
+	g_stats.ms_total += now_ms() - t0;
+	return rc;
+}
 
 // Phase 1: everything up to the compacted streams in device memory + header.blockOffset[].
-int compress_core(const FrameSource& src, klb_image_header& h, std::vector<ShardOut>& shards, std::vector<uint64_t>& shardFirstBlock)
+// With a FileSink and one GPU, large stacks take the slab pipeline: the payload is then already in the file when this returns
+// (shards stays empty) and only the header + table are left to write.
+int compress_core(const FrameSource& src, klb_image_header& h, std::vector<ShardOut>& shards, std::vector<uint64_t>& shardFirstBlock,
+                  const FileSink* sink = nullptr)
 {
 	memset(&g_stats, 0, sizeof(g_stats));
 	int rc = validate(h, true);
@@ -312,6 +448,14 @@ int compress_core(const FrameSource& src, klb_image_header& h, std::vector<Shard
 	g_stats.predictor = k;
 
 	const int D = (int)std::min<uint64_t>((uint64_t)ndev, L.nSlabs);
+	if (sink && D == 1) {
+		const uint64_t per = slabs_per_batch(h, L, k != 0 && video);
+		if (per) {
+			FileSink fs = *sink; fs.base = sizeof(uint8_t) * 320 + L.Nb * sizeof(uint64_t);
+			shards.clear(); shardFirstBlock.clear();
+			return compress_pipelined(src, h, L, desc, k, video, fs, per);
+		}
+	}
 	const std::vector<uint64_t> cut = shard_cuts(h, L, D, k != 0 && video);
 	shards.assign(D, ShardOut());
 	shardFirstBlock.assign(D, 0);
@@ -410,8 +554,8 @@ struct PayloadSource {
 			for (const auto& r : ranges) { cudaMemcpyAsync((uint8_t*)dst + dpos, base + r.first, r.second - r.first, cudaMemcpyHostToDevice, st); dpos += r.second - r.first; }
 			return LFM_OK;
 		}
-		const uint64_t CH = (uint64_t)32 << 20;
-		uint8_t* pin = (uint8_t*)e.pinned(2 * CH);
+		const uint64_t CH = (uint64_t)16 << 20;
+		uint8_t* pin = (uint8_t*)e.pinned(kStageBufs * kStageChunk, 0);
 		if (!pin) return LFM_ERR_CUDA;
 		cudaEvent_t ev[2]; cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
 		int rc = LFM_OK;
@@ -439,6 +583,91 @@ struct PayloadSource {
 		return rc;
 	}
 };
+
+// Full reads of large stacks on one GPU, the mirror image of compress_pipelined: while batch b (whole z-slabs) is decoded and
+// un-predicted, the streams of batch b + 1 are read from the file / host memory into the second payload buffer (pinned staging,
+// copy stream 0, own host thread) and the pixels of batch b - 1 travel to the caller's buffer (copy stream 1, own host thread).
+static int decompress_pipelined(const klb_image_header& h, const Layout& L, const StackDesc& desc, int k, int video,
+                                const PayloadSource& psrc, uint16_t* out, uint64_t per)
+{
+	Engine& e = Engine::for_device(g_set.first_device);
+	cudaSetDevice(e.device());
+	const int dev = e.device();
+	cudaStream_t up_st = (cudaStream_t)e.copy_stream(0), down_st = (cudaStream_t)e.copy_stream(1);
+	const uint64_t nbatch = (L.nSlabs + per - 1) / per;
+	struct Batch { uint64_t s0, s1, f0, nf, beg, end; };
+	std::vector<Batch> B(nbatch);
+	uint64_t max_nf = 0, max_pay = 0;
+	for (uint64_t b = 0; b < nbatch; b++) {
+		Batch& bt = B[b];
+		bt.s0 = b * per; bt.s1 = std::min(L.nSlabs, (b + 1) * per);
+		uint64_t f0, f1; slab_frames(h, L, bt.s0, bt.s1, f0, f1);
+		bt.f0 = f0; bt.nf = f1 - f0 + 1;
+		const uint64_t id0 = bt.s0 * L.blocksPerSlab, id1 = bt.s1 * L.blocksPerSlab;
+		bt.beg = id0 ? h.blockOffset[id0 - 1] : 0; bt.end = h.blockOffset[id1 - 1];
+		max_nf = std::max(max_nf, bt.nf); max_pay = std::max(max_pay, bt.end - bt.beg);
+	}
+	const size_t img_bytes = (size_t)max_nf * L.fpx * 2;
+	if (e.reserve(e.user[UB_PAY], max_pay + 16) || e.reserve(e.user[UB_PAY2], max_pay + 16) || e.reserve(e.user[UB_IMG], img_bytes) ||
+	    e.reserve(e.user[UB_IMG2], img_bytes) || (k != 0 && e.reserve(e.user[UB_SYM], img_bytes))) return LFM_ERR_CUDA;
+	if (!e.pinned(kStageBufs * kStageChunk, 0) || !e.pinned(kStageBufs * kStageChunk, 1)) return LFM_ERR_CUDA;
+	uint8_t* dpay[2] = { (uint8_t*)e.user[UB_PAY].p, (uint8_t*)e.user[UB_PAY2].p };
+	uint16_t* dimg[2] = { (uint16_t*)e.user[UB_IMG].p, (uint16_t*)e.user[UB_IMG2].p };
+	uint16_t* dsym = (uint16_t*)e.user[UB_SYM].p;
+	std::thread up_th[2], dn_th[2];
+	int up_rc[2] = { 0, 0 }, dn_rc[2] = { 0, 0 };
+	auto fetch = [&](uint64_t b, int slot) {
+		cudaSetDevice(dev);
+		std::vector<std::pair<uint64_t, uint64_t>> ranges(1, std::make_pair(B[b].beg, B[b].end));
+		up_rc[slot] = psrc.to_device(e, dpay[slot], ranges, up_st);
+		if (cudaStreamSynchronize(up_st) != cudaSuccess) { cudaGetLastError(); up_rc[slot] = LFM_ERR_CUDA; }
+	};
+	auto join_all = [&]() { for (auto& t : up_th) if (t.joinable()) t.join(); for (auto& t : dn_th) if (t.joinable()) t.join(); };
+	int rc = LFM_OK;
+	std::vector<uint64_t> ids, beg, end;
+	const double t0 = now_ms();
+	up_th[0] = std::thread(fetch, 0, 0);
+	for (uint64_t b = 0; b < nbatch && rc == LFM_OK; b++) {
+		const int slot = (int)(b & 1);
+		up_th[slot].join();
+		if ((rc = up_rc[slot])) { if (rc == LFM_ERR_BZIP) std::cerr << "ERROR: lfm_b200: file is truncated" << std::endl; break; }
+		if (b + 1 < nbatch) up_th[slot ^ 1] = std::thread(fetch, b + 1, slot ^ 1);    // its payload buffer was decoded by batch b - 1 (done)
+		if (dn_th[slot].joinable()) { dn_th[slot].join(); if ((rc = dn_rc[slot])) break; }   // image buffer `slot` (batch b - 2) has left
+		const Batch& bt = B[b];
+		const uint64_t id0 = bt.s0 * L.blocksPerSlab, cnt = (bt.s1 - bt.s0) * L.blocksPerSlab;
+		ids.resize(cnt); beg.resize(cnt); end.resize(cnt);
+		for (uint64_t i = 0; i < cnt; i++) {
+			ids[i] = id0 + i;
+			beg[i] = ((id0 + i) ? h.blockOffset[id0 + i - 1] : 0) - bt.beg; end[i] = h.blockOffset[id0 + i] - bt.beg;
+		}
+		uint16_t* res = dimg[slot] - bt.f0 * L.fpx;                     // virtual base: absolute frame indexing
+		uint16_t* sym_base = k != 0 ? dsym - bt.f0 * L.fpx : res;
+		DecompressStats st;
+		rc = e.decompress_blocks(dpay[slot], beg.data(), end.data(), ids.data(), cnt, sym_base, desc, &st);
+		if (rc) { g_err = e.last_error(); break; }
+		if (k != 0) {
+			rc = e.unpredict(sym_base, res, desc, k, video, (uint32_t)bt.f0, (uint32_t)bt.nf);
+			st.launches += video ? 2 : 1;
+			if (rc) break;
+			if (cudaStreamSynchronize((cudaStream_t)e.stream()) != cudaSuccess) { cudaGetLastError(); rc = LFM_ERR_CUDA; break; }
+			g_stats.ms_unpredict += e.last_unpredict_ms();
+		}
+		g_stats.ms_decode += st.ms_decode; g_stats.ms_imtf += st.ms_imtf; g_stats.ms_ibwt += st.ms_ibwt; g_stats.ms_unrle += st.ms_unrle;
+		g_stats.gpu_launches += st.launches;
+		const uint16_t* srcp = dimg[slot]; uint16_t* dstp = out + bt.f0 * L.fpx; const size_t nbytes = (size_t)bt.nf * L.fpx * 2;
+		// one download at a time (they share the pinned ring and copy stream 1): batch b - 1 had all of this batch's kernels to finish
+		if (dn_th[slot ^ 1].joinable()) { dn_th[slot ^ 1].join(); if ((rc = dn_rc[slot ^ 1])) break; }
+		dn_th[slot] = std::thread([&, slot, srcp, dstp, nbytes]() {
+			cudaSetDevice(dev);
+			d2h_staged(e, dstp, srcp, nbytes, down_st);
+			if (cudaStreamSynchronize(down_st) != cudaSuccess) { cudaGetLastError(); dn_rc[slot] = LFM_ERR_CUDA; }
+		});
+	}
+	join_all();
+	for (int i = 0; i < 2; i++) { if (!rc && up_rc[i]) rc = up_rc[i]; if (!rc && dn_rc[i]) rc = dn_rc[i]; }
+	g_stats.ms_total = now_ms() - t0;
+	return rc;
+}
 
 int decompress_core(const klb_image_header& h, const PayloadSource& psrc, uint16_t* out, const klb_ROI* roi)
 {
@@ -492,6 +721,10 @@ int decompress_core(const klb_image_header& h, const PayloadSource& psrc, uint16
 	// blockSize[4] > 1) the frames of neighbouring slabs interleave, and one GPU decodes the stack.
 	const bool disjoint = h.blockSize[3] == 1 && h.blockSize[4] == 1;
 	const int D = (full && contiguous && disjoint && slabs.size() == L.nSlabs) ? (int)std::min<uint64_t>((uint64_t)ndev, slabs.size()) : 1;
+	if (full && D == 1 && desc.codec == 1) {
+		const uint64_t per = slabs_per_batch(h, L, k != 0 && video);
+		if (per) return decompress_pipelined(h, L, desc, k, video, psrc, out, per);
+	}
 	const std::vector<uint64_t> cut = shard_cuts(h, L, D, k != 0 && video);
 
 	std::vector<int> rcs(D, 0);
@@ -612,7 +845,7 @@ static int stream_payload_to_fd(std::vector<ShardOut>& shards, int fd, uint64_t 
 		cudaSetDevice(s.device);
 		Engine& e = Engine::for_device(s.device);
 		cudaStream_t st = (cudaStream_t)e.stream();
-		uint8_t* pin = (uint8_t*)e.pinned(kStageBufs * kStageChunk);
+		uint8_t* pin = (uint8_t*)e.pinned(kStageBufs * kStageChunk, 1);
 		if (!pin) { rcs[d] = LFM_ERR_CUDA; return; }
 		cudaEvent_t ev[kStageBufs];
 		for (auto& x : ev) cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
@@ -682,8 +915,9 @@ static int write_stack_to_file(const std::string& filename, const FrameSource& s
 	int rc;
 	try {
 		std::vector<ShardOut> shards; std::vector<uint64_t> first;
-		rc = compress_core(src, header, shards, first);
-		if (rc == 0) rc = write_file(fd, header, shards);
+		FileSink sink; sink.fd = fd;
+		rc = compress_core(src, header, shards, first, &sink);
+		if (rc == 0) rc = write_file(fd, header, shards);              // header + table (+ whatever payload is still on the GPUs)
 		if (rc == 0 && ftruncate(fd, (off_t)header.getCompressedFileSizeInBytes()) != 0) rc = LFM_ERR_CREATE;
 		if (rc != 0 && ftruncate(fd, 0) != 0) { /* nothing more to do */ }
 	} catch (const std::bad_alloc&) { g_err = "out of host memory"; rc = LFM_ERR_CREATE; }

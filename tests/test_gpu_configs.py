@@ -169,6 +169,39 @@ def test_two_gpus_in_process_full_read_and_video(L, tmp_path):
     assert t.device.index == 0
 
 
+def test_slab_pipeline_file_path(L, oracle, tmp_path, monkeypatch):
+    """writeImage / readImageFull of stacks with many z-slabs on one GPU run as a three-stage pipeline over slab batches (upload |
+    kernels | file write, and the mirror image for reading; klb_imageIO.cpp compress_pipelined / decompress_pipelined).  Forced
+    here with small batches: file bytes == the one-shot memory path == the oracle, exact read back -- image and video stacks
+    (odd block depth: batches must start on even frames), predictor off, codec NONE, and the slices API"""
+    import ctypes as C
+    a = lf_synth_int((45, 200, 230), 13, seed=11).numpy().view(np.uint16)
+    fn, fo = str(tmp_path / "p.lfm"), str(tmp_path / "o.lfm")
+    for hv, bs, kb in ((0, (64, 64, 4, 1, 1), 400), (0x80 | 12, (64, 64, 3, 1, 1), 300), (8, (96, 96, 1, 1, 1), 100), (8 + 7, (64, 64, 5, 1, 1), 1)):
+        monkeypatch.setenv("LFM_B200_NO_PIPELINE", "1")
+        one_shot = L.compress_to_bytes(a, header_version=hv, nnum=13, block_size=bs, way=0)
+        monkeypatch.delenv("LFM_B200_NO_PIPELINE")
+        monkeypatch.setenv("LFM_B200_BATCH_KB", str(kb))
+        L.write_stack(a, fn, header_version=hv, nnum=13, block_size=bs, way=0)
+        got = open(fn, "rb").read()
+        assert got == one_shot, (hex(hv), bs)
+        rc, _ = oracle.write(a, fo, hv, 13, 0, block_size=bs)
+        assert rc == 0 and open(fo, "rb").read() == got
+        assert np.array_equal(L.read_stack(fn, way=0), a), (hex(hv), bs)
+        assert np.array_equal(L.decompress_from_bytes(got, a.shape, way=0), a)
+        monkeypatch.delenv("LFM_B200_BATCH_KB")
+    monkeypatch.setenv("LFM_B200_BATCH_KB", "200")
+    L.write_stack(a, fn, header_version=8 + 4, nnum=13, block_size=(64, 64, 2, 1, 1), way=0, codec=0)
+    assert np.array_equal(L.read_stack(fn, way=0), a)
+    ptrs = (C.c_void_p * a.shape[0])(*[a[z].ctypes.data for z in range(a.shape[0])])
+    xyzct = L._u32x5(230, 200, 45, 1, 1)
+    bsz = L._u32x5(64, 64, 4, 1, 1)
+    L.set_way(0)
+    assert L.lib.writeKLBstackSlices(ptrs, os.fsencode(fn), xyzct, 1, -1, None, bsz, 1, None) == 0
+    L.write_stack(a, fo, header_version=0, nnum=13, block_size=(64, 64, 4, 1, 1), way=0)
+    assert open(fn, "rb").read() == open(fo, "rb").read()
+
+
 def _klb_none_payload(a, bs):
     """KLB_COMPRESSION_TYPE::NONE: blocks in id order (x fastest), each the verbatim rows of its box"""
     Z, Y, X = a.shape

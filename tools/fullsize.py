@@ -59,6 +59,21 @@ for name in (sys.argv[1:] or ["c3", "c4", "c5"]):
         assert np.array_equal(hon, hn)
         res.update(e2e_compress_gbs=raw / best[0] / 1e9, e2e_decompress_gbs=raw / best[1] / 1e9, file_bytes=int(nblob))
         del h, blob, ho
+        # the drop-in file API with PAGEABLE memory (what JNI / MEX callers pass), file on /dev/shm: writeLFMstackEx + readKLBstackInPlace
+        pg = d.cpu().numpy().view(np.uint16).copy(); po = np.empty_like(pg)
+        fn = os.fsencode("/dev/shm/lfm_fullsize_%d.lfm" % os.getpid())
+        bestf = [1e9, 1e9]
+        for rep in range(2):
+            t0 = time.perf_counter()
+            rc = L.lib.writeLFMstackEx(pg.ctypes.data, fn, xyzct, 1, -1, None, None, 1, None, hv, T); t1 = time.perf_counter()
+            assert rc == 0, rc
+            dt = C.c_int(); rc = L.lib.readKLBstackInPlace(fn, po.ctypes.data, C.byref(dt), -1); t2 = time.perf_counter()
+            assert rc == 0, rc
+            bestf = [min(bestf[0], t1 - t0), min(bestf[1], t2 - t1)]
+        assert np.array_equal(po, pg)
+        os.remove(fn)
+        res.update(file_api_compress_gbs=raw / bestf[0] / 1e9, file_api_decompress_gbs=raw / bestf[1] / 1e9)
+        del pg, po
     print(json.dumps(res), flush=True)
     del d, back
     torch.cuda.empty_cache()
