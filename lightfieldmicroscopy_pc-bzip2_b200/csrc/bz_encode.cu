@@ -554,20 +554,21 @@ constexpr uint32_t HP_INF = 0xFFFFFFFFu;             // weight of an empty heap 
 // Leaves are nodes 1..alpha with weights lw[1..alpha]; parent[] receives the links (HP_NOPARENT at the root).
 __device__ __forceinline__ void hp_build_tree(uint64_t* heap, uint16_t* parent, const uint32_t* lw, int alpha)
 {
+	// (heap walks without data-dependent branches, see hp_build_tree32 below)
 	for (int i = 0; i < 2 * alpha + 6; i++) heap[i] = (uint64_t)HP_INF << 32;
 	heap[0] = 0;
-	// up-heap: the ancestors of a slot are known before anything is compared, so all of them are fetched at once (independent
-	// shared-memory loads in flight together) and the walk itself is register arithmetic; heap[0] (weight 0) stops it
 	auto up_heap = [&](int z, uint32_t wt, uint32_t node) {
 		uint64_t anc[9];                                              // the heap never holds more than 2^9 - 1 entries
 		#pragma unroll
 		for (int k = 0; k < 9; k++) anc[k] = heap[z >> (k + 1)];
+		int m = 0;
 		#pragma unroll
-		for (int k = 0; k < 9; k++) {
-			if (!(wt < (uint32_t)(anc[k] >> 32))) break;
-			heap[z] = anc[k]; z >>= 1;
+		for (int k = 0; k < 9; k++) {                                 // keys do not increase towards the root: the first m ancestors move down
+			const bool mv = wt < (uint32_t)(anc[k] >> 32);
+			if (mv) heap[z >> k] = anc[k];
+			m += mv ? 1 : 0;
 		}
-		heap[z] = ((uint64_t)wt << 32) | node;
+		heap[z >> m] = ((uint64_t)wt << 32) | node;
 	};
 	int n_heap = 0;
 	for (int i = 1; i <= alpha; i++) {
@@ -585,32 +586,35 @@ __device__ __forceinline__ void hp_build_tree(uint64_t* heap, uint16_t* parent, 
 			n_heap--;
 			const uint32_t tw = (uint32_t)(tmp >> 32);
 			int z = 1;
-			if (n_heap >= 1) {
-				// down-heap, TWO levels per shared-memory round trip: the four grandchildren and the eight great-grandchildren of
-				// the current slot are fetched while its children (already in registers) are being compared; slots below the heap
-				// hold HP_INF, so the walk always stops there (clamped addresses are never used: their parents are HP_INF)
-				ulonglong2 ch = *reinterpret_cast<const ulonglong2*>(heap + 2);               // children of the root
-				for (;;) {
-					const int g = min(4 * z, HP_HEAP - 4), q8 = 8 * z;
-					const ulonglong2 ga = *reinterpret_cast<const ulonglong2*>(heap + g);
-					const ulonglong2 gb = *reinterpret_cast<const ulonglong2*>(heap + g + 2);
-					const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(heap + min(q8, HP_HEAP - 2));
-					const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(heap + min(q8 + 2, HP_HEAP - 2));
-					const ulonglong2 q2 = *reinterpret_cast<const ulonglong2*>(heap + min(q8 + 4, HP_HEAP - 2));
-					const ulonglong2 q3 = *reinterpret_cast<const ulonglong2*>(heap + min(q8 + 6, HP_HEAP - 2));
-					const bool r1 = (uint32_t)(ch.y >> 32) < (uint32_t)(ch.x >> 32);
-					const uint64_t c1 = r1 ? ch.y : ch.x;
-					if (tw < (uint32_t)(c1 >> 32)) break;
-					heap[z] = c1; z = 2 * z + (r1 ? 1 : 0);
-					const ulonglong2 ch2 = r1 ? gb : ga;
-					const bool r2 = (uint32_t)(ch2.y >> 32) < (uint32_t)(ch2.x >> 32);
-					const uint64_t c2 = r2 ? ch2.y : ch2.x;
-					if (tw < (uint32_t)(c2 >> 32)) break;
-					heap[z] = c2; z = 2 * z + (r2 ? 1 : 0);
-					ch = r1 ? (r2 ? q3 : q2) : (r2 ? q1 : q0);
-				}
-				heap[z] = tmp;
+			// down-heap, TWO levels per shared-memory round trip: the four grandchildren and the eight great-grandchildren of the
+			// current slot are fetched while its children (already in registers) are being compared; slots below the heap hold
+			// HP_INF, so the walk stops there by itself (clamped addresses are never used: their parents are HP_INF)
+			const int levels = 31 - __clz(n_heap | 1);
+			ulonglong2 ch = *reinterpret_cast<const ulonglong2*>(heap + 2);               // children of the root
+			bool going = n_heap >= 1;
+			#pragma unroll 1
+			for (int it = 0; it < levels; it += 2) {
+				const int g = min(4 * z, HP_HEAP - 4), q8 = 8 * z;
+				const ulonglong2 ga = *reinterpret_cast<const ulonglong2*>(heap + g);
+				const ulonglong2 gb = *reinterpret_cast<const ulonglong2*>(heap + g + 2);
+				const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(heap + min(q8, HP_HEAP - 2));
+				const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(heap + min(q8 + 2, HP_HEAP - 2));
+				const ulonglong2 q2 = *reinterpret_cast<const ulonglong2*>(heap + min(q8 + 4, HP_HEAP - 2));
+				const ulonglong2 q3 = *reinterpret_cast<const ulonglong2*>(heap + min(q8 + 6, HP_HEAP - 2));
+				const bool r1 = (uint32_t)(ch.y >> 32) < (uint32_t)(ch.x >> 32);
+				const uint64_t c1 = r1 ? ch.y : ch.x;
+				going = going & !(tw < (uint32_t)(c1 >> 32));
+				if (going) heap[z] = c1;
+				z = going ? 2 * z + (r1 ? 1 : 0) : z;
+				const ulonglong2 ch2 = r1 ? gb : ga;
+				const bool r2 = (uint32_t)(ch2.y >> 32) < (uint32_t)(ch2.x >> 32);
+				const uint64_t c2 = r2 ? ch2.y : ch2.x;
+				going = going & !(tw < (uint32_t)(c2 >> 32));
+				if (going) heap[z] = c2;
+				z = going ? 2 * z + (r2 ? 1 : 0) : z;
+				ch = r1 ? (r2 ? q3 : q2) : (r2 ? q1 : q0);
 			}
+			if (n_heap >= 1) heap[z] = tmp;
 		}
 		n_nodes++;
 		parent[(uint32_t)pick[0]] = (uint16_t)n_nodes; parent[(uint32_t)pick[1]] = (uint16_t)n_nodes;
