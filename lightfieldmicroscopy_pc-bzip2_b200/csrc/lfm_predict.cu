@@ -1126,6 +1126,199 @@ k_unpredict_bands(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H,
 	asm volatile("bar.sync 1, %0;" :: "r"(ncomp + 32) : "memory");                            // w == nsteps_run: everything is stored
 }
 
+// =====================================================================================================
+// Way "space", predictors 1, 2 and 4: the rule is LINEAR modulo 2^16 (the same sub-aperture pixel of the left / upper / both
+// neighbouring microlenses, src/lfm_Predictors_space.cu), so the inverse is a strided prefix sum and needs no wavefront:
+//   k = 4:  pixel = 2-D prefix sum, over the tile grid (tx, ty) of its sub-aperture image (u, v), of the residuals -- with
+//           tile (0,0) (decoded by k_unpredict_seed) as the corner term: a column pass (stride T rows) and a row pass (stride T
+//           pixels), the second one in place;
+//   k = 1:  first tile column by a column pass (its rule looks up), then every row by a row pass seeded with that column;
+//   k = 2:  first tile row by a row pass, then every column by a column pass seeded with that row.
+// Both passes stream whole 128-byte lines; frames are processed in groups that fit L2, so the in-place second pass reads what
+// the first one has just written.  Arithmetic is 2 x 16 bits per 32-bit word (__vadd2 wraps each half: exactly the int16
+// truncation of the reference).
+// element source rules for the heads of the chains: 0 = residual, 1 = from `out` inside tile (0,0) only (the seed),
+// 2 = from `out` for the whole first tile column / row (already final)
+// =====================================================================================================
+__device__ __forceinline__ uint32_t unsymbolize16x2(uint32_t w)
+{
+	return ((w >> 1) & 0x7FFF7FFFu) ^ ((w & 0x00010001u) * 0xFFFFu);      // per half: (s >> 1) ^ -(s & 1)
+}
+
+constexpr int SC_ROWS_NT = 256;
+template <bool SRC_OUT>
+__global__ void __launch_bounds__(SC_ROWS_NT)
+k_unscan_rows(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T, uint32_t z_start, uint32_t z_step,
+              int rows_per_cta, int y_limit, int head_rule, int pitch)
+{
+	extern __shared__ __align__(16) uint16_t sc_rows[];                   // [rows_per_cta][pitch]
+	const int tid = (int)threadIdx.x;
+	const uint32_t z = z_start + blockIdx.y * z_step;
+	const uint64_t fbase = (uint64_t)z * W * H;
+	const int y0 = (int)blockIdx.x * rows_per_cta;
+	const int nrows = min(rows_per_cta, min(H, y_limit) - y0);
+	if (nrows <= 0) return;
+	const uint16_t* src = (SRC_OUT ? (const uint16_t*)out : sym) + fbase;
+	const uint16_t* o = out + fbase;
+	if ((W & 7) == 0) {                                                 // rows are whole 16-byte vectors
+		const int vpr = W >> 3;
+		for (int i = tid; i < nrows * vpr; i += SC_ROWS_NT) {
+			const int r = i / vpr, xv = i - r * vpr;
+			uint4 q = *reinterpret_cast<const uint4*>(src + (size_t)(y0 + r) * W + xv * 8);
+			if (!SRC_OUT) { q.x = unsymbolize16x2(q.x); q.y = unsymbolize16x2(q.y); q.z = unsymbolize16x2(q.z); q.w = unsymbolize16x2(q.w); }
+			*reinterpret_cast<uint4*>(sc_rows + (size_t)r * pitch + xv * 8) = q;
+		}
+	} else {
+		for (int i = tid; i < nrows * W; i += SC_ROWS_NT) {
+			const int r = i / W, x = i - r * W;
+			const uint16_t sv = src[(size_t)(y0 + r) * W + x];
+			sc_rows[(size_t)r * pitch + x] = SRC_OUT ? sv : (uint16_t)unsymbolize16(sv);
+		}
+	}
+	__syncthreads();
+	if (!SRC_OUT && head_rule) {                                          // heads of the chains that are already decoded
+		const int tw = min(T, W);
+		for (int i = tid; i < nrows * tw; i += SC_ROWS_NT) {
+			const int r = i / tw, x = i - r * tw;
+			if (head_rule == 2 || y0 + r < T) sc_rows[(size_t)r * pitch + x] = o[(size_t)(y0 + r) * W + x];
+		}
+		__syncthreads();
+	}
+	for (int g = tid; g < nrows * T; g += SC_ROWS_NT) {                   // thread = (row, u): the chain over tx
+		const int r = g / T, u = g - r * T;
+		uint16_t* row = sc_rows + (size_t)r * pitch;
+		uint32_t acc = 0;
+		for (int xb = u; xb < W; xb += 8 * T) {                             // eight loads first: the stores below may alias them
+			uint32_t val[8];
+			#pragma unroll
+			for (int j = 0; j < 8; j++) { const int x = xb + j * T; val[j] = x < W ? row[x] : 0u; }
+			#pragma unroll
+			for (int j = 0; j < 8; j++) { const int x = xb + j * T; acc += val[j]; if (x < W) row[x] = (uint16_t)acc; }
+		}
+	}
+	__syncthreads();
+	uint16_t* dst = out + fbase;
+	if ((W & 7) == 0) {
+		const int vpr = W >> 3;
+		for (int i = tid; i < nrows * vpr; i += SC_ROWS_NT) {
+			const int r = i / vpr, xv = i - r * vpr;
+			*reinterpret_cast<uint4*>(dst + (size_t)(y0 + r) * W + xv * 8) = *reinterpret_cast<const uint4*>(sc_rows + (size_t)r * pitch + xv * 8);
+		}
+	} else {
+		for (int i = tid; i < nrows * W; i += SC_ROWS_NT) { const int r = i / W, x = i - r * W; dst[(size_t)(y0 + r) * W + x] = sc_rows[(size_t)r * pitch + x]; }
+	}
+}
+
+constexpr int SC_COLS_NT = 128;
+constexpr int SC_COLS_B = 12;                                             // rows fetched ahead of the running sum
+// thread = (VEC adjacent columns, v): the chain over ty.  VEC = 4 / 2 need W to be a multiple of 4 / 2 (64- / 32-bit accesses).
+template <bool SRC_OUT, int VEC>
+__global__ void __launch_bounds__(SC_COLS_NT)
+k_unscan_cols(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T, uint32_t z_start, uint32_t z_step,
+              int x_limit, int head_rule)
+{
+	const int x = VEC * (int)(blockIdx.x * SC_COLS_NT + threadIdx.x);
+	if (x >= min(W, x_limit)) return;
+	const int v = (int)blockIdx.y;
+	if (v >= H) return;
+	const uint32_t z = z_start + blockIdx.z * z_step;
+	const uint64_t fbase = (uint64_t)z * W * H;
+	const uint16_t* src = (SRC_OUT ? (const uint16_t*)out : sym) + fbase;
+	uint16_t* o = out + fbase;
+	constexpr int NW = VEC == 4 ? 2 : 1;                                    // 32-bit words per thread and row
+	uint32_t acc[NW];
+	#pragma unroll
+	for (int w = 0; w < NW; w++) acc[w] = 0;
+	for (int yb = v; yb < H; yb += T * SC_COLS_B) {
+		uint32_t val[SC_COLS_B][NW];
+		#pragma unroll
+		for (int j = 0; j < SC_COLS_B; j++) {                               // independent loads first: the stores below may alias them
+			const int y = yb + j * T;
+			#pragma unroll
+			for (int w = 0; w < NW; w++) val[j][w] = 0;
+			if (y < H) {
+				const size_t at = (size_t)y * W + x;
+				if (VEC == 1) {
+					uint32_t sv = src[at];
+					if (!SRC_OUT) { sv = (uint32_t)unsymbolize16((uint16_t)sv) & 0xffffu; if (y < T && head_rule && (head_rule == 2 || x < T)) sv = o[at]; }
+					val[j][0] = sv;
+				} else {
+					uint32_t wv[NW];
+					if (VEC == 4) { const uint2 q = *reinterpret_cast<const uint2*>(src + at); wv[0] = q.x; wv[NW - 1] = q.y; }
+					else wv[0] = *reinterpret_cast<const uint32_t*>(src + at);
+					if (!SRC_OUT) {
+						#pragma unroll
+						for (int w = 0; w < NW; w++) {
+							wv[w] = unsymbolize16x2(wv[w]);
+							if (y < T && head_rule) {                           // heads that are already decoded (per half)
+								const uint32_t ov = *reinterpret_cast<const uint32_t*>(o + at + 2 * w);
+								const bool h0 = head_rule == 2 || x + 2 * w < T, h1 = head_rule == 2 || x + 2 * w + 1 < T;
+								wv[w] = (h0 ? (ov & 0xffffu) : (wv[w] & 0xffffu)) | (h1 ? (ov & 0xffff0000u) : (wv[w] & 0xffff0000u));
+							}
+						}
+					}
+					#pragma unroll
+					for (int w = 0; w < NW; w++) val[j][w] = wv[w];
+				}
+			}
+		}
+		#pragma unroll
+		for (int j = 0; j < SC_COLS_B; j++) {
+			const int y = yb + j * T;
+			if (y < H) {
+				const size_t at = (size_t)y * W + x;
+				if (VEC == 1) { acc[0] = (acc[0] + val[j][0]) & 0xffffu; o[at] = (uint16_t)acc[0]; }
+				else {
+					#pragma unroll
+					for (int w = 0; w < NW; w++) acc[w] = __vadd2(acc[w], val[j][w]);
+					if (VEC == 4) *reinterpret_cast<uint2*>(o + at) = make_uint2(acc[0], acc[NW - 1]);
+					else *reinterpret_cast<uint32_t*>(o + at) = acc[0];
+				}
+			}
+		}
+	}
+}
+
+// returns 0 ok, 1 launch error, 2 not applicable
+static int launch_unpredict_space_scans(const uint16_t* sym, uint16_t* out, int W, int H, int T, int k,
+                                        uint32_t z_start, uint32_t z_step, uint32_t count, cudaStream_t st)
+{
+	if (k != 1 && k != 2 && k != 4) return 2;
+	const int vec = ((W & 3) == 0 && ((((uintptr_t)sym | (uintptr_t)out) & 7) == 0)) ? 4 : ((W & 1) == 0 && ((((uintptr_t)sym | (uintptr_t)out) & 3) == 0)) ? 2 : 1;
+	const int pitch = (W + 7) & ~7;
+	int R = std::min(16, (int)((48 * 1024) / ((size_t)pitch * 2)));
+	if (R < 1) return 2;                                                   // rows wider than 24 K pixels: the wavefront kernels
+	while (R > 1 && (uint64_t)((H + R - 1) / R) * count < 592) R >>= 1;     // enough CTAs for a single frame
+	const size_t rsmem = (size_t)R * pitch * 2;
+	const unsigned wpb = UF_NT / 32;
+	k_unpredict_seed<<<(count + wpb - 1) / wpb, UF_NT, 0, st>>>(sym, out, W, H, T, 2, k, z_start, z_step, count, 0);
+	// frames in groups whose symbols + pixels fit L2, so that the second pass finds the first one's output there
+	const uint64_t fbytes = (uint64_t)W * H * 2;
+	const uint32_t group = (uint32_t)std::min<uint64_t>(65535, std::max<uint64_t>(1, ((uint64_t)64 << 20) / fbytes));
+	auto rows = [&](bool src_out, uint32_t zs, uint32_t n, int y_limit, int head) {
+		const dim3 grid((unsigned)((std::min(H, y_limit) + R - 1) / R), n);
+		if (src_out) k_unscan_rows<true><<<grid, SC_ROWS_NT, rsmem, st>>>(sym, out, W, H, T, zs, z_step, R, y_limit, head, pitch);
+		else k_unscan_rows<false><<<grid, SC_ROWS_NT, rsmem, st>>>(sym, out, W, H, T, zs, z_step, R, y_limit, head, pitch);
+	};
+	auto cols = [&](uint32_t zs, uint32_t n, int x_limit, int head) {
+		const int xl = std::min(W, x_limit);
+		const int vc = x_limit >= W ? vec : 1;                              // the restricted pass stops at a column that need not be even
+		const int nthr = (xl + vc - 1) / vc;
+		const dim3 grid((unsigned)((nthr + SC_COLS_NT - 1) / SC_COLS_NT), (unsigned)std::min(T, H), n);
+		if (vc == 4) k_unscan_cols<false, 4><<<grid, SC_COLS_NT, 0, st>>>(sym, out, W, H, T, zs, z_step, x_limit, head);
+		else if (vc == 2) k_unscan_cols<false, 2><<<grid, SC_COLS_NT, 0, st>>>(sym, out, W, H, T, zs, z_step, x_limit, head);
+		else k_unscan_cols<false, 1><<<grid, SC_COLS_NT, 0, st>>>(sym, out, W, H, T, zs, z_step, x_limit, head);
+	};
+	const int ALL = 0x7fffffff;
+	for (uint32_t f0 = 0; f0 < count; f0 += group) {
+		const uint32_t n = std::min(group, count - f0), zs = z_start + f0 * z_step;
+		if (k == 4) { cols(zs, n, ALL, 1); rows(true, zs, n, ALL, 0); }
+		else if (k == 1) { cols(zs, n, T, 1); rows(false, zs, n, ALL, 2); }
+		else { rows(false, zs, n, T, 1); cols(zs, n, ALL, 2); }
+	}
+	return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 // per-device progress flags of the band pipeline (grown on demand; launches on one device are stream-ordered by the engine)
 static uint32_t* ub_flags(size_t n)
 {
@@ -1243,6 +1436,11 @@ int launch_unpredict(const uint16_t* sym, uint16_t* out, int W, int H, int T, in
 	int G = std::min(4, T);
 	while (G > 1 && ((size_t)G * plane_b + 16 > (size_t)UG_MAX_SMEM || G * nxr > 1024)) G--;
 	const bool grid_ok = nxr <= 1024 && plane_b + 16 <= (size_t)UG_MAX_SMEM;
+	static const int scans_on = getenv("LFM_B200_SCANS") ? atoi(getenv("LFM_B200_SCANS")) : 1;
+	if (!video && way == 2 && scans_on) {                    // linear rules: strided prefix sums
+		const int rcs = launch_unpredict_space_scans(sym, out, W, H, T, k, z_start, z_step, count, st);
+		if (rcs != 2) return rcs;
+	}
 	if (!video && way == 2 && grid_ok) {                    // tile (0,0), then T*T sub-aperture recurrences per frame
 		k_unpredict_seed<<<(count + wpb - 1) / wpb, UF_NT, 0, st>>>(sym, out, W, H, T, way, k, z_start, z_step, count, 0);
 		const size_t smem = (size_t)G * plane_b + 16;
