@@ -204,78 +204,130 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	__syncwarp();
 	top_up();
 
-	// ---- symbols (decompress.c:349-487 without the MTF): append until EOB. One lookup per symbol; the rare events
-	// (code longer than DEC_LB bits, 32-symbol flush + ring top-up, next selector) stay off the common path.
-	// One group of 50 symbols per outer iteration.  The inner loop has ONE branch: it leaves on a long code, on EOB or at
-	// the end of the group.  Consuming a LUT entry is pure register arithmetic that is a no-op for the "long code" entry
-	// 0, so it is done before the exit test and stays off the branch's shadow; the refill is predicated; the symbol goes
-	// to a shared staging ring (lane 0), which is flushed with coalesced stores at the group boundaries.
+	// ---- symbols (decompress.c:349-487 without the MTF): append until EOB.  A lone warp is bound by the instructions it issues
+	// (~4 cycles each), not by the lookup -> shift -> lookup chain, so the loop is written for the fewest instructions per symbol:
+	//   * a group of 50 symbols is decoded straight through, six symbols per loop trip; the 64-bit bit buffer is refilled once
+	//     per THREE symbols (>= 33 valid bits after a refill, a table code takes <= DEC_LB = 10);
+	//   * no per-symbol end test: EOB is looked for once per group among the 50 staged symbols; the group that holds it (and a
+	//     group with an invalid code) is decoded again from the saved reader state by the careful one-symbol-at-a-time loop,
+	//     which stops at EOB and fails on invalid codes -- whatever the fast path decoded beyond EOB is discarded;
+	//   * every lane stores the (uniform) symbol to the staging row: one STS with an immediate offset, no predicate;
+	//   * a code longer than DEC_LB bits (table entry 0, ~1 % of the symbols) takes bzip2's limit/base/perm walk in line.
 	const uint32_t EOB = n_in_use + 1;
-	uint32_t nsym = 0, flushed = 0;
+	uint32_t nsym = 0;
 	bool done = false;
 	uint32_t hi = (uint32_t)(bb >> 32), lo = (uint32_t)bb;
+	auto refill = [&]() {                                    // predicated: adds the next word when <= 32 bits are left (then lo is empty)
+		const bool fill = bc <= 32u;
+		const uint32_t add_hi = __funnelshift_rc(nxt, 0u, bc);             // nxt >> bc, 0 for bc == 32 (clamped shift)
+		const uint32_t add_lo = nxt << ((32u - bc) & 31u);
+		hi |= fill ? add_hi : 0u;
+		lo = fill ? add_lo : lo;
+		bc += fill ? 32u : 0u;
+		wi += fill ? 1u : 0u;
+		nxt = sw[wi & (DEC_RING - 1)];
+	};
 	for (int grp = 0; !done; grp++) {
 		if (grp >= n_sel) FAIL(2);
 		const int t = (selector[grp >> 1] >> ((grp & 1) * 4)) & 15;
 		if (t >= n_groups) FAIL(2);
 		const uint16_t* lut = S.lut[t];
-		uint32_t k = 0;
-		bool stop = false;
-		while (!stop && k < (uint32_t)kGSize) {
-			uint32_t e;
-			#pragma unroll 1
-			for (;;) {
-				// lazy refill, decided on the bit count left by the PREVIOUS symbol: off the lookup -> shift -> lookup chain.
-				// At least 13 valid bits are always present, so the DEC_LB-bit index does not depend on the inserted word.
-				const uint32_t idx = hi >> (32 - DEC_LB);
-				const bool fill = bc <= 32u;
-				const uint64_t add = (uint64_t)nxt << ((32u - bc) & 31u);
-				hi |= fill ? (uint32_t)(add >> 32) : 0u;
-				lo |= fill ? (uint32_t)add : 0u;
-				bc += fill ? 32u : 0u;
-				wi += fill ? 1u : 0u;
-				nxt = sw[wi & (DEC_RING - 1)];
-				e = lut[idx];                                                      // len | sym << 5   (0: longer than DEC_LB bits)
-				if ((e == 0u) | stop | (k >= (uint32_t)kGSize)) break;
-				const uint32_t nhi = __funnelshift_l(lo, hi, e);                   // funnel shifts take their count modulo 32
-				lo = __funnelshift_l(0u, lo, e);
-				hi = nhi;
-				bc -= e & 31u;
-				const uint32_t sym = e >> 5;
-				if (lane == 0) so[nsym & (DEC_OUT - 1)] = (uint16_t)sym;
-				nsym++; k++;
-				stop = (sym == EOB);
+		const uint32_t hi0 = hi, lo0 = lo, bc0 = bc, wi0 = wi, nxt0 = nxt;          // reader state at the start of the group
+		bool bad = false;
+		// bzip2's limit/base/perm walk for ONE symbol (decompress.c GET_MTF_VAL); an invalid code only raises `bad` here
+		auto long_symbol = [&]() -> uint32_t {
+			refill();                                            // >= 33 bits: the walk looks at 20
+			const uint32_t window = hi >> 12;
+			const int32_t* limit = S.limit[t]; const int32_t* base = S.base[t];
+			int zn = S.minlen[t];
+			while (zn < 20 && (int32_t)(window >> (20 - zn)) > limit[zn]) zn++;
+			const int32_t idx = (int32_t)(window >> (20 - zn)) - base[zn];
+			bad = bad | ((int32_t)(window >> (20 - zn)) > limit[zn]) | (idx < 0) | (idx >= kMaxAlpha);
+			const uint32_t sym = S.perm[t][bad ? 0 : idx];
+			hi = __funnelshift_l(lo, hi, (uint32_t)zn); lo <<= zn; bc -= (uint32_t)zn;
+			refill();                                            // the symbols after it in this run of three find >= 33 bits again
+			return sym;
+		};
+		// a run of N <= 3 symbols after one refill, WITHOUT a branch per symbol: consuming table entry 0 (a long code) is a no-op,
+		// so the run is decoded blindly and, if one of its entries was 0, decoded again with the long codes walked in line
+		auto run = [&](uint16_t* dst, auto NC) {
+			constexpr int N = decltype(NC)::value;
+			refill();
+			const uint32_t h0 = hi, l0 = lo, b0 = bc;
+			uint32_t lowest = 0xffffffffu;
+			#pragma unroll
+			for (int i = 0; i < N; i++) {
+				const uint32_t e = lut[hi >> (32 - DEC_LB)];      // len | sym << 5   (0: longer than DEC_LB bits)
+				hi = __funnelshift_l(lo, hi, e); lo = __funnelshift_l(0u, lo, e); bc -= e & 31u;     // funnel shifts take their count modulo 32
+				dst[i] = (uint16_t)(e >> 5);
+				lowest = min(lowest, e);
 			}
-			if (stop || k >= (uint32_t)kGSize) break;
-			{   // code longer than DEC_LB bits: bzip2's limit/base/perm walk (decompress.c GET_MTF_VAL)
-				bb = ((uint64_t)hi << 32) | lo;
-				const uint32_t window = peek(20);
-				const int32_t* limit = S.limit[t]; const int32_t* base = S.base[t];
-				int zn = S.minlen[t]; int32_t zvec = (int32_t)(window >> (20 - zn));
-				for (;;) {
-					if (zn > 20) FAIL(2);
-					if (zvec <= limit[zn]) break;
-					zn++;
-					if (zn <= 20) zvec = (int32_t)(window >> (20 - zn));
+			if (lowest == 0u) {
+				hi = h0; lo = l0; bc = b0;
+				#pragma unroll 1
+				for (int i = 0; i < N; i++) {
+					const uint32_t e = lut[hi >> (32 - DEC_LB)];
+					uint32_t sym = e >> 5;
+					if (e == 0u) sym = long_symbol();
+					else { hi = __funnelshift_l(lo, hi, e); lo = __funnelshift_l(0u, lo, e); bc -= e & 31u; }
+					dst[i] = (uint16_t)sym;
 				}
-				int32_t idx = zvec - base[zn];
-				if (idx < 0 || idx >= kMaxAlpha) FAIL(2);
-				const uint32_t sym = S.perm[t][idx];
-				drop((uint32_t)zn);
-				hi = (uint32_t)(bb >> 32); lo = (uint32_t)bb;
-				if (lane == 0) so[nsym & (DEC_OUT - 1)] = (uint16_t)sym;
-				nsym++; k++;
+			}
+		};
+		uint16_t* sg = so;
+		#pragma unroll 1
+		for (int c = 0; c < kGSize / 6; c++, sg += 6) {
+			run(sg, std::integral_constant<int, 3>()); run(sg + 3, std::integral_constant<int, 3>());
+			if (bad) break;
+		}
+		if (!bad) run(sg, std::integral_constant<int, 2>());
+		static_assert(kGSize == 50 && kGSize % 6 == 2 && DEC_OUT >= 64, "group layout of the fast path");
+		__syncwarp();
+		uint32_t v0 = so[lane], v1 = so[32 + (lane & 31)];
+		uint32_t cnt = (uint32_t)kGSize;
+		const uint32_t eobm0 = __ballot_sync(0xffffffffu, v0 == EOB), eobm1 = __ballot_sync(0xffffffffu, v1 == EOB && lane < (uint32_t)kGSize - 32u);
+		__syncwarp();
+		if (bad | ((eobm0 | eobm1) != 0u)) {                   // uniform: the last group of the block (or an invalid code)
+			hi = hi0; lo = lo0; bc = bc0; wi = wi0; nxt = nxt0;
+			uint32_t k = 0;
+			bool stop = false;
+			while (!stop && k < (uint32_t)kGSize) {
+				refill();
+				const uint32_t e = lut[hi >> (32 - DEC_LB)];
+				uint32_t sym;
+				if (e != 0u) { hi = __funnelshift_l(lo, hi, e); lo = __funnelshift_l(0u, lo, e); bc -= e & 31u; sym = e >> 5; }
+				else {
+					bb = ((uint64_t)hi << 32) | lo;
+					const uint32_t window = peek(20);
+					const int32_t* limit = S.limit[t]; const int32_t* base = S.base[t];
+					int zn = S.minlen[t]; int32_t zvec = (int32_t)(window >> (20 - zn));
+					for (;;) {
+						if (zn > 20) FAIL(2);
+						if (zvec <= limit[zn]) break;
+						zn++;
+						if (zn <= 20) zvec = (int32_t)(window >> (20 - zn));
+					}
+					const int32_t idx = zvec - base[zn];
+					if (idx < 0 || idx >= kMaxAlpha) FAIL(2);
+					sym = S.perm[t][idx];
+					drop((uint32_t)zn);
+					hi = (uint32_t)(bb >> 32); lo = (uint32_t)bb;
+				}
+				so[k] = (uint16_t)sym;
+				k++;
 				stop = (sym == EOB);
 			}
+			done = stop; cnt = k;
+			__syncwarp();
+			v0 = so[lane]; v1 = so[32 + (lane & 31)];
+			__syncwarp();
 		}
-		done = stop;
+		if (lane < cnt && nsym + lane < mcap) mtfv[nsym + lane] = (uint16_t)v0;
+		if (32u + lane < cnt && nsym + 32u + lane < mcap) mtfv[nsym + 32u + lane] = (uint16_t)v1;
+		nsym += cnt;
 		if (nsym > mcap || wi > wi_limit) FAIL(2);               // more symbols than any block of this geometry can hold
-		__syncwarp();
-		while (flushed + 32 <= nsym) { mtfv[flushed + lane] = so[(flushed + lane) & (DEC_OUT - 1)]; flushed += 32; }
-		__syncwarp();
 		top_up();
 	}
-	if (flushed + lane < nsym) mtfv[flushed + lane] = so[(flushed + lane) & (DEC_OUT - 1)];
 	bb = ((uint64_t)hi << 32) | lo;
 	if (bc <= 32u) { bb |= (uint64_t)nxt << (32u - bc); bc += 32u; wi++; nxt = sw[wi & (DEC_RING - 1)]; }      // back to the header reader's invariant
 	if (wi > wi_limit) FAIL(2);
