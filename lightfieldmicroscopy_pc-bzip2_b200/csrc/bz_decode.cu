@@ -155,19 +155,47 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 			if (lane == 0) selector[i >> 1] = (i & 1) ? (uint8_t)((selector[i >> 1] & 15u) | (t << 4)) : (uint8_t)t;
 		}
 	}
+	// code lengths (decompress.c:314-331): per symbol a run of (1, d) bit pairs -- d = 0: +1, d = 1: -1 -- closed by a 0 bit.  The
+	// whole record is read from one 32-bit window without a loop: the closing bit is the first 0 at an even position, the deltas
+	// are the odd bits before it.  The encoder only writes runs of equal deltas (compress.c:574-581), for which checking the length
+	// before and after the run is bzip2's per-step range check; anything else (mixed deltas, more than 15 pairs) takes the
+	// bit-by-bit loop.  Failures are collected and reported per table: no branch per symbol besides the loop itself.
 	for (int t = 0; t < n_groups; t++) {
 		int curr = (int)get(5);
-		for (int i = 0; i < alpha; i++) {
-			if ((i & 15) == 0) { top_up(); if (wi > wi_limit) FAIL(2); }
-			for (;;) {
-				if (curr < 1 || curr > 20) FAIL(2);
-				uint32_t two = peek(2);
-				if (!(two & 2)) { drop(1); break; }
-				drop(2);
-				curr += (two & 1) ? -1 : 1;
+		bool badlen = false;
+		for (int i0 = 0; i0 < alpha; i0 += 16) {
+			top_up(); if (wi > wi_limit) FAIL(2);
+			const int i1 = min(alpha, i0 + 16);
+			#pragma unroll 1
+			for (int i = i0; i < i1; i++) {
+				const uint32_t w = (uint32_t)(bb >> 32);
+				const uint32_t z = ~w & 0xAAAAAAAAu;
+				const uint32_t lz = (uint32_t)__clz((int)z);      // 2 * (number of pairs); 32: no closing bit in the window
+				const uint32_t k = lz >> 1;
+				const uint32_t ones = (uint32_t)__popc(w & 0x55555555u & ~__funnelshift_rc(0xFFFFFFFFu, 0u, lz));
+				if (z == 0u || (ones != 0u && ones != k)) {          // rare: the reference loop
+					for (;;) {
+						if (curr < 1 || curr > 20) FAIL(2);
+						uint32_t two = peek(2);
+						if (!(two & 2)) { drop(1); break; }
+						drop(2);
+						curr += (two & 1) ? -1 : 1;
+					}
+				} else {
+					badlen = badlen | (curr < 1) | (curr > 20);
+					curr += (int)k - 2 * (int)ones;
+					badlen = badlen | (curr < 1) | (curr > 20);
+					const uint32_t nb = lz + 1u;                     // <= 31
+					bb <<= nb; bc -= nb;
+					const bool fill = bc < 32u;
+					bb |= fill ? ((uint64_t)nxt << ((32u - bc) & 31u)) : 0ull;
+					bc += fill ? 32u : 0u; wi += fill ? 1u : 0u;
+					nxt = sw[wi & (DEC_RING - 1)];
+				}
+				if (lane == 0) S.len[t][i] = (uint8_t)curr;
 			}
-			if (lane == 0) S.len[t][i] = (uint8_t)curr;
 		}
+		if (badlen) FAIL(2);
 	}
 	__syncwarp();
 	// ---- decode tables: lane t builds table t (huffman.c:170-205 + the lookup)
