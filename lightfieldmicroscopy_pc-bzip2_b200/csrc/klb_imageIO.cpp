@@ -167,7 +167,18 @@ public:
 	// never destroyed: the workers wait on the condition variables for the life of the process (destroying a condition
 	// variable with waiters blocks in pthread_cond_destroy at exit)
 	static CopyPool& get() { static CopyPool* p = new CopyPool; return *p; }
-	static constexpr int kWorkers = 3;
+	// workers beside the calling thread: the host cores this process may count on (one rank per GPU under torchrun: the
+	// box's cores divided by LOCAL_WORLD_SIZE), at least 3, at most 7
+	static int workers()
+	{
+		static const int n = [] {
+			const int hw = (int)std::thread::hardware_concurrency();
+			const int ranks = std::max(1, env_int("LOCAL_WORLD_SIZE", 1));
+			const int forced = env_int("LFM_B200_COPY_THREADS", 0);
+			return forced > 0 ? std::min(forced, 32) - 1 : std::min(7, std::max(3, hw / ranks - 1));
+		}();
+		return n;
+	}
 	// run f(0..parts-1): part 0 on the calling thread, the others on the workers; returns when all are done
 	template <class F> void run(int parts, F f)
 	{
@@ -185,7 +196,7 @@ public:
 		caller_.notify_all();
 	}
 private:
-	CopyPool() { for (int i = 0; i < kWorkers; i++) std::thread([this] { loop(); }).detach(); }
+	CopyPool() { for (int i = 0; i < workers(); i++) std::thread([this] { loop(); }).detach(); }
 	void loop()
 	{
 		std::unique_lock<std::mutex> lk(mu_);
@@ -205,7 +216,7 @@ private:
 };
 void par_memcpy(void* dst, const void* src, size_t n)
 {
-	const int nt = CopyPool::kWorkers + 1;
+	const int nt = CopyPool::workers() + 1;
 	if (n < ((size_t)512 << 10)) { memcpy(dst, src, n); return; }
 	const size_t part = (n / nt + 63) & ~(size_t)63;
 	CopyPool::get().run(nt, [=](int i) {
@@ -213,12 +224,51 @@ void par_memcpy(void* dst, const void* src, size_t n)
 		if (len) memcpy((uint8_t*)dst + o, (const uint8_t*)src + o, len);
 	});
 }
+// file I/O of a staging buffer split over the copy pool (a single pwrite / pread of a tmpfs or page-cache file is a
+// single-threaded memcpy: ~13 GB/s measured on the B200 box, tools/pcie_probe.py)
+static int write_all(int fd, const void* p, size_t n, uint64_t at)
+{
+	size_t done = 0;
+	while (done < n) {
+		const ssize_t w = pwrite(fd, (const uint8_t*)p + done, n - done, (off_t)(at + done));
+		if (w <= 0) return LFM_ERR_CREATE;
+		done += (size_t)w;
+	}
+	return LFM_OK;
+}
+static int read_all(int fd, void* p, size_t n, uint64_t at)
+{
+	size_t done = 0;
+	while (done < n) {
+		const ssize_t got = pread(fd, (uint8_t*)p + done, n - done, (off_t)(at + done));
+		if (got <= 0) return LFM_ERR_BZIP;
+		done += (size_t)got;
+	}
+	return LFM_OK;
+}
+template <class IO> static int par_io(size_t n, IO io)          // io(offset, length) -> rc, on 4 KB aligned parts
+{
+	const int nt = CopyPool::workers() + 1;
+	if (n < ((size_t)1 << 20)) return io((size_t)0, n);
+	const size_t part = ((n + nt - 1) / nt + 4095) & ~(size_t)4095;
+	std::atomic<int> rc(LFM_OK);
+	CopyPool::get().run(nt, [&](int i) {
+		const size_t o = std::min(n, part * (size_t)i), len = std::min(n, part * (size_t)(i + 1)) - o;
+		if (len) { const int r = io(o, len); if (r) rc.store(r); }
+	});
+	return rc.load();
+}
+static int par_pread(int fd, uint8_t* buf, size_t n, uint64_t at) { return par_io(n, [=](size_t o, size_t len) { return read_all(fd, buf + o, len, at + o); }); }
 constexpr size_t kStageChunk = (size_t)8 << 20;
 constexpr int kStageBufs = 4;
 // pageable <-> device copies of at least 2 MB are staged: big ones in 8 MB chunks, a single frame in 2 MB chunks so that the
 // host copy of chunk i+1 overlaps the DMA of chunk i
 constexpr size_t kStageMin = (size_t)2 << 20;
-inline size_t stage_chunk(size_t bytes) { return bytes >= ((size_t)64 << 20) ? kStageChunk : ((size_t)2 << 20); }
+inline size_t stage_chunk(size_t bytes)
+{
+	static const size_t small = (size_t)std::min(8 << 10, std::max(256, env_int("LFM_B200_STAGE_KB", 2 << 10))) << 10;     // test knob
+	return bytes >= ((size_t)64 << 20) ? kStageChunk : small;
+}
 
 void h2d_staged(Engine& e, void* dst, const void* src, size_t bytes, cudaStream_t st)
 {
@@ -554,7 +604,9 @@ struct PayloadSource {
 			for (const auto& r : ranges) { cudaMemcpyAsync((uint8_t*)dst + dpos, base + r.first, r.second - r.first, cudaMemcpyHostToDevice, st); dpos += r.second - r.first; }
 			return LFM_OK;
 		}
-		const uint64_t CH = (uint64_t)16 << 20;
+		uint64_t total = 0;
+		for (const auto& r : ranges) total += r.second - r.first;
+		const uint64_t CH = total >= ((uint64_t)64 << 20) ? (uint64_t)16 << 20 : (uint64_t)2 << 20;      // two buffers: 16 MB chunks fit the 32 MB ring
 		uint8_t* pin = (uint8_t*)e.pinned(kStageBufs * kStageChunk, 0);
 		if (!pin) return LFM_ERR_CUDA;
 		cudaEvent_t ev[2]; cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
@@ -565,12 +617,7 @@ struct PayloadSource {
 				const uint64_t len = std::min<uint64_t>(CH, r.second - off);
 				uint8_t* buf = pin + (i & 1) * CH;
 				if (i >= 2) cudaEventSynchronize(ev[i & 1]);          // the copy that last used this buffer has finished
-				uint64_t done = 0;
-				while (done < len) {
-					ssize_t got = pread(fd, buf + done, (size_t)(len - done), (off_t)(file_off + off + done));
-					if (got <= 0) { rc = LFM_ERR_BZIP; break; }
-					done += (uint64_t)got;
-				}
+				rc = par_pread(fd, buf, (size_t)len, file_off + off);
 				if (rc) break;
 				cudaMemcpyAsync((uint8_t*)dst + dpos, buf, len, cudaMemcpyHostToDevice, st);
 				cudaEventRecord(ev[i & 1], st);
@@ -850,24 +897,19 @@ static int stream_payload_to_fd(std::vector<ShardOut>& shards, int fd, uint64_t 
 		cudaEvent_t ev[kStageBufs];
 		for (auto& x : ev) cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
 		const uint64_t bytes = s.payload_bytes;
-		const size_t nch = (size_t)((bytes + kStageChunk - 1) / kStageChunk);
+		const size_t CH = kStageChunk;
+		const size_t nch = (size_t)((bytes + CH - 1) / CH);
 		auto issue = [&](size_t i) {
-			const uint64_t o = (uint64_t)i * kStageChunk; const size_t len = (size_t)std::min<uint64_t>(kStageChunk, bytes - o);
-			cudaMemcpyAsync(pin + (i % kStageBufs) * kStageChunk, s.d_payload + o, len, cudaMemcpyDeviceToHost, st);
+			const uint64_t o = (uint64_t)i * CH; const size_t len = (size_t)std::min<uint64_t>(CH, bytes - o);
+			cudaMemcpyAsync(pin + (i % kStageBufs) * CH, s.d_payload + o, len, cudaMemcpyDeviceToHost, st);
 			cudaEventRecord(ev[i % kStageBufs], st);
 		};
 		for (size_t i = 0; i < std::min<size_t>(nch, kStageBufs - 1); i++) issue(i);
 		for (size_t i = 0; i < nch && rcs[d] == LFM_OK; i++) {
 			if (i + kStageBufs - 1 < nch) issue(i + kStageBufs - 1);       // its buffer was written out in the previous iteration
 			if (cudaEventSynchronize(ev[i % kStageBufs]) != cudaSuccess) { cudaGetLastError(); rcs[d] = LFM_ERR_CUDA; break; }
-			const uint64_t o = (uint64_t)i * kStageChunk; const size_t len = (size_t)std::min<uint64_t>(kStageChunk, bytes - o);
-			const uint8_t* buf = pin + (i % kStageBufs) * kStageChunk;
-			size_t done = 0;
-			while (done < len) {
-				const ssize_t w = pwrite(fd, buf + done, len - done, (off_t)(file_off + off[d] + o + done));
-				if (w <= 0) { rcs[d] = LFM_ERR_CREATE; break; }
-				done += (size_t)w;
-			}
+			const uint64_t o = (uint64_t)i * CH; const size_t len = (size_t)std::min<uint64_t>(CH, bytes - o);
+			rcs[d] = write_all(fd, pin + (i % kStageBufs) * CH, len, file_off + off[d] + o);     // (writes of one tmpfs file serialise on its inode lock: splitting them over threads was measured slower)
 		}
 		cudaStreamSynchronize(st);
 		for (auto& x : ev) cudaEventDestroy(x);
@@ -881,17 +923,6 @@ static int stream_payload_to_fd(std::vector<ShardOut>& shards, int fd, uint64_t 
 	g_stats.ms_d2h = now_ms() - t0;
 	g_stats.ms_total += g_stats.ms_d2h;
 	for (int rc : rcs) if (rc) return rc;
-	return LFM_OK;
-}
-
-static int write_all(int fd, const void* p, size_t n, uint64_t at)
-{
-	size_t done = 0;
-	while (done < n) {
-		const ssize_t w = pwrite(fd, (const uint8_t*)p + done, n - done, (off_t)(at + done));
-		if (w <= 0) return LFM_ERR_CREATE;
-		done += (size_t)w;
-	}
 	return LFM_OK;
 }
 
