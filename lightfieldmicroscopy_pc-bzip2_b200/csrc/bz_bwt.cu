@@ -26,7 +26,7 @@ extern __shared__ __align__(16) uint8_t bwt_smem[];
 template <int NT>
 __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 4)
 k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jobs, uint32_t njobs,
-      uint8_t* __restrict__ bwt_all, uint32_t* __restrict__ scratch_all, int text_in_smem)
+      uint8_t* __restrict__ bwt_all, uint32_t* __restrict__ scratch_all, int text_in_smem, int prefix_forced)
 {
 	constexpr int BWT_NT = NT;                       // shadows the namespace constant inside this kernel
 	uint32_t* wcnt = reinterpret_cast<uint32_t*>(bwt_smem);
@@ -66,9 +66,12 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 			if ((tid & 31) == 0) jobs[job].in_use[tid >> 5] = bal;
 		}
 
-		// ---- phase 1: 8 LSD passes over the 8-byte prefix (byte 7 first)
+		// ---- phase 1: LSD passes over the rotation prefix (last byte first).  Prefix length: every byte costs a full pass, every
+		// byte less leaves more ties to the doubling phase; measured on light-field residuals (uint16, high bytes mostly 0): 6 bytes
+		// win on 18 KB blocks (c2 stage 0.61 -> 0.51 ms; 5: 0.66, 4: 0.82), 8 bytes on 147 KB blocks (12.1 ms; 6: 12.6, 4: 30.8)
+		const int prefix = prefix_forced ? prefix_forced : (n <= 49152u ? 6 : 8);
 		uint32_t* src = nullptr; uint32_t* dst = scr + (size_t)S_SA0 * cap;
-		for (int p = 7; p >= 0; p--) {
+		for (int p = prefix - 1; p >= 0; p--) {
 			if (tid < 256) run[tid] = base[tid];
 			__syncthreads();
 			const uint32_t* s = src; uint32_t* d = dst;
@@ -79,7 +82,7 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 			src = dst;
 			dst = (dst == scr + (size_t)S_SA0 * cap) ? scr + (size_t)S_SA1 * cap : scr + (size_t)S_SA0 * cap;
 		}
-		uint32_t* sa = src;                               // sorted by 8-byte prefix
+		uint32_t* sa = src;                               // sorted by the prefix
 		uint32_t* isa = scr + (size_t)S_ISA * cap;
 
 		// ---- phase 2: group heads, ranks, unresolved set
@@ -87,12 +90,13 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 		uint32_t* Rk[2] = { scr + (size_t)S_R0 * cap, scr + (size_t)S_R1 * cap };
 		uint32_t* V[2] = { scr + (size_t)S_V0 * cap, scr + (size_t)S_V1 * cap };
 		uint32_t* U[2] = { scr + (size_t)S_U0 * cap, scr + (size_t)S_U1 * cap };
+		const uint64_t pmask = prefix >= 8 ? ~0ull : ((1ull << (8 * prefix)) - 1ull);
 		uint32_t m = split_groups<NT>(n, red,
-			[&](uint32_t j) -> uint64_t {                 // the 8-byte prefix of rotation sa[j]: three aligned words, shifted
+			[&](uint32_t j) -> uint64_t {                 // the sorted prefix of rotation sa[j]: three aligned words, shifted
 				const uint32_t idx = sa[j], sh = (idx & 3u) * 8u;
 				const uint32_t* tw = reinterpret_cast<const uint32_t*>(text + (idx & ~3u));
 				const uint32_t w0 = tw[0], w1 = tw[1], w2 = tw[2];
-				return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+				return (((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh)) & pmask;
 			},
 			[&](uint32_t j) { return j; },
 			[&](uint32_t j, uint32_t head, bool un, uint32_t slot) {
@@ -104,7 +108,7 @@ k_bwt(const uint8_t* __restrict__ txt_all, uint32_t cap, EncJob* __restrict__ jo
 		// ---- phase 3: prefix doubling on the unresolved set
 		const int npass = n <= (1u << 8) ? 1 : n <= (1u << 16) ? 2 : 3;
 		int cur = 0, ucur = 0;
-		uint64_t h = 8;
+		uint64_t h = (uint64_t)prefix;
 		while (m > 0 && h < n) {
 			uint32_t hh = (uint32_t)h;
 			for (uint32_t e = tid; e < m; e += BWT_NT) {
@@ -193,15 +197,16 @@ int bwt_ctas_per_sm(uint32_t cap, int text_in_smem)
 void launch_bwt(const uint8_t* txt, uint32_t cap, EncJob* jobs, uint32_t njobs, uint8_t* bwt, uint32_t* scratch,
                 int grid, int text_in_smem, cudaStream_t st)
 {
+	static const int prefix = getenv("LFM_B200_BWT_PREFIX") ? std::min(8, std::max(2, atoi(getenv("LFM_B200_BWT_PREFIX")))) : 0;      // 0: by block size
 	if (bwt_ctas_per_sm(cap, text_in_smem) == 4) {
 		const size_t smem = bwt_smem_bytes_nt(cap, text_in_smem, 256);
 		cudaFuncSetAttribute(k_bwt<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		k_bwt<256><<<grid, 256, smem, st>>>(txt, cap, jobs, njobs, bwt, scratch, text_in_smem);
+		k_bwt<256><<<grid, 256, smem, st>>>(txt, cap, jobs, njobs, bwt, scratch, text_in_smem, prefix);
 		return;
 	}
 	const size_t smem = bwt_smem_bytes_nt(cap, text_in_smem, 1024);
 	cudaFuncSetAttribute(k_bwt<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	k_bwt<1024><<<grid, 1024, smem, st>>>(txt, cap, jobs, njobs, bwt, scratch, text_in_smem);
+	k_bwt<1024><<<grid, 1024, smem, st>>>(txt, cap, jobs, njobs, bwt, scratch, text_in_smem, prefix);
 }
 
 }  // namespace lfm

@@ -1145,8 +1145,7 @@ __device__ __forceinline__ uint32_t unsymbolize16x2(uint32_t w)
 	return ((w >> 1) & 0x7FFF7FFFu) ^ ((w & 0x00010001u) * 0xFFFFu);      // per half: (s >> 1) ^ -(s & 1)
 }
 
-constexpr int SC_ROWS_NT = 256;
-template <bool SRC_OUT>
+template <bool SRC_OUT, int SC_ROWS_NT>
 __global__ void __launch_bounds__(SC_ROWS_NT)
 k_unscan_rows(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T, uint32_t z_start, uint32_t z_step,
               int rows_per_cta, int y_limit, int head_rule, int pitch)
@@ -1279,16 +1278,83 @@ k_unscan_cols(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int
 	}
 }
 
+// The column pass for whole frames with every load independent (the chain of k_unscan_cols waits a DRAM latency per batch of 12
+// rows: ncu 72 % long-scoreboard stalls, 13 warps per SM): CTA = 32 column quads x SEG warps, one v; warp s owns Q consecutive
+// tile rows of the chain, fetches its Q rows at once, sums them in registers, and the warps' totals are combined through shared
+// memory (two levels: no serial dependence between loads).  Chains longer than SEG * Q rows take further rounds with a carry.
+constexpr int SC_SEG = 16, SC_Q = 9;
+__global__ void __launch_bounds__(32 * SC_SEG)
+k_unscan_cols_seg(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, int T, uint32_t z_start, uint32_t z_step, int head_rule)
+{
+	__shared__ uint2 tot[SC_SEG][32];
+	const int lane = (int)threadIdx.x, s = (int)threadIdx.y;
+	const int x = 4 * (int)(blockIdx.x * 32 + lane);
+	const int v = (int)blockIdx.y;
+	const bool live = x < W;                                              // W is a multiple of 4 here
+	const uint32_t z = z_start + blockIdx.z * z_step;
+	const uint64_t fbase = (uint64_t)z * W * H;
+	const uint16_t* src = sym + fbase;
+	uint16_t* o = out + fbase;
+	const int NR = (H - v + T - 1) / T;                                   // rows of this chain: y = v + T i
+	uint2 carry = make_uint2(0u, 0u);
+	for (int r0 = 0; r0 < NR; r0 += SC_SEG * SC_Q) {
+		const int i0 = r0 + s * SC_Q;
+		uint2 val[SC_Q];
+		#pragma unroll
+		for (int j = 0; j < SC_Q; j++) {
+			const int i = i0 + j;
+			val[j] = make_uint2(0u, 0u);
+			if (live && i < NR) {
+				const size_t at = (size_t)(v + T * i) * W + x;
+				uint2 q = *reinterpret_cast<const uint2*>(src + at);
+				q.x = unsymbolize16x2(q.x); q.y = unsymbolize16x2(q.y);
+				if (i == 0 && head_rule) {                                    // heads that are already decoded (per half); row y = v < T
+					const uint2 ov = *reinterpret_cast<const uint2*>(o + at);
+					const bool h0 = head_rule == 2 || x < T, h1 = head_rule == 2 || x + 1 < T, h2 = head_rule == 2 || x + 2 < T, h3 = head_rule == 2 || x + 3 < T;
+					q.x = (h0 ? (ov.x & 0xffffu) : (q.x & 0xffffu)) | (h1 ? (ov.x & 0xffff0000u) : (q.x & 0xffff0000u));
+					q.y = (h2 ? (ov.y & 0xffffu) : (q.y & 0xffffu)) | (h3 ? (ov.y & 0xffff0000u) : (q.y & 0xffff0000u));
+				}
+				val[j] = q;
+			}
+		}
+		#pragma unroll
+		for (int j = 1; j < SC_Q; j++) { val[j].x = __vadd2(val[j].x, val[j - 1].x); val[j].y = __vadd2(val[j].y, val[j - 1].y); }
+		tot[s][lane] = val[SC_Q - 1];
+		__syncthreads();
+		uint2 before = carry, all = carry;
+		#pragma unroll
+		for (int k = 0; k < SC_SEG; k++) {
+			const uint2 t = tot[k][lane];
+			all.x = __vadd2(all.x, t.x); all.y = __vadd2(all.y, t.y);
+			if (k < s) { before.x = __vadd2(before.x, t.x); before.y = __vadd2(before.y, t.y); }
+		}
+		carry = all;
+		#pragma unroll
+		for (int j = 0; j < SC_Q; j++) {
+			const int i = i0 + j;
+			if (live && i < NR) {
+				const size_t at = (size_t)(v + T * i) * W + x;
+				*reinterpret_cast<uint2*>(o + at) = make_uint2(__vadd2(val[j].x, before.x), __vadd2(val[j].y, before.y));
+			}
+		}
+		__syncthreads();
+	}
+}
+
 // returns 0 ok, 1 launch error, 2 not applicable
 static int launch_unpredict_space_scans(const uint16_t* sym, uint16_t* out, int W, int H, int T, int k,
                                         uint32_t z_start, uint32_t z_step, uint32_t count, cudaStream_t st)
 {
 	if (k != 1 && k != 2 && k != 4) return 2;
 	const int vec = ((W & 3) == 0 && ((((uintptr_t)sym | (uintptr_t)out) & 7) == 0)) ? 4 : ((W & 1) == 0 && ((((uintptr_t)sym | (uintptr_t)out) & 3) == 0)) ? 2 : 1;
-	const int pitch = (W + 7) & ~7;
-	int R = std::min(16, (int)((48 * 1024) / ((size_t)pitch * 2)));
+	const int pitch = ((W + 7) & ~7) + 16;                               // +8 words: the rows of a CTA start in different banks (the chain threads of one step touch R rows)
+	// rows per CTA: R * T chain threads; small CTAs (R = 8, 128 threads) so that seven of them share an SM and the load, chain and
+	// store phases of different CTAs overlap (R = 16 / 256 threads: 4 per SM, ncu 45 % of the warp slots, DRAM latency exposed)
+	static const int r_forced = getenv("LFM_B200_SCAN_R") ? atoi(getenv("LFM_B200_SCAN_R")) : 0;
+	int R = std::min(r_forced > 0 ? r_forced : 8, (int)((48 * 1024) / ((size_t)pitch * 2)));
 	if (R < 1) return 2;                                                   // rows wider than 24 K pixels: the wavefront kernels
 	while (R > 1 && (uint64_t)((H + R - 1) / R) * count < 592) R >>= 1;     // enough CTAs for a single frame
+	const int rnt = R * T > 128 ? 256 : R * T > 64 ? 128 : 64;
 	const size_t rsmem = (size_t)R * pitch * 2;
 	const unsigned wpb = UF_NT / 32;
 	k_unpredict_seed<<<(count + wpb - 1) / wpb, UF_NT, 0, st>>>(sym, out, W, H, T, 2, k, z_start, z_step, count, 0);
@@ -1297,24 +1363,39 @@ static int launch_unpredict_space_scans(const uint16_t* sym, uint16_t* out, int 
 	const uint32_t group = (uint32_t)std::min<uint64_t>(65535, std::max<uint64_t>(1, ((uint64_t)64 << 20) / fbytes));
 	auto rows = [&](bool src_out, uint32_t zs, uint32_t n, int y_limit, int head) {
 		const dim3 grid((unsigned)((std::min(H, y_limit) + R - 1) / R), n);
-		if (src_out) k_unscan_rows<true><<<grid, SC_ROWS_NT, rsmem, st>>>(sym, out, W, H, T, zs, z_step, R, y_limit, head, pitch);
-		else k_unscan_rows<false><<<grid, SC_ROWS_NT, rsmem, st>>>(sym, out, W, H, T, zs, z_step, R, y_limit, head, pitch);
+		#define LFM_ROWS(SO, NT) k_unscan_rows<SO, NT><<<grid, NT, rsmem, st>>>(sym, out, W, H, T, zs, z_step, R, y_limit, head, pitch)
+		if (src_out) { if (rnt == 256) LFM_ROWS(true, 256); else if (rnt == 128) LFM_ROWS(true, 128); else LFM_ROWS(true, 64); }
+		else { if (rnt == 256) LFM_ROWS(false, 256); else if (rnt == 128) LFM_ROWS(false, 128); else LFM_ROWS(false, 64); }
+		#undef LFM_ROWS
 	};
 	auto cols = [&](uint32_t zs, uint32_t n, int x_limit, int head) {
 		const int xl = std::min(W, x_limit);
 		const int vc = x_limit >= W ? vec : 1;                              // the restricted pass stops at a column that need not be even
 		const int nthr = (xl + vc - 1) / vc;
 		const dim3 grid((unsigned)((nthr + SC_COLS_NT - 1) / SC_COLS_NT), (unsigned)std::min(T, H), n);
-		if (vc == 4) k_unscan_cols<false, 4><<<grid, SC_COLS_NT, 0, st>>>(sym, out, W, H, T, zs, z_step, x_limit, head);
+		static const int seg_on = getenv("LFM_B200_SCAN_SEG") ? atoi(getenv("LFM_B200_SCAN_SEG")) : 1;
+		if (vc == 4 && seg_on) {
+			const dim3 g2((unsigned)((W / 4 + 31) / 32), (unsigned)std::min(T, H), n);
+			k_unscan_cols_seg<<<g2, dim3(32, SC_SEG), 0, st>>>(sym, out, W, H, T, zs, z_step, head);
+		}
+		else if (vc == 4) k_unscan_cols<false, 4><<<grid, SC_COLS_NT, 0, st>>>(sym, out, W, H, T, zs, z_step, x_limit, head);
 		else if (vc == 2) k_unscan_cols<false, 2><<<grid, SC_COLS_NT, 0, st>>>(sym, out, W, H, T, zs, z_step, x_limit, head);
 		else k_unscan_cols<false, 1><<<grid, SC_COLS_NT, 0, st>>>(sym, out, W, H, T, zs, z_step, x_limit, head);
 	};
 	const int ALL = 0x7fffffff;
-	for (uint32_t f0 = 0; f0 < count; f0 += group) {
-		const uint32_t n = std::min(group, count - f0), zs = z_start + f0 * z_step;
-		if (k == 4) { cols(zs, n, ALL, 1); rows(true, zs, n, ALL, 0); }
-		else if (k == 1) { cols(zs, n, T, 1); rows(false, zs, n, ALL, 2); }
-		else { rows(false, zs, n, T, 1); cols(zs, n, ALL, 2); }
+	if (k == 4) {
+		for (uint32_t f0 = 0; f0 < count; f0 += group) {
+			const uint32_t n = std::min(group, count - f0), zs = z_start + f0 * z_step;
+			cols(zs, n, ALL, 1); rows(true, zs, n, ALL, 0);
+		}
+	} else {
+		// one restricted pass (first tile column / row: a short latency-bound launch, so ONE launch for all frames), then one
+		// full pass straight from the symbols: nothing to keep in L2 between them
+		for (uint32_t f0 = 0; f0 < count; f0 += 65535u) {
+			const uint32_t n = std::min(65535u, count - f0), zs = z_start + f0 * z_step;
+			if (k == 1) { cols(zs, n, T, 1); rows(false, zs, n, ALL, 2); }
+			else { rows(false, zs, n, T, 1); cols(zs, n, ALL, 2); }
+		}
 	}
 	return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
