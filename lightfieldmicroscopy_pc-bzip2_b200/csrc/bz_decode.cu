@@ -206,10 +206,11 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 		for (int i = 0; i < 24; i++) { base[i] = 0; limit[i] = 0; }
 		for (int i = 0; i < alpha; i++) { int l = S.len[t][i]; mx = l > mx ? l : mx; mn = l < mn ? l : mn; base[l + 1]++; }
 		for (int i = 1; i < 23; i++) base[i] += base[i - 1];
-		{
-			int32_t nxt[24];
-			for (int i = 0; i < 24; i++) nxt[i] = base[i];
-			for (int i = 0; i < alpha; i++) { int l = S.len[t][i]; S.perm[t][nxt[l]++] = (uint16_t)i; }
+		{   // counting sort by length; the running positions live in limit[] (shared memory, filled in below) instead of a
+			// thread-local array indexed by the length (local memory, or a chain of 24 selects per access)
+			for (int i = 0; i < 24; i++) limit[i] = base[i];
+			for (int i = 0; i < alpha; i++) { int l = S.len[t][i]; S.perm[t][limit[l]++] = (uint16_t)i; }
+			for (int i = 0; i < 24; i++) limit[i] = 0;
 		}
 		// lookup: symbols in (length, symbol) order own consecutive, left-to-right ranges of the DEC_LB-bit code space
 		{
