@@ -317,6 +317,7 @@ def main():
         fname = obj[0]
     hout = np.empty_like(pool[0])                     # pageable
     e2e = dict(tc=0.0, td=0.0, h2d=0, d2h=0, file=0)
+    trace = []
     lb = L._u32x5(0, 0, rank * nfr, 0, 0); ub = L._u32x5(W - 1, H - 1, (rank + 1) * nfr - 1, 0, 0)
     hdr_bytes = 320 + 8 * nb * world
 
@@ -339,13 +340,19 @@ def main():
                 d0 = torch.from_numpy(a[0].view(np.int16)).cuda() if rank == 0 else None
                 hv_i = video | (8 + agree_on_predictor(d0.data_ptr() if rank == 0 else 0))
             stored, sizes, npay = L.shard_compress(a, hv_i, nnum=nnum, block_size=(96, 96, bdepth, 1, 1))
+            ta = time.perf_counter()
             block_offset = exchange_sizes(np.cumsum(sizes.astype(np.int64)))
+            tb = time.perf_counter()
             if rank == 0:
                 L.write_header(fname, (W, H, nfr * world, 1, 1), (96, 96, bdepth, 1, 1), stored, nnum, block_offset)
+            tc = time.perf_counter()
             L.shard_write_payload(fname, hdr_bytes + (int(block_offset[rank * nb - 1]) if rank else 0))
+            td = time.perf_counter()
             dist.barrier()                             # the file is complete
             torch.cuda.synchronize()
             t1 = time.perf_counter()
+            if timed and os.environ.get("LFM_BENCH_TRACE"):
+                trace.append((ta - t0, tb - ta, tc - tb, td - tc, t1 - td))
             rc = L.lib.readKLBroiInPlace(os.fsencode(fname), hout.ctypes.data, lb, ub, -1)
             assert rc == 0, "readKLBroiInPlace rc=%d" % rc
             t2 = time.perf_counter()
@@ -375,6 +382,9 @@ def main():
     for i in range(args.steps):
         step_e2e(2 + i, True)
     barrier(); t_e2e = time.perf_counter() - te0
+    if trace:                                              # LFM_BENCH_TRACE=1: where the sharded write spends its time, per rank (stderr)
+        m = np.mean(np.array(trace), axis=0) * 1e3
+        sys.stderr.write("rank %d e2e write: shard_compress %.3f | size exchange %.3f | header %.3f | payload -> file %.3f | barrier %.3f ms\n" % ((rank,) + tuple(m)))
     if rank == 0 and os.path.exists(fname):
         os.remove(fname)
 

@@ -15,6 +15,7 @@
 #include <fcntl.h>
 #include <unistd.h>
 #include <sys/stat.h>
+#include <sys/mman.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -898,6 +899,20 @@ static int stream_payload_to_fd(std::vector<ShardOut>& shards, int fd, uint64_t 
 		for (auto& x : ev) cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
 		const uint64_t bytes = s.payload_bytes;
 		const size_t CH = kStageChunk;
+		// destination: a shared mapping of this shard's byte range when the file allows it.  write() / pwrite() of one file serialise
+		// on its inode lock (ranks and threads that write disjoint ranges of ONE .lfm file queue up: measured 0.39 -> 1.0 ms per
+		// 4 MB payload with two ranks); stores through a mapping do not, and the copy is split over the pool.
+		static const int mmap_on = env_int("LFM_B200_MMAP_WRITE", 1);
+		const uint64_t fbeg = file_off + off[d], fend = fbeg + bytes;
+		const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE), mbase = fbeg & ~(page - 1);
+		uint8_t* map = nullptr;
+		if (mmap_on && bytes >= ((uint64_t)256 << 10)) {
+			struct stat sb;
+			if (fstat(fd, &sb) == 0 && ((uint64_t)sb.st_size >= fend || posix_fallocate(fd, sb.st_size, (off_t)(fend - (uint64_t)sb.st_size)) == 0)) {
+				void* m = mmap(nullptr, (size_t)(fend - mbase), PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)mbase);
+				if (m != MAP_FAILED) map = (uint8_t*)m;
+			}
+		}
 		const size_t nch = (size_t)((bytes + CH - 1) / CH);
 		auto issue = [&](size_t i) {
 			const uint64_t o = (uint64_t)i * CH; const size_t len = (size_t)std::min<uint64_t>(CH, bytes - o);
@@ -909,8 +924,10 @@ static int stream_payload_to_fd(std::vector<ShardOut>& shards, int fd, uint64_t 
 			if (i + kStageBufs - 1 < nch) issue(i + kStageBufs - 1);       // its buffer was written out in the previous iteration
 			if (cudaEventSynchronize(ev[i % kStageBufs]) != cudaSuccess) { cudaGetLastError(); rcs[d] = LFM_ERR_CUDA; break; }
 			const uint64_t o = (uint64_t)i * CH; const size_t len = (size_t)std::min<uint64_t>(CH, bytes - o);
-			rcs[d] = write_all(fd, pin + (i % kStageBufs) * CH, len, file_off + off[d] + o);     // (writes of one tmpfs file serialise on its inode lock: splitting them over threads was measured slower)
+			if (map) par_memcpy(map + (fbeg - mbase) + o, pin + (i % kStageBufs) * CH, len);
+			else rcs[d] = write_all(fd, pin + (i % kStageBufs) * CH, len, fbeg + o);
 		}
+		if (map) munmap(map, (size_t)(fend - mbase));
 		cudaStreamSynchronize(st);
 		for (auto& x : ev) cudaEventDestroy(x);
 	};
@@ -941,7 +958,7 @@ static int write_stack_to_file(const std::string& filename, const FrameSource& s
 	LFM_API_LOCK();
 	// the file is overwritten in place and cut to its final size at the end (same result as "wb", but an existing file of about
 	// the same size keeps its pages: rewriting a stack does not pay for page allocation again)
-	const int fd = open(filename.c_str(), O_WRONLY | O_CREAT, 0666);
+	const int fd = open(filename.c_str(), O_RDWR | O_CREAT, 0666);
 	if (fd < 0) { std::cout << "ERROR: file " << filename << " could not be opened" << std::endl; return LFM_ERR_CREATE; }
 	int rc;
 	try {
@@ -1267,7 +1284,7 @@ int lfmShardWritePayload(const char* filename, uint64_t file_offset)
 try {
 	LFM_API_LOCK();
 	if (!filename || !*filename) return LFM_ERR_OPEN;
-	const int fd = open(filename, O_WRONLY | O_CREAT, 0666);      // no truncation: ranks write their ranges in any order
+	const int fd = open(filename, O_RDWR | O_CREAT, 0666);        // no truncation: ranks write their ranges in any order (O_RDWR: the range is mapped)
 	if (fd < 0) return LFM_ERR_CREATE;
 	int rc = stream_payload_to_fd(g_pending, fd, file_offset);
 	if (close(fd) != 0 && rc == 0) rc = LFM_ERR_CREATE;
