@@ -409,6 +409,30 @@ def main():
             else:
                 e2m["tc"] += t1 - t0; e2m["td"] += t2 - t1
 
+    # ---- the same stack with the predictor chosen by the 2-D entropy rule on frame 0 (headerVersion 0: SURVEY.md 8d asks for C2 both
+    # fixed and auto): device resident, a few steps, N = 1 only
+    auto_leg = None
+    if world == 1 and not auto:
+        ta = dict(tc=0.0, td=0.0, sel=0.0, k=-1)
+        nst = max(3, min(args.steps, 10))
+        for i in range(2 + nst):
+            d = dpool[i % POOL]
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            rc = L.lib.lfmCompressDevice(d.data_ptr(), xyzct, bsp, video, nnum, C.byref(shv), off.ctypes.data, nb, C.byref(dp), C.byref(pb))
+            assert rc == 0, "lfmCompressDevice (auto) rc=%d" % rc
+            t1 = time.perf_counter()
+            sc = L.stats()
+            rc = L.lib.lfmDecompressDevice(dp, off.ctypes.data, nb, xyzct, bsp, shv.value, nnum, dout.data_ptr())
+            torch.cuda.synchronize(); t2 = time.perf_counter()
+            assert rc == 0, "lfmDecompressDevice (auto) rc=%d" % rc
+            if i < 2:
+                assert torch.equal(dout, d), "auto-select round trip mismatch"
+            else:
+                ta["tc"] += t1 - t0; ta["td"] += t2 - t1; ta["sel"] += sc.ms_select; ta["k"] = sc.predictor
+        auto_leg = {"value": raw * nst / (ta["tc"] + ta["td"]) / 1e9, "unit": "GB/s", "steps": nst, "ms_per_step": (ta["tc"] + ta["td"]) / nst * 1e3,
+                    "ms_select": ta["sel"] / nst, "selected_predictor": ta["k"], "headerVersion": int(video),
+                    "note": "same frames, predictor picked per stack by the 2-D entropy rule (7 candidate predictions + 8 entropy estimates on frame 0)"}
+
     # ---- predictor kernels alone (the HBM-bound stage the north star quotes a roofline target for): forward and inverse
     # on a 32-frame 2048x2048 stack (268 MB, larger than L2), algorithmic traffic 4 B/px, timed by CUDA events on the
     # engine stream inside lfmDebugPredictDevice.  Rank 0 only.
@@ -494,6 +518,8 @@ def main():
                              "note": "the block codec (sort, entropy coding) is latency / shared-memory bound, not HBM bound: the HBM roofline is quoted as the contract asks; the HBM-bound kernels of the path are the predictors, see predictor_roofline"},
                 "predictor_roofline": None if pred_roof is None else dict(pred_roof, peak=peak, unit="GB/s",
                     frac={k: v["achieved_gbs"] / peak for k, v in pred_roof.get("runs", {}).items()})}
+        if auto_leg is not None:
+            line["auto_select"] = auto_leg
         if e2m is not None:
             line["e2e_memory"] = {"value": raw * args.steps / (e2m["tc"] + e2m["td"]) / 1e9, "unit": "GB/s", "api": "lfmCompressToBuffer + lfmDecompressFromMemory, pinned host buffers, no file",
                                   "compress_gbs": raw * args.steps / e2m["tc"] / 1e9, "decompress_gbs": raw * args.steps / e2m["td"] / 1e9}

@@ -9,6 +9,7 @@
 // The integer part is exact; the per-bin terms are fp32 like the reference, summed in a fixed order in fp64
 // (the reference's fp32 thrust::reduce order is unspecified).
 #include "lfm_radix.cuh"
+#include <cstdlib>
 
 namespace lfm {
 
@@ -130,6 +131,118 @@ k_select_entropy(const uint32_t* __restrict__ hist_all, uint64_t fpx, uint32_t c
 	if (threadIdx.x == 0) e_out[cc] = (float)part[0];
 }
 
+// ---- the same pair histogram WITHOUT the sort.  The stably sorted value list is, bucket after bucket, the values val(j) = b[j-1]
+// of the positions j that hold key b[j] = c, in position order.  So its adjacent pairs are
+//   (val(j), val(next(j)))   for every position j that has a later position next(j) with the same key, and
+//   (val(last position of c), val(first position of c'))   for consecutive non-empty buckets c < c',
+// and "the next position with the same key" needs no sort:
+//   k_select_next   one warp per segment of SN_SEG positions walks it BACKWARD 32 positions at a time with a 256-entry table of the
+//                   nearest later value per key (match.any finds the pairs inside a group of 32), counts the pairs it can close, and
+//                   leaves, per key, the value at its first and at its last position of the segment;
+//   k_select_link   one thread per key chains the segments (last of one -> first of the next one that holds the key) and one
+//                   thread closes the bucket boundaries.
+// Integer result identical to the sorted formulation (tests: entropies and winners against the reference's, file bytes).
+constexpr uint32_t SN_SEG = 2048;                 // positions per warp
+constexpr int SN_WARPS = 8;
+constexpr uint16_t SN_NONE = 0xFFFFu;
+__global__ void __launch_bounds__(32 * SN_WARPS)
+k_select_next(CandPtrs cands, uint64_t fpx, uint32_t chunk_px, uint32_t nchunks, uint16_t* __restrict__ tabs_all, uint32_t tstride,
+              uint32_t* __restrict__ hist_all)
+{
+	__shared__ uint16_t tab_s[SN_WARPS][256];
+	__shared__ __align__(16) uint8_t seg_s[SN_WARPS][16 + SN_SEG];                  // bytes j0 - 1 .. j1 - 1 of the segment at offset 15 ..
+	const uint32_t lane = lane_id(), w = warp_id();
+	const uint32_t chunk = blockIdx.y, cand = blockIdx.z, cc = cand * nchunks + chunk;
+	const uint64_t px0 = (uint64_t)chunk * chunk_px;
+	const uint32_t n = (uint32_t)(min((uint64_t)chunk_px, fpx - px0) * 2);          // positions 0 .. n (n + 1 of them)
+	const uint32_t seg = blockIdx.x * SN_WARPS + w, nseg = (n + 1 + SN_SEG - 1) / SN_SEG;
+	if (seg >= nseg) return;
+	const uint8_t* b = reinterpret_cast<const uint8_t*>(cands.p[cand] + px0);
+	uint32_t* hist = hist_all + (size_t)cc * 65536;
+	uint16_t* first = tabs_all + (size_t)cc * tstride + (size_t)seg * 512, * last = first + 256;
+	uint16_t* tab = tab_s[w];
+	for (uint32_t i = lane; i < 256; i += 32) { tab[i] = SN_NONE; last[i] = SN_NONE; }
+	__syncwarp();
+	const uint32_t j0 = seg * SN_SEG, j1 = min(n + 1, j0 + SN_SEG);
+	// the segment's bytes once, coalesced (a group of 32 positions per iteration would pay a DRAM latency per iteration)
+	uint8_t* sb = seg_s[w] + 16;                                                     // sb[i] = b[j0 + i], sb[-1] = b[j0 - 1]
+	for (uint32_t q = lane * 16; q < SN_SEG; q += 32 * 16) {
+		uint4 v = make_uint4(0u, 0u, 0u, 0u);
+		if (j0 + q + 16 <= n && (reinterpret_cast<uintptr_t>(b + j0 + q) & 15u) == 0u) v = *reinterpret_cast<const uint4*>(b + j0 + q);   // (frames of odd sizes are not 16-byte aligned)
+		else { uint32_t wv[4] = { 0u, 0u, 0u, 0u }; for (int k = 0; k < 16; k++) if (j0 + q + k < n) wv[k >> 2] |= (uint32_t)b[j0 + q + k] << (8 * (k & 3)); v = make_uint4(wv[0], wv[1], wv[2], wv[3]); }
+		*reinterpret_cast<uint4*>(sb + q) = v;
+	}
+	if (lane == 0) sb[-1] = j0 ? b[j0 - 1] : (uint8_t)0;
+	__syncwarp();
+	const uint32_t lt_incl = (2u << lane) - 1u;                                      // lanes <= this one (lane 31: all)
+	for (uint32_t g1 = j1; g1 > j0; ) {                                              // groups of 32 positions, last group first
+		const uint32_t g0 = g1 - j0 > 32u ? g1 - 32u : j0;
+		// group [g0, g1): lane l holds position g0 + l; the first (partial) group of a segment is aligned at its START
+		const uint32_t j = g0 + lane;
+		const bool act = j < g1;
+		const uint32_t am = __ballot_sync(0xffffffffu, act);
+		uint32_t key = 0, val = 0;
+		if (act) { key = sb[(int)(j - j0)]; val = sb[(int)(j - j0) - 1]; }             // position n holds key 0 (staged as 0), b[-1] = 0
+		if (act) {
+			const uint32_t peers = __match_any_sync(am, key);
+			const uint32_t higher = peers & ~lt_incl;
+			const uint32_t partner = higher ? (uint32_t)__ffs((int)higher) - 1u : lane;
+			uint32_t pv = __shfl_sync(am, val, partner);
+			bool has = higher != 0u;
+			if (!has) { const uint32_t t = tab[key]; has = t != SN_NONE; pv = t; if (!has) last[key] = (uint16_t)val; }   // no later position in the segment: its last one
+			const uint32_t hm = __ballot_sync(am, has);
+			if (has) {
+				const uint32_t k2 = (val << 8) | pv;
+				const uint32_t same = __match_any_sync(hm, k2);
+				if (lane == (uint32_t)(__ffs((int)same) - 1)) atomicAdd(&hist[k2], (uint32_t)__popc(same));
+			}
+			__syncwarp(am);
+			if ((peers & (lt_incl >> 1)) == 0u) tab[key] = (uint16_t)val;               // first position of the key in the group: the nearest later one for what comes before
+		}
+		__syncwarp();
+		g1 = g0;
+	}
+	for (uint32_t i = lane; i < 256; i += 32) first[i] = tab[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_select_link(const uint16_t* __restrict__ tabs_all, uint32_t tstride, uint64_t fpx, uint32_t chunk_px, uint32_t nchunks,
+              uint32_t* __restrict__ hist_all)
+{
+	__shared__ uint16_t first_all[256], last_all[256];
+	const uint32_t cc = blockIdx.x, chunk = cc % nchunks, c = threadIdx.x;
+	const uint64_t px0 = (uint64_t)chunk * chunk_px;
+	const uint32_t n = (uint32_t)(min((uint64_t)chunk_px, fpx - px0) * 2);
+	const uint32_t nseg = (n + 1 + SN_SEG - 1) / SN_SEG;
+	const uint16_t* tabs = tabs_all + (size_t)cc * tstride;
+	uint32_t* hist = hist_all + (size_t)cc * 65536;
+	uint32_t carry = SN_NONE, f0 = SN_NONE;
+	for (uint32_t s0 = 0; s0 < nseg; s0 += 16) {                                     // sixteen segments' entries in flight
+		uint32_t f[16], l[16];
+		#pragma unroll
+		for (int k = 0; k < 16; k++) {
+			const uint32_t sg = s0 + k;
+			f[k] = sg < nseg ? tabs[(size_t)sg * 512 + c] : (uint32_t)SN_NONE;
+			l[k] = sg < nseg ? tabs[(size_t)sg * 512 + 256 + c] : (uint32_t)SN_NONE;
+		}
+		#pragma unroll
+		for (int k = 0; k < 16; k++) if (f[k] != SN_NONE) {
+			if (carry != SN_NONE) atomicAdd(&hist[(carry << 8) | f[k]], 1u);
+			else f0 = f[k];
+			carry = l[k];
+		}
+	}
+	first_all[c] = (uint16_t)f0; last_all[c] = (uint16_t)carry;
+	__syncthreads();
+	if (c == 0) {                                                                    // bucket boundaries
+		uint32_t prev = SN_NONE;
+		for (int k = 0; k < 256; k++) if (first_all[k] != SN_NONE) {
+			if (prev != SN_NONE) atomicAdd(&hist[(prev << 8) | first_all[k]], 1u);
+			prev = last_all[k];
+		}
+	}
+}
+
 // sorted: ncand*nchunks*sstride bytes; hist: ncand*nchunks*65536 uint32 (zeroed here); e_out: ncand*nchunks floats;
 // scratch: select_scratch_words() uint32
 size_t select_scratch_words(int ncand, uint32_t nchunks) { return (size_t)ncand * nchunks * SEL_P * 256; }
@@ -139,10 +252,18 @@ void launch_select(const uint16_t* const cand_ptrs[8], int ncand, uint64_t fpx, 
 	CandPtrs cp;
 	for (int i = 0; i < 8; i++) cp.p[i] = cand_ptrs[i < ncand ? i : 0];
 	cudaMemsetAsync(hist, 0, (size_t)ncand * nchunks * 65536 * sizeof(uint32_t), st);
-	k_select_count<<<dim3(SEL_P, nchunks, ncand), BWT_NT, 0, st>>>(cp, fpx, chunk_px, nchunks, scratch);
-	k_select_starts<<<ncand * nchunks, 256, 0, st>>>(scratch);
-	k_select_sort<<<dim3(SEL_P, nchunks, ncand), BWT_NT, 0, st>>>(cp, fpx, chunk_px, nchunks, sorted, sstride, scratch);
-	k_select_hist<<<dim3(32, ncand * nchunks), SH_NT, 0, st>>>(sorted, sstride, fpx, chunk_px, nchunks, hist);
+	static const int sorted_path = getenv("LFM_B200_SELECT_SORT") ? atoi(getenv("LFM_B200_SELECT_SORT")) : 0;
+	const uint32_t max_seg = (chunk_px * 2 + 1 + SN_SEG - 1) / SN_SEG;
+	if (!sorted_path && (size_t)max_seg * 1024 <= (size_t)sstride) {                   // the segment tables live in the (unused) sort buffer
+		const uint32_t tstride = sstride / 2;                                           // uint16 elements per (candidate, chunk)
+		k_select_next<<<dim3((max_seg + SN_WARPS - 1) / SN_WARPS, nchunks, ncand), 32 * SN_WARPS, 0, st>>>(cp, fpx, chunk_px, nchunks, reinterpret_cast<uint16_t*>(sorted), tstride, hist);
+		k_select_link<<<ncand * nchunks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(sorted), tstride, fpx, chunk_px, nchunks, hist);
+	} else {
+		k_select_count<<<dim3(SEL_P, nchunks, ncand), BWT_NT, 0, st>>>(cp, fpx, chunk_px, nchunks, scratch);
+		k_select_starts<<<ncand * nchunks, 256, 0, st>>>(scratch);
+		k_select_sort<<<dim3(SEL_P, nchunks, ncand), BWT_NT, 0, st>>>(cp, fpx, chunk_px, nchunks, sorted, sstride, scratch);
+		k_select_hist<<<dim3(32, ncand * nchunks), SH_NT, 0, st>>>(sorted, sstride, fpx, chunk_px, nchunks, hist);
+	}
 	k_select_entropy<<<ncand * nchunks, SE_NT, 0, st>>>(hist, fpx, chunk_px, nchunks, e_out);
 }
 
