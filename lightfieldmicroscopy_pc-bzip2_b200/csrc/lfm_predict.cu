@@ -17,7 +17,36 @@
 
 namespace cg = cooperative_groups;
 
+#include <cuda.h>                                   // CUtensorMap (type and enums only: the encoder is fetched through the runtime)
+
 namespace lfm {
+
+// ---- TMA staging of the forward predictor's tile (cp.async.bulk.tensor: ONE thread issues the copy of the whole tile + halo box,
+// out-of-image parts are zero-filled by the copy engine, completion on an mbarrier) -----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");              // the init is visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+{
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+	             :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	uint32_t done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	} while (!done);
+}
+
 
 constexpr int PF_NT = 256;
 
@@ -99,7 +128,7 @@ __global__ void __launch_bounds__(PF_NT)
 k_predict_fwd(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int W, int H, int T, int video,
               uint32_t z0, int band, int hw)
 {
-	extern __shared__ __align__(16) uint8_t pf_smem[];
+	extern __shared__ __align__(128) uint8_t pf_smem[];
 	uint16_t* sm = reinterpret_cast<uint16_t*>(pf_smem);
 	const int tid = (int)threadIdx.x;
 	const int cols = PF_NT - hw;                                 // output columns per CTA
@@ -180,9 +209,10 @@ constexpr int PF2_NT = PF_NT / 2;
 template <int WAY, int K>
 __global__ void __launch_bounds__(PF2_NT)
 k_predict_fwd2(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int W, int H, int T, int video,
-               uint32_t z0, int band, int hw)
+               uint32_t z0, int band, int hw, const __grid_constant__ CUtensorMap tmap, int use_tma)
 {
-	extern __shared__ __align__(16) uint8_t pf_smem[];
+	extern __shared__ __align__(128) uint8_t pf_smem[];
+	__shared__ __align__(8) uint64_t tile_bar;
 	uint16_t* sm = reinterpret_cast<uint16_t*>(pf_smem);
 	const int tid = (int)threadIdx.x;
 	const int cols = PF_NT - hw;                                 // output columns per CTA
@@ -194,7 +224,16 @@ k_predict_fwd2(const uint16_t* __restrict__ img, uint16_t* __restrict__ sym, int
 	const int ys = y0 - (T + 1), xs = x0 - hw;                   // image coordinates of smem element (0, 0); may be negative
 	const int yc = max(0, ys);
 	const int nrows = y1 - yc;
-	{
+	if (use_tma) {
+		// the box of PF_PITCH columns x (band + T + 1) rows at image coordinates (xs, ys) of frame blockIdx.z of this launch
+		if (tid == 0) mbar_init(&tile_bar, 1);
+		__syncthreads();
+		if (tid == 0) {
+			mbar_expect_tx(&tile_bar, (uint32_t)((band + T + 1) * PF_PITCH * 2));
+			tma_load_3d(sm, &tmap, &tile_bar, xs, ys, (int)blockIdx.z);
+		}
+		mbar_wait(&tile_bar, 0);
+	} else {
 		const int cv = tid & 31, rr = tid >> 5;                    // 16-byte column cv (of 32) of rows rr, rr+4, ...
 		const int xv = xs + cv * 8;
 		if (xv >= 0 && xv < W) {
@@ -1447,6 +1486,20 @@ static int launch_unpredict_bands(const uint16_t* sym, uint16_t* out, int W, int
 	return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder()
+{
+	static const TensorMapEncodeFn fn = [] {
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+		return (TensorMapEncodeFn)p;
+	}();
+	return fn;
+}
+
 template <int WAY, int K>
 static void launch_predict_fwd_wk(const uint16_t* img, uint16_t* sym, int W, int H, int T, int video, uint32_t z0, uint32_t nz,
                                   cudaStream_t st)
@@ -1463,10 +1516,25 @@ static void launch_predict_fwd_wk(const uint16_t* img, uint16_t* sym, int W, int
 	const size_t smem = (size_t)(band + T + 1) * PF_PITCH * 2;
 	if (pairs) cudaFuncSetAttribute(k_predict_fwd2<WAY, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	else if (tile) cudaFuncSetAttribute(k_predict_fwd<WAY, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	static const int tma_on = getenv("LFM_B200_TMA") ? atoi(getenv("LFM_B200_TMA")) : 1;
 	for (uint32_t zb = 0; zb < nz; zb += 65535) {            // gridDim.z limit
 		const uint32_t cz = std::min<uint32_t>(65535, nz - zb);
 		dim3 grid((unsigned)colchunks, (unsigned)((H + band - 1) / band), cz);
-		if (pairs) k_predict_fwd2<WAY, K><<<grid, PF2_NT, smem, st>>>(img, sym, W, H, T, video, z0 + zb, band, hw);
+		if (pairs) {
+			// tensor map of the cz frames of this launch: uint16 [cz][H][W], box = one tile + halo
+			CUtensorMap tmap; memset(&tmap, 0, sizeof(tmap));
+			int use_tma = 0;
+			if (tma_on && tensor_map_encoder()) {
+				const cuuint64_t gdim[3] = { (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)cz };
+				const cuuint64_t gstr[2] = { (cuuint64_t)W * 2, (cuuint64_t)W * H * 2 };
+				const cuuint32_t box[3] = { (cuuint32_t)PF_PITCH, (cuuint32_t)(band + T + 1), 1u };
+				const cuuint32_t estr[3] = { 1u, 1u, 1u };
+				void* base = const_cast<uint16_t*>(img + (uint64_t)(z0 + zb) * W * H);
+				use_tma = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+				                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+			}
+			k_predict_fwd2<WAY, K><<<grid, PF2_NT, smem, st>>>(img, sym, W, H, T, video, z0 + zb, band, hw, tmap, use_tma);
+		}
 		else if (tile) k_predict_fwd<WAY, K><<<grid, PF_NT, smem, st>>>(img, sym, W, H, T, video, z0 + zb, band, hw);
 		else k_predict_fwd_rows<WAY, K><<<grid, PF_NT, 0, st>>>(img, sym, W, H, T, video, z0 + zb, band);   // huge Nnum
 	}
