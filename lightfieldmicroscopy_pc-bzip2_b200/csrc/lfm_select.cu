@@ -142,67 +142,83 @@ k_select_entropy(const uint32_t* __restrict__ hist_all, uint64_t fpx, uint32_t c
 //   k_select_link   one thread per key chains the segments (last of one -> first of the next one that holds the key) and one
 //                   thread closes the bucket boundaries.
 // Integer result identical to the sorted formulation (tests: entropies and winners against the reference's, file bytes).
-constexpr uint32_t SN_SEG = 2048;                 // positions per warp
+constexpr uint32_t SN_SEG = 2048;                 // positions per warp and round
 constexpr int SN_WARPS = 8;
+constexpr int SN_PARTS = 8;                       // CTAs per (candidate, chunk): each walks every SN_PARTS-th group of SN_WARPS segments
+constexpr uint32_t SN_HOT = 32;                   // pairs whose first byte is below this are counted in shared memory
 constexpr uint16_t SN_NONE = 0xFFFFu;
+// ncu of the first version (one match.any for the key, one to aggregate equal pairs before the global atomic): MIO bound, 24 % of
+// the issue slots.  Now the key peers come from eight ballots, and the pairs whose first byte is small -- high bytes and small
+// residuals: most of them, and the ones that would contend for the same global counter -- go to a 32 x 256 shared-memory
+// histogram that the CTA adds to the global one once, after ~55 segments; the others are spread over 57 K counters.
 __global__ void __launch_bounds__(32 * SN_WARPS)
 k_select_next(CandPtrs cands, uint64_t fpx, uint32_t chunk_px, uint32_t nchunks, uint16_t* __restrict__ tabs_all, uint32_t tstride,
               uint32_t* __restrict__ hist_all)
 {
-	__shared__ uint16_t tab_s[SN_WARPS][256];
-	__shared__ __align__(16) uint8_t seg_s[SN_WARPS][16 + SN_SEG];                  // bytes j0 - 1 .. j1 - 1 of the segment at offset 15 ..
+	extern __shared__ __align__(16) uint8_t sn_smem[];
+	uint32_t* hot = reinterpret_cast<uint32_t*>(sn_smem);                            // [SN_HOT][256]
+	uint16_t (*tab_s)[256] = reinterpret_cast<uint16_t (*)[256]>(sn_smem + SN_HOT * 256 * 4);
+	uint8_t (*seg_s)[16 + SN_SEG] = reinterpret_cast<uint8_t (*)[16 + SN_SEG]>(sn_smem + SN_HOT * 256 * 4 + SN_WARPS * 256 * 2);
 	const uint32_t lane = lane_id(), w = warp_id();
 	const uint32_t chunk = blockIdx.y, cand = blockIdx.z, cc = cand * nchunks + chunk;
 	const uint64_t px0 = (uint64_t)chunk * chunk_px;
 	const uint32_t n = (uint32_t)(min((uint64_t)chunk_px, fpx - px0) * 2);          // positions 0 .. n (n + 1 of them)
-	const uint32_t seg = blockIdx.x * SN_WARPS + w, nseg = (n + 1 + SN_SEG - 1) / SN_SEG;
-	if (seg >= nseg) return;
+	const uint32_t nseg = (n + 1 + SN_SEG - 1) / SN_SEG;
 	const uint8_t* b = reinterpret_cast<const uint8_t*>(cands.p[cand] + px0);
 	uint32_t* hist = hist_all + (size_t)cc * 65536;
-	uint16_t* first = tabs_all + (size_t)cc * tstride + (size_t)seg * 512, * last = first + 256;
 	uint16_t* tab = tab_s[w];
-	for (uint32_t i = lane; i < 256; i += 32) { tab[i] = SN_NONE; last[i] = SN_NONE; }
-	__syncwarp();
-	const uint32_t j0 = seg * SN_SEG, j1 = min(n + 1, j0 + SN_SEG);
-	// the segment's bytes once, coalesced (a group of 32 positions per iteration would pay a DRAM latency per iteration)
 	uint8_t* sb = seg_s[w] + 16;                                                     // sb[i] = b[j0 + i], sb[-1] = b[j0 - 1]
-	for (uint32_t q = lane * 16; q < SN_SEG; q += 32 * 16) {
-		uint4 v = make_uint4(0u, 0u, 0u, 0u);
-		if (j0 + q + 16 <= n && (reinterpret_cast<uintptr_t>(b + j0 + q) & 15u) == 0u) v = *reinterpret_cast<const uint4*>(b + j0 + q);   // (frames of odd sizes are not 16-byte aligned)
-		else { uint32_t wv[4] = { 0u, 0u, 0u, 0u }; for (int k = 0; k < 16; k++) if (j0 + q + k < n) wv[k >> 2] |= (uint32_t)b[j0 + q + k] << (8 * (k & 3)); v = make_uint4(wv[0], wv[1], wv[2], wv[3]); }
-		*reinterpret_cast<uint4*>(sb + q) = v;
-	}
-	if (lane == 0) sb[-1] = j0 ? b[j0 - 1] : (uint8_t)0;
-	__syncwarp();
 	const uint32_t lt_incl = (2u << lane) - 1u;                                      // lanes <= this one (lane 31: all)
-	for (uint32_t g1 = j1; g1 > j0; ) {                                              // groups of 32 positions, last group first
-		const uint32_t g0 = g1 - j0 > 32u ? g1 - 32u : j0;
-		// group [g0, g1): lane l holds position g0 + l; the first (partial) group of a segment is aligned at its START
-		const uint32_t j = g0 + lane;
-		const bool act = j < g1;
-		const uint32_t am = __ballot_sync(0xffffffffu, act);
-		uint32_t key = 0, val = 0;
-		if (act) { key = sb[(int)(j - j0)]; val = sb[(int)(j - j0) - 1]; }             // position n holds key 0 (staged as 0), b[-1] = 0
-		if (act) {
-			const uint32_t peers = __match_any_sync(am, key);
-			const uint32_t higher = peers & ~lt_incl;
-			const uint32_t partner = higher ? (uint32_t)__ffs((int)higher) - 1u : lane;
-			uint32_t pv = __shfl_sync(am, val, partner);
-			bool has = higher != 0u;
-			if (!has) { const uint32_t t = tab[key]; has = t != SN_NONE; pv = t; if (!has) last[key] = (uint16_t)val; }   // no later position in the segment: its last one
-			const uint32_t hm = __ballot_sync(am, has);
-			if (has) {
-				const uint32_t k2 = (val << 8) | pv;
-				const uint32_t same = __match_any_sync(hm, k2);
-				if (lane == (uint32_t)(__ffs((int)same) - 1)) atomicAdd(&hist[k2], (uint32_t)__popc(same));
-			}
-			__syncwarp(am);
-			if ((peers & (lt_incl >> 1)) == 0u) tab[key] = (uint16_t)val;               // first position of the key in the group: the nearest later one for what comes before
+	for (uint32_t i = threadIdx.x; i < SN_HOT * 256; i += 32 * SN_WARPS) hot[i] = 0;
+	__syncthreads();
+	for (uint32_t seg = blockIdx.x * SN_WARPS + w; seg < nseg; seg += SN_PARTS * SN_WARPS) {
+		uint16_t* first = tabs_all + (size_t)cc * tstride + (size_t)seg * 512, * last = first + 256;
+		for (uint32_t i = lane; i < 256; i += 32) { tab[i] = SN_NONE; last[i] = SN_NONE; }
+		const uint32_t j0 = seg * SN_SEG, j1 = min(n + 1, j0 + SN_SEG);
+		// the segment's bytes once, coalesced (a group of 32 positions per iteration would pay a DRAM latency per iteration)
+		for (uint32_t q = lane * 16; q < SN_SEG; q += 32 * 16) {
+			uint4 v = make_uint4(0u, 0u, 0u, 0u);
+			if (j0 + q + 16 <= n && (reinterpret_cast<uintptr_t>(b + j0 + q) & 15u) == 0u) v = *reinterpret_cast<const uint4*>(b + j0 + q);   // (frames of odd sizes are not 16-byte aligned)
+			else { uint32_t wv[4] = { 0u, 0u, 0u, 0u }; for (int k = 0; k < 16; k++) if (j0 + q + k < n) wv[k >> 2] |= (uint32_t)b[j0 + q + k] << (8 * (k & 3)); v = make_uint4(wv[0], wv[1], wv[2], wv[3]); }
+			*reinterpret_cast<uint4*>(sb + q) = v;
 		}
+		if (lane == 0) sb[-1] = j0 ? b[j0 - 1] : (uint8_t)0;
 		__syncwarp();
-		g1 = g0;
+		for (uint32_t g1 = j1; g1 > j0; ) {                                          // groups of 32 positions, last group first
+			const uint32_t g0 = g1 - j0 > 32u ? g1 - 32u : j0;
+			// group [g0, g1): lane l holds position g0 + l; the first (partial) group of a segment is aligned at its START
+			const uint32_t j = g0 + lane;
+			const bool act = j < g1;
+			const uint32_t am = __ballot_sync(0xffffffffu, act);
+			uint32_t key = 0, val = 0;
+			if (act) { key = sb[(int)(j - j0)]; val = sb[(int)(j - j0) - 1]; }         // position n holds key 0 (staged as 0), b[-1] = 0
+			uint32_t peers = am;                                                     // lanes with the same key: eight ballots
+			#pragma unroll
+			for (int bit = 0; bit < 8; bit++) {
+				const uint32_t bm = __ballot_sync(0xffffffffu, (key >> bit) & 1u);
+				peers &= ((key >> bit) & 1u) ? bm : ~bm;
+			}
+			const uint32_t higher = peers & ~lt_incl;
+			const uint32_t partner = (act && higher) ? (uint32_t)__ffs((int)higher) - 1u : lane;
+			uint32_t pv = __shfl_sync(0xffffffffu, val, partner);
+			if (act) {
+				bool has = higher != 0u;
+				if (!has) { const uint32_t t = tab[key]; has = t != SN_NONE; pv = t; if (!has) last[key] = (uint16_t)val; }   // no later position in the segment: its last one
+				if (has) {
+					if (val < SN_HOT) atomicAdd(&hot[val * 256 + pv], 1u);
+					else atomicAdd(&hist[(val << 8) | pv], 1u);
+				}
+			}
+			__syncwarp();
+			if (act && (peers & (lt_incl >> 1)) == 0u) tab[key] = (uint16_t)val;       // first position of the key in the group: the nearest later one for what comes before
+			__syncwarp();
+			g1 = g0;
+		}
+		for (uint32_t i = lane; i < 256; i += 32) first[i] = tab[i];
+		__syncwarp();
 	}
-	for (uint32_t i = lane; i < 256; i += 32) first[i] = tab[i];
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < SN_HOT * 256; i += 32 * SN_WARPS) { const uint32_t c = hot[i]; if (c) atomicAdd(&hist[i], c); }
 }
 
 __global__ void __launch_bounds__(256)
@@ -256,7 +272,9 @@ void launch_select(const uint16_t* const cand_ptrs[8], int ncand, uint64_t fpx, 
 	const uint32_t max_seg = (chunk_px * 2 + 1 + SN_SEG - 1) / SN_SEG;
 	if (!sorted_path && (size_t)max_seg * 1024 <= (size_t)sstride) {                   // the segment tables live in the (unused) sort buffer
 		const uint32_t tstride = sstride / 2;                                           // uint16 elements per (candidate, chunk)
-		k_select_next<<<dim3((max_seg + SN_WARPS - 1) / SN_WARPS, nchunks, ncand), 32 * SN_WARPS, 0, st>>>(cp, fpx, chunk_px, nchunks, reinterpret_cast<uint16_t*>(sorted), tstride, hist);
+		const size_t sn_smem = (size_t)SN_HOT * 256 * 4 + (size_t)SN_WARPS * 256 * 2 + (size_t)SN_WARPS * (16 + SN_SEG);
+		cudaFuncSetAttribute(k_select_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sn_smem);
+		k_select_next<<<dim3(SN_PARTS, nchunks, ncand), 32 * SN_WARPS, sn_smem, st>>>(cp, fpx, chunk_px, nchunks, reinterpret_cast<uint16_t*>(sorted), tstride, hist);
 		k_select_link<<<ncand * nchunks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(sorted), tstride, fpx, chunk_px, nchunks, hist);
 	} else {
 		k_select_count<<<dim3(SEL_P, nchunks, ncand), BWT_NT, 0, st>>>(cp, fpx, chunk_px, nchunks, scratch);
