@@ -221,25 +221,28 @@ k_select_next(CandPtrs cands, uint64_t fpx, uint32_t chunk_px, uint32_t nchunks,
 	for (uint32_t i = threadIdx.x; i < SN_HOT * 256; i += 32 * SN_WARPS) { const uint32_t c = hot[i]; if (c) atomicAdd(&hist[i], c); }
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int SL_Q = 4;                            // segment ranges per key, chained by different threads
+__global__ void __launch_bounds__(256 * SL_Q)
 k_select_link(const uint16_t* __restrict__ tabs_all, uint32_t tstride, uint64_t fpx, uint32_t chunk_px, uint32_t nchunks,
               uint32_t* __restrict__ hist_all)
 {
+	__shared__ uint16_t first_q[SL_Q][256], last_q[SL_Q][256];
 	__shared__ uint16_t first_all[256], last_all[256];
-	const uint32_t cc = blockIdx.x, chunk = cc % nchunks, c = threadIdx.x;
+	const uint32_t cc = blockIdx.x, chunk = cc % nchunks, c = threadIdx.x & 255u, qd = threadIdx.x >> 8;
 	const uint64_t px0 = (uint64_t)chunk * chunk_px;
 	const uint32_t n = (uint32_t)(min((uint64_t)chunk_px, fpx - px0) * 2);
 	const uint32_t nseg = (n + 1 + SN_SEG - 1) / SN_SEG;
+	const uint32_t per = (nseg + SL_Q - 1) / SL_Q, sA = min(nseg, qd * per), sB = min(nseg, sA + per);
 	const uint16_t* tabs = tabs_all + (size_t)cc * tstride;
 	uint32_t* hist = hist_all + (size_t)cc * 65536;
 	uint32_t carry = SN_NONE, f0 = SN_NONE;
-	for (uint32_t s0 = 0; s0 < nseg; s0 += 16) {                                     // sixteen segments' entries in flight
+	for (uint32_t s0 = sA; s0 < sB; s0 += 16) {                                      // sixteen segments' entries in flight
 		uint32_t f[16], l[16];
 		#pragma unroll
 		for (int k = 0; k < 16; k++) {
 			const uint32_t sg = s0 + k;
-			f[k] = sg < nseg ? tabs[(size_t)sg * 512 + c] : (uint32_t)SN_NONE;
-			l[k] = sg < nseg ? tabs[(size_t)sg * 512 + 256 + c] : (uint32_t)SN_NONE;
+			f[k] = sg < sB ? tabs[(size_t)sg * 512 + c] : (uint32_t)SN_NONE;
+			l[k] = sg < sB ? tabs[(size_t)sg * 512 + 256 + c] : (uint32_t)SN_NONE;
 		}
 		#pragma unroll
 		for (int k = 0; k < 16; k++) if (f[k] != SN_NONE) {
@@ -248,9 +251,23 @@ k_select_link(const uint16_t* __restrict__ tabs_all, uint32_t tstride, uint64_t 
 			carry = l[k];
 		}
 	}
-	first_all[c] = (uint16_t)f0; last_all[c] = (uint16_t)carry;
+	first_q[qd][c] = (uint16_t)f0; last_q[qd][c] = (uint16_t)carry;
 	__syncthreads();
-	if (c == 0) {                                                                    // bucket boundaries
+	if (qd == 0) {                                                                   // the ranges of a key, in order
+		uint32_t cy = SN_NONE, fa = SN_NONE;
+		#pragma unroll
+		for (int q = 0; q < SL_Q; q++) {
+			const uint32_t f = first_q[q][c], l = last_q[q][c];
+			if (f != SN_NONE) {
+				if (cy != SN_NONE) atomicAdd(&hist[(cy << 8) | f], 1u);
+				else fa = f;
+				cy = l;
+			}
+		}
+		first_all[c] = (uint16_t)fa; last_all[c] = (uint16_t)cy;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {                                                          // bucket boundaries
 		uint32_t prev = SN_NONE;
 		for (int k = 0; k < 256; k++) if (first_all[k] != SN_NONE) {
 			if (prev != SN_NONE) atomicAdd(&hist[(prev << 8) | first_all[k]], 1u);
@@ -275,7 +292,7 @@ void launch_select(const uint16_t* const cand_ptrs[8], int ncand, uint64_t fpx, 
 		const size_t sn_smem = (size_t)SN_HOT * 256 * 4 + (size_t)SN_WARPS * 256 * 2 + (size_t)SN_WARPS * (16 + SN_SEG);
 		cudaFuncSetAttribute(k_select_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sn_smem);
 		k_select_next<<<dim3(SN_PARTS, nchunks, ncand), 32 * SN_WARPS, sn_smem, st>>>(cp, fpx, chunk_px, nchunks, reinterpret_cast<uint16_t*>(sorted), tstride, hist);
-		k_select_link<<<ncand * nchunks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(sorted), tstride, fpx, chunk_px, nchunks, hist);
+		k_select_link<<<ncand * nchunks, 256 * SL_Q, 0, st>>>(reinterpret_cast<const uint16_t*>(sorted), tstride, fpx, chunk_px, nchunks, hist);
 	} else {
 		k_select_count<<<dim3(SEL_P, nchunks, ncand), BWT_NT, 0, st>>>(cp, fpx, chunk_px, nchunks, scratch);
 		k_select_starts<<<ncand * nchunks, 256, 0, st>>>(scratch);
