@@ -20,6 +20,7 @@ sharded file is compared (md5) with the file ONE GPU writes for the same stack b
             (test/mainTest_lfmIO.cxx:96-126): N = 1: writeLFMstackEx + readKLBstackInPlace; N > 1: lfmShardCompress + lfmWriteHeader +
             lfmShardWritePayload, then readKLBroiInPlace per rank.  H2D, D2H and file I/O inside the timed region.
   e2e_memory   (N = 1) memory -> memory through lfmCompressToBuffer / lfmDecompressFromMemory with pinned buffers, no file
+  auto_select  (N = 1, workloads with a fixed predictor) the same frames with headerVersion 0: predictor picked by the 2-D entropy rule
   roofline  the kernel with the largest device time of the step (from the per-stage CUDA-event times of the engine stream; every
             stage is ONE kernel launch per step): algorithmic bytes of that kernel's interface per launch / mean
             launch time; peak = MEASURED_PEAKS.json hbm_gbs

@@ -675,12 +675,15 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 		if (ranked) {
 			// ---- write: sublist q starts at output offset n - dist_to_end(q)
 			for (uint32_t q0 = tid; q0 < nspl; q0 += BWT_NT * IB_ILP) {
-				uint32_t p[IB_ILP], off[IB_ILP], end[IB_ILP];
+				// 147 KB blocks: the bytes of a sublist leave as aligned 32-bit words (byte stores only for the ragged first and last word: a
+				// word shared with the neighbouring sublist): a quarter of the store instructions (16-frame slice: 5.43 -> 4.99 ms)
+				uint32_t p[IB_ILP], off[IB_ILP], end[IB_ILP], acc[IB_ILP], beg[IB_ILP];
 				#pragma unroll
 				for (int j = 0; j < IB_ILP; j++) {
 					const uint32_t q = q0 + j * BWT_NT;
-					p[j] = q < S ? (q << kshift) : p0; off[j] = 0; end[j] = 0;
+					p[j] = q < S ? (q << kshift) : p0; off[j] = 0; end[j] = 0; acc[j] = 0;
 					if (q < nspl) { off[j] = n - dfin[q]; end[j] = n; }     // end: upper bound, the walk stops at the next splitter
+					beg[j] = off[j];
 				}
 				bool any = true;
 				while (any) {
@@ -690,9 +693,17 @@ k_inv_bwt(const uint8_t* __restrict__ bwt_all, uint32_t cap, DecJob* __restrict_
 					for (int j = 0; j < IB_ILP; j++) if (off[j] < end[j]) e[j] = tt[p[j]];
 					#pragma unroll
 					for (int j = 0; j < IB_ILP; j++) if (off[j] < end[j]) {
-						txt[off[j]] = (uint8_t)e[j];
-						p[j] = e[j] >> 8; off[j]++;
-						if ((p[j] & (K - 1)) == 0 || p[j] == p0) end[j] = off[j]; else any = true;
+						const uint32_t o = off[j];
+						acc[j] |= (e[j] & 255u) << (8u * (o & 3u));
+						p[j] = e[j] >> 8; off[j] = o + 1;
+						const bool stop = (p[j] & (K - 1)) == 0 || p[j] == p0;
+						if (stop) end[j] = off[j]; else any = true;
+						if (NT != 1024) txt[o] = (uint8_t)e[j];              // small blocks (four CTAs per SM): plain byte stores measured faster
+						else if ((o & 3u) == 3u || stop) {
+							if (o + 1 - beg[j] == 4u) *reinterpret_cast<uint32_t*>(txt + (o & ~3u)) = acc[j];      // slots are 16-byte aligned
+							else for (uint32_t bpos = beg[j]; bpos <= o; bpos++) txt[bpos] = (uint8_t)(acc[j] >> (8u * (bpos & 3u)));
+							acc[j] = 0; beg[j] = o + 1;
+						}
 					}
 				}
 			}
