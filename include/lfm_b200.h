@@ -105,6 +105,9 @@ const char* lfmLastError(void);
    info[8] = { nblock, crc, origPtr, nInUse, nMTF, nGroups, nSelectors, streamBytes } */
 int lfmDebugEncodeBlock(const void* bytes, uint32_t n, uint8_t* rle1, uint8_t* bwt, uint16_t* mtfv, uint8_t* stream, uint32_t info[8]);
 
+/* test hook (no GPU needed): the threaded host copy behind the staging paths (pageable <-> pinned memory, mapped file ranges) */
+int lfmDebugParMemcpy(void* dst, const void* src, uint64_t n);
+
 /* measurement hook: run ONLY the predictor kernels on a device-resident stack, `reps` times back to back, and return
    the mean device time per repetition (CUDA events on the engine stream).  inverse = 0: forward predictor + symbolize
    d_in (pixels) -> d_out (symbols); inverse = 1: unsymbolize + inverse predictor d_in (symbols) -> d_out (pixels).

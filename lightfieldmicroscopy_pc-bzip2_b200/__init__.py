@@ -96,7 +96,7 @@ _libc.free.argtypes = [C.c_void_p]
 EXPORTS = ["writeKLBstack", "writeKLBstackSlices", "readKLBheader", "readKLBstack", "readKLBstackInPlace", "readKLBroiInPlace",
            "lfmSetPredictorWay", "lfmGetPredictorWay", "lfmSetDevices", "writeLFMstackEx", "readLFMheaderEx",
            "lfmCompressToMemory", "lfmCompressToBuffer", "lfmDecompressFromMemory", "lfmCompressDevice", "lfmDecompressDevice", "lfmNumBlocks",
-           "lfmGetLastStats", "lfmLastError", "lfmDebugEncodeBlock", "lfmDebugPredictDevice",
+           "lfmGetLastStats", "lfmLastError", "lfmDebugEncodeBlock", "lfmDebugPredictDevice", "lfmDebugParMemcpy",
            "lfmShardCompress", "lfmShardWritePayload", "lfmShardFetchPayload", "lfmWriteHeader", "lfmSelectDevice"]
 
 

@@ -27,11 +27,13 @@ __device__ const uint16_t kRNums[512] = BZ_RNUMS_INIT;
 //   * decoded symbols (RUNA/RUNB/rank+1/EOB) are gathered 32 at a time and stored coalesced.
 // Inverse move-to-front and run expansion are done in parallel by k_imtf.
 // =====================================================================================================
-constexpr int DEC_LB = 10;                       // lookup bits (9 was measured: 12 KB -> 6 KB per warp, but 16-22 % more time per stream)
-constexpr int DEC_LUT = 1 << DEC_LB;
+// lookup bits of the per-table code table: 10 when every stream is resident at once (a lone stream decodes 16-22 % faster with 10
+// bits: fewer codes take the long-code walk), 9 when the streams outnumber the warp slots that shared memory leaves (12 KB -> 6 KB
+// of tables per warp: 10 -> 15 warps per SM at 147 KB blocks); chosen per launch, launch_decode()
 
-struct DecWarpSmem {
-	uint16_t lut[kGroups][DEC_LUT];              // len | sym << 5   (0: longer than DEC_LB bits)
+template <int DEC_LB>
+struct DecWarpSmemT {
+	uint16_t lut[kGroups][1 << DEC_LB];              // len | sym << 5   (0: longer than DEC_LB bits)
 	int32_t  limit[kGroups][24];
 	int32_t  base[kGroups][24];
 	uint16_t perm[kGroups][kMaxAlpha + 2];
@@ -47,6 +49,7 @@ __host__ __device__ inline size_t dec_sel_bytes(uint32_t selcap) { return (((siz
 
 extern __shared__ __align__(16) uint8_t dec_smem[];
 
+template <int DEC_LB>
 __global__ void __launch_bounds__(256)
 k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ begin, const uint64_t* __restrict__ end,
               uint32_t njobs, DecJob* __restrict__ jobs, uint16_t* __restrict__ mtfv_all, uint32_t mcap, uint32_t cap,
@@ -55,6 +58,8 @@ k_huff_decode(const uint8_t* __restrict__ payload, const uint64_t* __restrict__ 
 	const uint32_t lane = lane_id(), w = warp_id(), nw = blockDim.x >> 5;
 	const uint32_t job = blockIdx.x * nw + w;
 	if (job >= njobs) return;
+	using DecWarpSmem = DecWarpSmemT<DEC_LB>;
+	constexpr int DEC_LUT = 1 << DEC_LB;
 	const size_t per_warp = sizeof(DecWarpSmem) + dec_sel_bytes(selcap) + (size_t)DEC_RING * 4 + (size_t)DEC_OUT * 2;
 	DecWarpSmem& S = *reinterpret_cast<DecWarpSmem*>(dec_smem + (size_t)w * per_warp);
 	uint8_t* selector = dec_smem + (size_t)w * per_warp + sizeof(DecWarpSmem);
@@ -941,19 +946,32 @@ int launch_decode(const uint8_t* payload, const uint64_t* begin, const uint64_t*
                   uint16_t* mtfv, uint32_t mcap, uint8_t* q_scratch, uint8_t* bwt, uint32_t cap, uint32_t selcap, cudaStream_t st,
                   cudaEvent_t between)
 {
-	const size_t per_warp = sizeof(DecWarpSmem) + dec_sel_bytes(selcap) + (size_t)DEC_RING * 4 + (size_t)DEC_OUT * 2;
-	// warps per CTA: whatever puts the most streams on an SM (227 KB of shared memory, 1 KB reserved per CTA)
-	int nw = 0; size_t best = 0;
-	for (int c = 1; c <= 8; c++) {
-		const size_t cta = per_warp * c + 1024;
-		if (cta > 200 * 1024) break;
-		const size_t warps = std::min<size_t>(32, (227 * 1024) / cta) * c;
-		if (warps >= best) { best = warps; nw = c; }
-	}
+	static const int lb_forced = getenv("LFM_B200_DEC_LB") ? atoi(getenv("LFM_B200_DEC_LB")) : 0;
+	int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	auto plan = [&](size_t table_bytes, int& nw, size_t& per_warp) -> size_t {      // warps per CTA for the most streams per SM; returns streams per SM
+		per_warp = table_bytes + dec_sel_bytes(selcap) + (size_t)DEC_RING * 4 + (size_t)DEC_OUT * 2;
+		nw = 0; size_t best = 0;
+		for (int c = 1; c <= 8; c++) {
+			const size_t cta = per_warp * c + 1024;                                    // 227 KB of shared memory, 1 KB reserved per CTA
+			if (cta > 200 * 1024) break;
+			const size_t warps = std::min<size_t>(32, (227 * 1024) / cta) * c;
+			if (warps >= best) { best = warps; nw = c; }
+		}
+		return best;
+	};
+	int nw = 0; size_t per_warp = 0;
+	const size_t resident10 = plan(sizeof(DecWarpSmemT<10>), nw, per_warp) * (size_t)sms;
+	const bool nine = lb_forced == 9 || (lb_forced != 10 && (size_t)njobs > resident10);
+	if (nine) plan(sizeof(DecWarpSmemT<9>), nw, per_warp);
 	if (nw < 1) return 1;
 	const size_t smem = per_warp * nw;
-	cudaFuncSetAttribute(k_huff_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	k_huff_decode<<<(njobs + nw - 1) / nw, nw * 32, smem, st>>>(payload, begin, end, njobs, jobs, mtfv, mcap, cap, selcap, nsub);
+	if (nine) {
+		cudaFuncSetAttribute(k_huff_decode<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		k_huff_decode<9><<<(njobs + nw - 1) / nw, nw * 32, smem, st>>>(payload, begin, end, njobs, jobs, mtfv, mcap, cap, selcap, nsub);
+	} else {
+		cudaFuncSetAttribute(k_huff_decode<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		k_huff_decode<10><<<(njobs + nw - 1) / nw, nw * 32, smem, st>>>(payload, begin, end, njobs, jobs, mtfv, mcap, cap, selcap, nsub);
+	}
 	if (between) cudaEventRecord(between, st);               // stage timing: Huffman decode | inverse MTF
 	const size_t smem2 = imtf_smem_bytes();
 	cudaFuncSetAttribute(k_imtf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);

@@ -682,23 +682,19 @@ __device__ __forceinline__ bool hp_build_tree32(uint32_t* heap, uint16_t* parent
 				const uint4 g = *reinterpret_cast<const uint4*>(heap + min(4 * z, SLOTS - 4));
 				const uint4 qa = *reinterpret_cast<const uint4*>(heap + min(8 * z, SLOTS - 4));
 				const uint4 qb = *reinterpret_cast<const uint4*>(heap + min(8 * z + 4, SLOTS - 4));
-				// the lane waits ~20 cycles for every dependent instruction, so whatever does not need the outcome of the first level
-				// is computed for BOTH children before it is known: smaller grandchild, stop test and next pair under either child
 				const bool r1 = (ch.y >> 10) < (ch.x >> 10);
 				const uint32_t c1 = r1 ? ch.y : ch.x;
-				const bool r2a = (g.y >> 10) < (g.x >> 10), r2b = (g.w >> 10) < (g.z >> 10);
-				const uint32_t c2a = r2a ? g.y : g.x, c2b = r2b ? g.w : g.z;
-				const bool s2a = tw < (c2a >> 10), s2b = tw < (c2b >> 10);
-				const uint32_t chax = r2a ? qa.z : qa.x, chay = r2a ? qa.w : qa.y, chbx = r2b ? qb.z : qb.x, chby = r2b ? qb.w : qb.y;
 				going = going & !(tw < (c1 >> 10));
 				if (going) heap[z] = c1;
 				z = going ? 2 * z + (r1 ? 1 : 0) : z;
-				const bool r2 = r1 ? r2b : r2a;
-				const uint32_t c2 = r1 ? c2b : c2a;
-				going = going & !(r1 ? s2b : s2a);
+				const uint32_t a0 = r1 ? g.z : g.x, a1 = r1 ? g.w : g.y;
+				const bool r2 = (a1 >> 10) < (a0 >> 10);
+				const uint32_t c2 = r2 ? a1 : a0;
+				going = going & !(tw < (c2 >> 10));
 				if (going) heap[z] = c2;
 				z = going ? 2 * z + (r2 ? 1 : 0) : z;
-				ch.x = r1 ? chbx : chax; ch.y = r1 ? chby : chay;
+				const uint4 qq = r1 ? qb : qa;
+				ch.x = r2 ? qq.z : qq.x; ch.y = r2 ? qq.w : qq.y;
 			}
 			if (n_heap >= 1) heap[z] = tmp;
 		}

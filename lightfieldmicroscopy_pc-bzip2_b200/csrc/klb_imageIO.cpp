@@ -184,7 +184,11 @@ public:
 	template <class F> void run(int parts, F f)
 	{
 		std::unique_lock<std::mutex> lk(mu_);
-		caller_.wait(lk, [&] { return pending_ == 0 && next_ >= nparts_; });     // one batch at a time
+		// one batch at a time.  The pool is busy until its caller has finished part 0 as well: "no part pending" alone would let a
+		// second caller (the upload, download and file threads of the slab pipelines run side by side) install its batch while
+		// the first one is still inside f(0), and the first caller's clean-up would then drop parts of the second batch
+		caller_.wait(lk, [&] { return !busy_; });
+		busy_ = true;
 		task_ = [&f](int i) { f(i); };
 		nparts_ = parts; next_ = 1; pending_ = parts - 1;
 		lk.unlock();
@@ -192,7 +196,7 @@ public:
 		f(0);
 		lk.lock();
 		caller_.wait(lk, [&] { return pending_ == 0; });
-		nparts_ = 0; next_ = 0;
+		nparts_ = 0; next_ = 0; busy_ = false;
 		lk.unlock();
 		caller_.notify_all();
 	}
@@ -214,12 +218,13 @@ private:
 	std::condition_variable work_, caller_;
 	std::function<void(int)> task_;
 	int nparts_ = 0, next_ = 0, pending_ = 0;
+	bool busy_ = false;
 };
 void par_memcpy(void* dst, const void* src, size_t n)
 {
 	const int nt = CopyPool::workers() + 1;
 	if (n < ((size_t)512 << 10)) { memcpy(dst, src, n); return; }
-	const size_t part = (n / nt + 63) & ~(size_t)63;
+	const size_t part = ((n + nt - 1) / nt + 63) & ~(size_t)63;          // ceil: floor(n / nt) rounded to 64 can leave the last n mod nt bytes uncopied
 	CopyPool::get().run(nt, [=](int i) {
 		const size_t o = std::min(n, part * (size_t)i), len = std::min(n, part * (size_t)(i + 1)) - o;
 		if (len) memcpy((uint8_t*)dst + o, (const uint8_t*)src + o, len);
@@ -1317,6 +1322,9 @@ try {
 	if (close(fd) != 0 && rc == 0) rc = LFM_ERR_CREATE;
 	return rc;
 } LFM_CATCH
+
+/* test hook (no GPU needed): the threaded host copy the staging paths use (pageable <-> pinned memory, mapped file ranges) */
+int lfmDebugParMemcpy(void* dst, const void* src, uint64_t n) { if (!dst || !src) return 1; par_memcpy(dst, src, (size_t)n); return 0; }
 
 int lfmGetLastStats(lfm_stats* out) { if (!out) return 1; *out = g_stats; return 0; }
 const char* lfmLastError(void) { return g_err.c_str(); }

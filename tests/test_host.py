@@ -35,6 +35,23 @@ def test_library_exports_every_declared_symbol(L):
     assert set(L.EXPORTS) <= set(names)
 
 
+def test_threaded_host_copy_copies_every_byte(L):
+    """the staging copies split a buffer over the copy pool in 64-byte aligned parts: every length must arrive whole (a length whose
+    per-thread share is a multiple of 64 once lost its last n mod threads bytes: the tail of a 241 MB payload, found at configs[4])"""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 256, (3 << 20) + 4096, dtype=np.uint8)
+    dst = np.zeros_like(src)
+    threads = [2, 3, 4, 5, 6, 7, 8]
+    sizes = {(1 << 20) + k for k in range(0, 9)} | {512 * 1024, 512 * 1024 + 1, (3 << 20) + 77}
+    sizes |= {64 * t * m + r for t in threads for m in (4096, 4097) for r in range(1, t)}     # floor(n / t) a multiple of 64, n mod t != 0
+    for n in sorted(sizes):
+        dst[:] = 0
+        assert L.lib.lfmDebugParMemcpy(C.c_void_p(dst.ctypes.data), C.c_void_p(src.ctypes.data), C.c_uint64(n)) == 0
+        assert np.array_equal(dst[:n], src[:n]), "par_memcpy dropped bytes at n=%d" % n
+        assert not dst[n:n + 64].any()
+
+
 def test_way_setter(L):
     prev = L.lib.lfmGetPredictorWay()
     assert L.lib.lfmSetPredictorWay(2) == prev and L.lib.lfmGetPredictorWay() == 2
