@@ -20,11 +20,12 @@ __device__ const uint16_t kRNums[512] = BZ_RNUMS_INIT;
 
 // =====================================================================================================
 // k_huff_decode : one warp per KLB block stream -- ONLY the inherently sequential part.
-//   * the compressed stream is staged once into shared memory as big-endian words (coalesced copy by the warp);
+//   * the compressed stream is staged through a shared-memory ring of big-endian words (coalesced copies by the warp);
 //   * every lane runs the same (uniform) parser, so nothing has to be broadcast;
 //   * a 64-bit bit buffer lives in registers; symbols of <= DEC_LB bits come out of a per-table lookup (one shared
 //     load per symbol on the critical path); longer ones use bzip2's limit/base/perm walk (decompress.c GET_MTF_VAL);
-//   * decoded symbols (RUNA/RUNB/rank+1/EOB) are gathered 32 at a time and stored coalesced.
+//   * a group of 50 symbols (RUNA/RUNB/rank+1/EOB) is decoded straight through -- three symbols per refill, no branch per
+//     symbol -- staged in shared memory and stored with two coalesced stores (details at the symbol loop below).
 // Inverse move-to-front and run expansion are done in parallel by k_imtf.
 // =====================================================================================================
 // lookup bits of the per-table code table: 10 when every stream is resident at once (a lone stream decodes 16-22 % faster with 10
