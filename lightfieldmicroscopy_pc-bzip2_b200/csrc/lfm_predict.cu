@@ -420,7 +420,27 @@ k_unpredict_seed(const uint16_t* __restrict__ sym, uint16_t* out, int W, int H, 
 		auto px = [&](int dx, int dy) { return (int)__ldcg(o + (size_t)(y + dy) * W + (x + dx)); };
 		o[(size_t)y * W + x] = (uint16_t)(unsymbolize16(__ldg(s + (size_t)y * W + x)) + predict0(px, T, way, k, tx, ty, u, v));
 	};
-	if (mode == 0) {
+	if (mode == 0 && T <= 32) {
+		// the tile stays in shared memory while its anti-diagonals are decoded (a step through global memory is an L2 round trip:
+		// 29 steps = 22 us for a 15 x 15 tile, more than the two scan passes of a whole 2048^2 frame); the rule of tile (0,0) only
+		// looks at its own left / upper pixels, a zero frame stands in for what lies outside the image
+		__shared__ uint16_t tile_s[UF_NT / 32][34 * 34];
+		uint16_t* tl = tile_s[warp_id()];
+		const int tw = min(T, W), th = min(T, H);
+		for (int i = (int)lane; i < 34 * 34; i += 32) tl[i] = 0;
+		__syncwarp();
+		for (int d = 0; d <= tw + th - 2; d++) {             // pixel anti-diagonals of the first tile
+			for (int u = (int)lane; u <= d; u += 32) {
+				const int v = d - u;
+				if (u < tw && v < th) {
+					auto px = [&](int dx, int dy) { return (int)tl[(v + dy + 1) * 34 + (u + dx + 1)]; };
+					tl[(v + 1) * 34 + u + 1] = (uint16_t)(unsymbolize16(__ldg(s + (size_t)v * W + u)) + predict0(px, T, way, k, 0, 0, u, v));
+				}
+			}
+			__syncwarp();
+		}
+		for (int i = (int)lane; i < tw * th; i += 32) { const int v = i / tw, u = i - v * tw; o[(size_t)v * W + u] = tl[(v + 1) * 34 + u + 1]; }
+	} else if (mode == 0) {
 		const int tw = min(T, W), th = min(T, H);
 		for (int d = 0; d <= tw + th - 2; d++) {             // pixel anti-diagonals of the first tile
 			for (int u = (int)lane; u <= d; u += 32) { int v = d - u; if (u < tw && v < th) decode_px(u, v, 0, 0, u, v); }

@@ -148,12 +148,12 @@ constexpr int SN_PARTS = 8;                       // CTAs per (candidate, chunk)
 constexpr uint32_t SN_HOT = 32;                   // pairs whose first byte is below this are counted in shared memory
 constexpr uint16_t SN_NONE = 0xFFFFu;
 // ncu of the first version (one match.any for the key, one to aggregate equal pairs before the global atomic): MIO bound, 24 % of
-// the issue slots.  Now the key peers come from eight ballots, and the pairs whose first byte is small -- high bytes and small
+// the issue slots.  Now ONE match.any (the key peers; eight ballots were measured slower), and the pairs whose first byte is small -- high bytes and small
 // residuals: most of them, and the ones that would contend for the same global counter -- go to a 32 x 256 shared-memory
 // histogram that the CTA adds to the global one once, after ~55 segments; the others are spread over 57 K counters.
 __global__ void __launch_bounds__(32 * SN_WARPS)
 k_select_next(CandPtrs cands, uint64_t fpx, uint32_t chunk_px, uint32_t nchunks, uint16_t* __restrict__ tabs_all, uint32_t tstride,
-              uint32_t* __restrict__ hist_all)
+              uint32_t* __restrict__ hist_all, int use_match)
 {
 	extern __shared__ __align__(16) uint8_t sn_smem[];
 	uint32_t* hot = reinterpret_cast<uint32_t*>(sn_smem);                            // [SN_HOT][256]
@@ -192,11 +192,14 @@ k_select_next(CandPtrs cands, uint64_t fpx, uint32_t chunk_px, uint32_t nchunks,
 			const uint32_t am = __ballot_sync(0xffffffffu, act);
 			uint32_t key = 0, val = 0;
 			if (act) { key = sb[(int)(j - j0)]; val = sb[(int)(j - j0) - 1]; }         // position n holds key 0 (staged as 0), b[-1] = 0
-			uint32_t peers = am;                                                     // lanes with the same key: eight ballots
-			#pragma unroll
-			for (int bit = 0; bit < 8; bit++) {
-				const uint32_t bm = __ballot_sync(0xffffffffu, (key >> bit) & 1u);
-				peers &= ((key >> bit) & 1u) ? bm : ~bm;
+			uint32_t peers = am;                                                     // lanes with the same key
+			if (use_match) peers = __match_any_sync(0xffffffffu, act ? key : 256u) & am;
+			else {
+				#pragma unroll
+				for (int bit = 0; bit < 8; bit++) {
+					const uint32_t bm = __ballot_sync(0xffffffffu, (key >> bit) & 1u);
+					peers &= ((key >> bit) & 1u) ? bm : ~bm;
+				}
 			}
 			const uint32_t higher = peers & ~lt_incl;
 			const uint32_t partner = (act && higher) ? (uint32_t)__ffs((int)higher) - 1u : lane;
@@ -289,9 +292,10 @@ void launch_select(const uint16_t* const cand_ptrs[8], int ncand, uint64_t fpx, 
 	const uint32_t max_seg = (chunk_px * 2 + 1 + SN_SEG - 1) / SN_SEG;
 	if (!sorted_path && (size_t)max_seg * 1024 <= (size_t)sstride) {                   // the segment tables live in the (unused) sort buffer
 		const uint32_t tstride = sstride / 2;                                           // uint16 elements per (candidate, chunk)
+		static const int use_match = getenv("LFM_B200_SELECT_MATCH") ? atoi(getenv("LFM_B200_SELECT_MATCH")) : 1;      // 0: eight ballots instead of one match.any (measured 0.78 against 0.70 ms)
 		const size_t sn_smem = (size_t)SN_HOT * 256 * 4 + (size_t)SN_WARPS * 256 * 2 + (size_t)SN_WARPS * (16 + SN_SEG);
 		cudaFuncSetAttribute(k_select_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sn_smem);
-		k_select_next<<<dim3(SN_PARTS, nchunks, ncand), 32 * SN_WARPS, sn_smem, st>>>(cp, fpx, chunk_px, nchunks, reinterpret_cast<uint16_t*>(sorted), tstride, hist);
+		k_select_next<<<dim3(SN_PARTS, nchunks, ncand), 32 * SN_WARPS, sn_smem, st>>>(cp, fpx, chunk_px, nchunks, reinterpret_cast<uint16_t*>(sorted), tstride, hist, use_match);
 		k_select_link<<<ncand * nchunks, 256 * SL_Q, 0, st>>>(reinterpret_cast<const uint16_t*>(sorted), tstride, fpx, chunk_px, nchunks, hist);
 	} else {
 		k_select_count<<<dim3(SEL_P, nchunks, ncand), BWT_NT, 0, st>>>(cp, fpx, chunk_px, nchunks, scratch);
